@@ -1,0 +1,9 @@
+"""Shim of diffusers.loaders: empty mixins (LoRA / attn-proc loading is not on the path)."""
+
+
+class UNet2DConditionLoadersMixin:
+    pass
+
+
+class LoraLoaderMixin:
+    pass

@@ -1,0 +1,72 @@
+"""ORACLE (test infrastructure only) — CPU restatement of the stage-2 pipeline's conditioning set-up and
+denoising loop, /root/reference/src/pipelines/stage2_inpaint_pipeline.py:420-525.
+
+Out of scope here exactly as in SURVEY.md §8: the VAE encode (:443) and decode (:528) — callers hand in
+`masked_latents` (already multiplied by the VAE scaling factor) and receive the final latents.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def prepare_conditioning(*, s_img_proj_f, pred_t_img_embed, st_pose_f, masked_latents, height, width,
+                         num_images_per_prompt=1, guidance_scale=2.0, mask=None, dtype=torch.float32):
+    """ref :427-466.  Returns dict(pose_cond, mask, masked_latents, feature_f, prior_embed) with the CFG batch layout
+    [uncond ; cond].  Quirk kept: only the tokens and the class embedding are zeroed for the unconditional half;
+    pose, mask and masked latents are NOT dropped (:455-462)."""
+    bs = s_img_proj_f.shape[0]
+    cfg = guidance_scale > 1.0
+    rep = 2 * num_images_per_prompt if cfg else 1
+    pose_cond = torch.cat([st_pose_f] * rep).to(dtype)                                   # :430-431
+    if mask is None:                                                                      # :434-437
+        mask1 = torch.ones((bs, 1, int(height / 8), int(width / 16)), dtype=torch.float32)
+        mask0 = torch.zeros((bs, 1, int(height / 8), int(width / 16)), dtype=torch.float32)
+        mask = torch.cat([mask1, mask0], dim=3)
+    mask = torch.cat([mask] * rep).to(dtype)                                              # :438-440
+    masked_latents = torch.cat([masked_latents] * rep).to(dtype)                          # :445
+    feature_f = torch.cat([s_img_proj_f, pred_t_img_embed], dim=1)                        # :448
+    feature_f = feature_f.repeat(bs * num_images_per_prompt, 1, 1).to(dtype)              # :449
+    prior_embed = pred_t_img_embed.repeat(bs * num_images_per_prompt, 1, 1).to(dtype)     # :452
+    if cfg:                                                                               # :455-462
+        feature_f = torch.cat([torch.zeros_like(feature_f), feature_f], dim=0)
+        prior_embed = torch.cat([torch.zeros_like(prior_embed), prior_embed], dim=0)
+    else:
+        raise NotImplementedError("reference's non-CFG branch repeats feature_f twice (:465, a latent bug); "
+                                  "the drivers always run guidance_scale=2")
+    return dict(pose_cond=pose_cond, mask=mask, masked_latents=masked_latents, feature_f=feature_f,
+                prior_embed=prior_embed)
+
+
+def cfg_combine(noise_pred, guidance_scale):
+    """ref :510-512"""
+    u, c = noise_pred.chunk(2)
+    return u + guidance_scale * (c - u)
+
+
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """ref :52-63 (disabled by the drivers: guidance_rescale = 0.0)"""
+    std_text = noise_pred_text.std(dim=list(range(1, noise_pred_text.ndim)), keepdim=True)
+    std_cfg = noise_cfg.std(dim=list(range(1, noise_cfg.ndim)), keepdim=True)
+    rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
+
+
+@torch.no_grad()
+def denoise_loop(unet, scheduler, *, latents, cond, num_inference_steps, guidance_scale=2.0, dtype=torch.float32,
+                 return_trajectory=False):
+    """ref :472-520.  `latents`: [n, 4, h, w] initial noise (already times init_noise_sigma); `cond` from
+    prepare_conditioning.  Returns the final latents (and, optionally, the per-step (eps, latents) list)."""
+    scheduler.set_timesteps(num_inference_steps)
+    latents = latents.to(dtype)
+    traj = []
+    for t in scheduler.timesteps:
+        x = torch.cat([latents] * 2)                                                      # :499
+        x = scheduler.scale_model_input(x, t)                                             # :500
+        x9 = torch.cat([x, cond["mask"], cond["masked_latents"]], dim=1).to(dtype)       # :501
+        eps = unet(x9, t, class_labels=cond["prior_embed"], encoder_hidden_states=cond["feature_f"],
+                   my_pose_cond=cond["pose_cond"], return_dict=False)[0]                  # :504-506
+        eps = cfg_combine(eps, guidance_scale)                                            # :510-512
+        latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :519
+        if return_trajectory:
+            traj.append((eps.clone(), latents.clone()))
+    return (latents, traj) if return_trajectory else latents

@@ -1,0 +1,424 @@
+// K1/K2 — implicit-GEMM convolution (3x3, stride 1/2, im2col-free) and linear GEMM on tcgen05 tensor cores.
+//
+//   D[M, N] = A[M, K] . W[N, K]^T  (+bias[N]) (+rowvec[image(m), N]) (+residual[M, N])   or GEGLU pairing
+//
+// * A is never materialised as an im2col matrix: activations are NHWC and every (tap, 64-channel) K-block of an
+//   output tile is ONE 4-D TMA box load (64 ch x W x tile_h x tile_b) whose start coordinate carries the tap offset;
+//   TMA's out-of-bounds zero fill IS the conv padding.  Stride-2 convs read through four "parity" tensor maps laid
+//   over the same NHWC buffer (element strides doubled), so they use the identical box loads.
+// * A 128 x BN fp32 accumulator lives in TMEM (double-buffered: the epilogue of tile i overlaps the MMAs of tile
+//   i+1); one elected thread issues tcgen05.mma (M=128, N=BN, K=16) from 128B-swizzled shared-memory operands.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+//   (tcgen05.ld -> fp32 math -> 16-bit stores).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+//
+// Replaces, on the reference path, torch.nn.Conv2d / torch.nn.Linear as called from diffusers' ResnetBlock2D,
+// Downsample2D/Upsample2D, Transformer2DModel and BasicTransformerBlock (reference call
+// sites src/models/stage2_inpaint_unet_2d_condition.py:321-343,348-361,407-429).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace pcdm {
+
+struct IGemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  int M, N;
+  int num_kb;      // K / 64
+  int m_tiles, n_tiles;
+  int mode;        // 0 = plain GEMM (A row-major [M, K], up to two K-segments), 1 = conv3x3 s1, 2 = conv3x3 s2
+  int H, W;        // conv: output height / width
+  int cblocks;     // conv: Cin / 64
+  int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
+  uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
+  const float* bias;
+  const float* rowvec;
+  int hw;          // rows per image for rowvec indexing
+  const void* residual;
+  long long ldr;
+  void* out;
+  long long ldo;
+  int geglu;
+  int out_f32;
+};
+
+template <int BN>
+struct IGemmCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int DT>
+__global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ IGemmParams p) {
+  using Cfg = IGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int hw = p.H * p.W;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int m0 = m_blk * 128;
+      int b0 = 0, y0 = 0;
+      if (p.mode != 0) {
+        b0 = m0 / hw;
+        y0 = (m0 - b0 * hw) / p.W;
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+        if (p.mode == 0) {
+          if (kb < p.kb_split) tma_load_2d(sa, &p.tmA[0], &full[stage], kb * 64, m0);
+          else tma_load_2d(sa, &p.tmA[1], &full[stage], (kb - p.kb_split) * 64, m0);
+        } else {
+          const int r = tap / 3, s = tap - r * 3;
+          if (p.mode == 1) {
+            tma_load_4d(sa, &p.tmA[0], &full[stage], cb * 64, s - 1, y0 + r - 1, b0);
+          } else {
+            // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
+            const int py = (r != 1), px = (s != 1);
+            tma_load_4d(sa, &p.tmA[py * 2 + px], &full[stage], cb * 64, (s == 0) ? -1 : 0, y0 + ((r == 0) ? -1 : 0),
+                        b0);
+          }
+          if (++cb == p.cblocks) { cb = 0; ++tap; }
+        }
+        tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(DT, 128, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_ss(d_tmem, make_desc_sw128(a_addr + k * 32, 1024, 16), make_desc_sw128(b_addr + k * 32, 1024, 16), idesc,
+                  (kb | k) != 0);
+        }
+        tc_commit(&empty[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    using T = typename TypeOf<DT>::T;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const long long m = (long long)m_blk * 128 + row;
+      const bool valid = m < p.M;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      const float* rv = (p.rowvec && valid) ? p.rowvec + (long long)(m / p.hw) * p.N : nullptr;
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tc_wait_ld();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (rv) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = __ldg(rp + j);
+                float2 f;
+                f = unpack2<DT>(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
+                f = unpack2<DT>(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
+                f = unpack2<DT>(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
+                f = unpack2<DT>(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + m * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
+                u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
+                u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
+                u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
+                op[j] = u;
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate)
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int n0 = n_blk * BN + c * 64;
+          if (n0 >= p.N) break;
+          uint32_t rh[32], rg[32];
+          tmem_ld32(t_row + c * 64, rh);
+          tmem_ld32(t_row + c * 64 + 32, rg);
+          tc_wait_ld();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float h = __uint_as_float(rh[j]), g = __uint_as_float(rg[j]);
+              if (p.bias) { h += __ldg(p.bias + n0 + j); g += __ldg(p.bias + n0 + 32 + j); }
+              v[j] = h * gelu_erf_f(g);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + m * p.ldo + (n0 >> 1));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
+              u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
+              u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
+              u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
+              op[j] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int DT>
+static int launch_igemm(const IGemmParams& p, cudaStream_t stream) {
+  using Cfg = IGemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  igemm_kernel<BN, DT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int pick_bn(int m_tiles, int N, int geglu) {
+  // minimise (waves x per-tile cost); small-N tiles are shared-memory-bandwidth bound on a single CTA
+  const int cand[4] = {256, 160, 128, 64};
+  const float eff[4] = {1.0f, 1.0f, 1.05f, 1.5f};
+  int best = 128;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (geglu && (bn % 64)) continue;
+    if (bn == 160 && (N % 160)) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * n_tiles;
+    const long long waves = (tiles + num_sms() - 1) / num_sms();
+    const float cost = (float)waves * bn * eff[i];
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, cudaStream_t stream) {
+  if (bn == 0) bn = pick_bn(p.m_tiles, p.N, p.geglu);
+  p.n_tiles = (p.N + bn - 1) / bn;
+  const int brows = p.N < bn ? p.N : bn;
+  p.b_bytes = (uint32_t)brows * 128u;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)p.N};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {64, (uint32_t)brows};
+    PCDM_CHECK(make_tmap(&p.tmB, w, 2, dims, strides, box), "weight tensor map");
+  }
+#define PCDM_LAUNCH(BN_)                                                      \
+  (dt == DT_F16 ? launch_igemm<BN_, DT_F16>(p, stream) : launch_igemm<BN_, DT_BF16>(p, stream))
+  switch (bn) {
+    case 64: return PCDM_LAUNCH(64);
+    case 128: return PCDM_LAUNCH(128);
+    case 160: return PCDM_LAUNCH(160);
+    case 256: return PCDM_LAUNCH(256);
+    default: return set_error(PCDM_ERR_INVALID, "igemm: BN must be 0, 64, 128, 160 or 256");
+  }
+#undef PCDM_LAUNCH
+}
+
+}  // namespace pcdm
+
+using namespace pcdm;
+
+extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w,
+                         void* out, long long ldo, const float* bias, const float* rowvec, int rows_per_image,
+                         const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
+                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !w || !out) return set_error(PCDM_ERR_INVALID, "gemm: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "gemm: dtype must be 0 (f16) or 1 (bf16)");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(PCDM_ERR_INVALID, "gemm: empty problem");
+  if (K % 64 || N % 32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: K must be a multiple of 64 and N of 32");
+  if (a2 && (k1 % 64 || k1 <= 0 || k1 >= K)) return set_error(PCDM_ERR_INVALID, "gemm: bad K split");
+  const bool geglu = flags & PCDM_FLAG_GEGLU;
+  if (geglu && (N % 64)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU needs N % 64 == 0");
+  if ((lda % 8) || (ldo % 8) || (residual && (ldr % 8))) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: strides must be multiples of 8");
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.num_kb = K / 64;
+  p.m_tiles = (M + 127) / 128;
+  p.mode = 0;
+  p.H = 1; p.W = 1;
+  p.kb_split = a2 ? k1 / 64 : p.num_kb;
+  const int arows = M < 128 ? M : 128;
+  p.a_bytes = (uint32_t)arows * 128u;
+  {
+    const int ka = a2 ? k1 : K;
+    const uint64_t dims[2] = {(uint64_t)ka, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {64, (uint32_t)arows};
+    PCDM_CHECK(make_tmap(&p.tmA[0], a, 2, dims, strides, box), "A tensor map");
+    if (a2) {
+      const uint64_t dims2[2] = {(uint64_t)(K - k1), (uint64_t)M};
+      const uint64_t strides2[1] = {(uint64_t)lda2 * 2};
+      PCDM_CHECK(make_tmap(&p.tmA[1], a2, 2, dims2, strides2, box), "A2 tensor map");
+    }
+  }
+  p.bias = bias; p.rowvec = rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
+  p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
+  p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0;
+  if (p.geglu && p.out_f32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU with fp32 output");
+  return dispatch_igemm(p, dtype, bn, w, K, stream);
+}
+
+extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
+                            const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype,
+                            int flags, int bn, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || !w_packed || !out) return set_error(PCDM_ERR_INVALID, "conv3x3: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "conv3x3: dtype must be 0 (f16) or 1 (bf16)");
+  if (stride != 1 && stride != 2) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: stride must be 1 or 2");
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(PCDM_ERR_INVALID, "conv3x3: empty problem");
+  if (Cin % 64 || Cout % 32) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: Cin must be a multiple of 64 and Cout of 32");
+  // output tile = 128 consecutive NHWC pixels = tile_b images x tile_h rows x W columns
+  if (W > 128 || (128 % W)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: output width must divide 128");
+  const int hw = H * W;
+  int tile_h, tile_b;
+  if (hw >= 128) {
+    if (hw % 128) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: H*W must be a multiple of 128 (or divide it)");
+    tile_h = 128 / W; tile_b = 1;
+  } else {
+    if (128 % hw) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: H*W must divide 128");
+    tile_h = H; tile_b = 128 / hw;
+  }
+  if (tile_b > B) tile_b = B;
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = B * hw; p.N = Cout; p.num_kb = 9 * (Cin / 64);
+  p.m_tiles = (p.M + 127) / 128;
+  p.mode = stride; p.H = H; p.W = W; p.cblocks = Cin / 64; p.kb_split = p.num_kb;
+  p.a_bytes = 128u * (uint32_t)(W * tile_h * tile_b);
+  const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)tile_h, (uint32_t)tile_b};
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)hw * Cin * 2};
+    PCDM_CHECK(make_tmap(&p.tmA[0], x, 4, dims, strides, box), "conv input tensor map");
+  } else {
+    const int Hin = 2 * H, Win = 2 * W;
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const char* base = reinterpret_cast<const char*>(x) + ((size_t)py * Win + px) * Cin * 2;
+        PCDM_CHECK(make_tmap(&p.tmA[py * 2 + px], base, 4, dims, strides, box), "conv parity tensor map");
+      }
+  }
+  p.bias = bias; p.rowvec = rowvec; p.hw = hw;
+  p.residual = residual; p.ldr = Cout; p.out = out; p.ldo = Cout;
+  p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0;
+  return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, stream);
+}
