@@ -41,21 +41,76 @@ const char* pcdm_last_error(void);
 /* torch.nn.Linear (+ fused epilogues).  Replaces the nn.Linear calls inside diffusers Transformer2DModel /
  * BasicTransformerBlock / Attention / GEGLU / TimestepEmbedding and the 1x1 conv_shortcut of ResnetBlock2D
  * (SURVEY.md §8a rows a3, a5, a7, a8).
- *   out[M, N] = A[M, K] . W[N, K]^T + bias[N] + rowvec[m / rows_per_image, N] + residual[M, N]
+ *   out[M, N] = act( A[M, K] . W[N, K]^T + bias[N] + rowvec[m / rows_per_image, :] + residual[M, N] )
  * A may be given as two K-segments (a: columns [0, k1), a2: columns [k1, K)) — the skip-concat of the up blocks
- * is consumed in place, never materialised.  lda/lda2/ldo/ldr are row strides in elements.
+ * is consumed in place, never materialised.  lda/lda2/ldo/ldr/ld_rowvec are row strides in elements.
+ * flags: PCDM_FLAG_GEGLU | PCDM_FLAG_OUT_F32 | PCDM_FLAG_SILU (act = SiLU, else identity).
  * K % 64 == 0, N % 32 == 0.  bn = 0 picks the N tile automatically (64/128/160/256 to force one). */
 int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w, void* out,
-              long long ldo, const float* bias, const float* rowvec, int rows_per_image, const void* residual,
-              long long ldr, int M, int N, int K, int dtype, int flags, int bn, void* stream);
+              long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
+              const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn, void* stream);
 
 /* torch.nn.Conv2d(Cin, Cout, 3, stride, padding=1) on NHWC activations, implicit GEMM (no im2col buffer).
- * Replaces conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2) and Upsample2D.conv.
+ * Replaces conv_in, conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2), Upsample2D.conv and conv_out
+ * (SURVEY.md §8a a4-a6, a10).
  *   x: [B, stride*H, stride*W, Cin]; out: [B, H, W, Cout]; w_packed: [Cout][3][3][Cin] (tap-major K);
- *   rowvec: [B, Cout] fp32 added per image (the resnet's time_emb_proj term); residual: [B, H, W, Cout]. */
+ *   rowvec: fp32, row b at rowvec + b*ld_rowvec, added per image (the resnet's time_emb_proj term);
+ *   residual: [B, H, W, Cout].  Cin % 64 == 0, Cout % 32 == 0, W | 128, (H*W) % 128 == 0 or 128 % (H*W) == 0. */
 int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
-                 const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype, int flags,
-                 int bn, void* stream);
+                 long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride,
+                 int dtype, int flags, int bn, void* stream);
+
+/* torch.nn.GroupNorm(groups, C, eps) (+ SiLU with PCDM_FLAG_SILU) over NHWC x = [x1 | x2] (x2 may be NULL; x1 then has
+ * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out
+ * (reference :817-819).  y: [B, HW, C].  workspace: pcdm_groupnorm_workspace_bytes(). */
+long long pcdm_groupnorm_workspace_bytes(int B, int groups);
+int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta, float eps,
+                   int B, int HW, int C, int groups, int dtype, int flags, void* workspace, void* stream);
+
+/* torch.nn.LayerNorm(C, eps) over rows; replaces norm1/norm2/norm3 of BasicTransformerBlock. */
+int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
+                   float eps, int M, int C, int dtype, void* stream);
+
+/* softmax(Q K^T * scale) V per head, head_dim 64, no mask.  Replaces xformers memory_efficient_attention /
+ * F.scaled_dot_product_attention behind diffusers' attention processors (stage2_batchtest_inpaint_model.py:133;
+ * SURVEY.md §8a a9).  q: element (b, s, h, d) at q[(b*Sq + s)*ldq + h*64 + d]; k, v likewise with Skv; out likewise
+ * with ldo — so q/k/v may be column slices of one fused projection buffer. */
+int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                   long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);
+
+/* Boundary layout conversion (the reference's tensors are NCHW).  *_dtype: 0 f16, 1 bf16, 2 f32 (destination of
+ * nchw_to_nhwc_pad must be 16-bit).  Replaces nothing arithmetic: forward() entry/exit at reference :579-595,:822-825. */
+int pcdm_nchw_to_nhwc_pad(const void* x, int src_dtype, void* y, int dst_dtype, int B, int C, int HW, int Cpad,
+                          void* stream);
+int pcdm_nhwc_to_nchw(const void* x, int src_dtype, long long ldc, void* y, int dst_dtype, int B, int C, int HW,
+                      void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(t f_i) | sin(t f_i)]
+ * (reference :677-682).  t: device fp32, t_count = 1 (broadcast) or B. */
+int pcdm_timestep_embedding(const float* t, int t_count, void* out, int dtype, int B, int dim, void* stream);
+
+/* F.interpolate(scale_factor=2, mode="nearest") on NHWC (inside diffusers Upsample2D). */
+int pcdm_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, void* stream);
+
+/* One fused launch per denoising step: CFG combine + DDIM (eta 0) update of the fp32 latents + rewrite of channels
+ * 0..3 of the next UNet input for both CFG halves (reference stage2_inpaint_pipeline.py:499-501,510-512,519).
+ * coef_table[step] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} (float4, device);
+ * step_counter: int[2] device {step, scratch=0}; the kernel advances step, so one CUDA graph serves every step.
+ * t_table (steps+1 fp32 timesteps, device) / t_cur (device scalar) are optional: when given, *t_cur = t_table[step+1]. */
+int pcdm_cfg_ddim_step(const void* eps, int eps_dtype, long long ld_eps, float* latents, void* x9, int x9_dtype,
+                       long long ld_x9, const float* coef_table, int* step_counter, float guidance_scale, int n,
+                       int HW, const float* t_table, float* t_cur, void* stream);
+
+/* DDIMScheduler.step (eta 0) on its own, for callers that drive the scheduler protocol tensor by tensor
+ * (stage2_inpaint_pipeline.py:519): prev = sqrt_a_prev * (sample - sqrt_one_minus_a_t * eps) * inv_sqrt_a_t
+ *                                          + sqrt_one_minus_a_prev * eps.   dtypes: 0 f16, 1 bf16, 2 f32. */
+int pcdm_ddim_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
+                   float inv_sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev, float sqrt_one_minus_a_prev,
+                   long long numel, void* stream);
+
+/* DDPMScheduler.add_noise (stage2_train_inpaint_model.py:361): out = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise. */
+int pcdm_add_noise(const void* x0, const void* noise, void* out, int dtype, const float* alphas_cumprod,
+                   const long long* timesteps, int B, long long per_sample, void* stream);
 
 #ifdef __cplusplus
 }

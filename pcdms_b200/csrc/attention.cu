@@ -1,0 +1,274 @@
+// K3 — fused multi-head attention, head_dim 64, no mask:  O = softmax(Q K^T / 8) V   (flash-style, online softmax).
+//
+// One CTA per (batch, head, 128-query tile).  Warp roles: warp 0 = TMA producer (Q once, then a 3-deep K/V ring),
+// warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = softmax (thread t owns query row t: with the
+// 32x32b TMEM access pattern a row's scores sit in one thread's registers, so row max / row sum need no shuffles).
+//
+// TMEM (512 columns):  S0,S1 : 2 x 128 fp32 score tiles (QK^T of block j+1 overlaps softmax of block j)
+//                      P0,P1 : 2 x 64 columns = 128 x 128 fp16/bf16 probabilities, fed to the PV MMA straight from
+//                              tensor memory (A operand in TMEM) — P never touches shared memory
+//                      O     : 64 fp32 columns, accumulated across KV blocks inside the tensor core
+// The running maximum is applied lazily: O/l are rescaled (by the softmax warps, TMEM round trip) only when a row's
+// maximum grows by more than 2^8, so most KV blocks need no correction; the final normalisation divides by l.
+// V is consumed in its natural [kv, d] layout as an MN-major B operand, K as a K-major B operand.
+//
+// Replaces xformers.memory_efficient_attention / F.scaled_dot_product_attention as enabled by the reference at
+// stage2_batchtest_inpaint_model.py:133 and used via diffusers' attention processors (the
+// processor protocol is mirrored at /root/reference/src/pipelines/PCDMs_pipeline.py:78-153).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace pcdm {
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  int B, heads, Sq, Skv;
+  int q_tiles;
+  void* out;
+  long long ldo;       // row stride of O in elements
+  float scale_log2;    // softmax scale * log2(e)
+};
+
+constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + 1024 + 256;
+constexpr int ATT_TMEM_S = 0, ATT_TMEM_P = 256, ATT_TMEM_O = 384;
+
+template <int DT>
+__global__ void __launch_bounds__(256, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + ATT_TILE_BYTES;  // stage s: K at s*2*TILE, V at s*2*TILE + TILE
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + ATT_KV_STAGES;
+  uint64_t* s_full = kv_empty + ATT_KV_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;                // [2]
+  uint64_t* pv_done = p_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.heads, b = bh / p.heads;
+  const int n_kv = (p.Skv + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, ATT_TILE_BYTES);
+    tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 128, h, b);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+      mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+      tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
+      tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
+      if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
+    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
+    const uint32_t q_addr = smem_u32(sQ);
+    mbar_wait(q_full, 0);
+    auto issue_qk = [&](int j) {
+      const int stage = j % ATT_KV_STAGES;
+      mbar_wait(&kv_full[stage], (uint32_t)((j / ATT_KV_STAGES) & 1));
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + ATT_TMEM_S + (j & 1) * 128, make_desc_sw128(q_addr + k * 32, 1024, 16),
+                make_desc_sw128(k_addr + k * 32, 1024, 16), idesc_qk, k != 0);
+      tc_commit(&s_full[j & 1]);
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const int stage = j % ATT_KV_STAGES;
+      const uint32_t v_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
+        umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + (j & 1) * 64 + k * 8,
+                make_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
+      tc_commit(&kv_empty[stage]);
+      tc_commit(&pv_done[j & 1]);
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / correction / epilogue =====================
+    using T = typename TypeOf<DT>::T;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float m_ref = -INFINITY;  // reference maximum (log2 domain) the accumulators are relative to
+    float l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&chunk)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S + (j & 1) * 128 + c * 32, chunk);
+      }
+      tc_wait_ld();
+      const int kv_left = p.Skv - j * 128;  // valid columns in this block
+      float mx = -INFINITY;
+      if (kv_left >= 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          if (i >= kv_left) s[i] = __float_as_uint(-INFINITY);
+          mx = fmaxf(mx, __uint_as_float(s[i]));
+        }
+      }
+      mx *= p.scale_log2;
+      // P buffer (j & 1) was last read by PV_{j-2}: make sure that MMA has retired before overwriting it
+      if (j >= 2) mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool grow = mx > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rescale O and l to the new reference maximum (needs PV_{j-1} to have landed in TMEM)
+          mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+          tc_fence_after();
+          const float m_new = grow ? mx : m_ref;
+          const float alpha = exp2f(m_ref - m_new);
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            {
+              uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
+              uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
+              tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32, lo);
+              tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32 + 16, hi);
+            }
+          }
+          l *= alpha;
+          m_ref = m_new;
+        }
+      }
+      float sum = 0.f;
+      const uint32_t p_addr = tmem + lane_off + ATT_TMEM_P + (j & 1) * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
+          const float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
+          sum += a + bq;
+          pk[i] = pack2<DT>(a, bq);
+        }
+        tmem_st16(p_addr + c * 16, pk);
+      }
+      l += sum;
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+    // epilogue: O / l
+    mbar_wait(&pv_done[(n_kv - 1) & 1], (uint32_t)(((n_kv - 1) >> 1) & 1));
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const long long qrow = (long long)qt * 128 + row;
+    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
+      tc_wait_ld();
+      if (qrow < p.Sq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+          u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+          u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+          u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace pcdm
+
+using namespace pcdm;
+
+static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, int heads, int B, int box_rows) {
+  // element (b, s, h, d) at ((b*S + s) * ld + h*64 + d)
+  const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)heads, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ld * 2, 128, (uint64_t)S * ld * 2};
+  const uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return make_tmap(m, base, 4, dims, strides, box);
+}
+
+extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                              void* out, long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!q || !k || !v || !out) return set_error(PCDM_ERR_INVALID, "attention: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "attention: bad dtype");
+  if (B <= 0 || heads <= 0 || Sq <= 0 || Skv <= 0) return set_error(PCDM_ERR_INVALID, "attention: empty problem");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error(PCDM_ERR_UNSUPPORTED, "attention: strides must be multiples of 8");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and
+  // are zero-filled, so short sequences need no special casing (zero K rows are masked, zero V rows add nothing).
+  PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128), "Q map");
+  PCDM_CHECK(make_qkv_map(&p.tmK, k, ldk, Skv, heads, B, 128), "K map");
+  PCDM_CHECK(make_qkv_map(&p.tmV, v, ldv, Skv, heads, B, 128), "V map");
+  p.B = B; p.heads = heads; p.Sq = Sq; p.Skv = Skv;
+  p.q_tiles = (Sq + 127) / 128;
+  p.out = out; p.ldo = ldo;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = B * heads * p.q_tiles;
+  if (dtype == DT_F16) attention_kernel<DT_F16><<<grid, 256, ATT_SMEM_BYTES, stream>>>(p);
+  else attention_kernel<DT_BF16><<<grid, 256, ATT_SMEM_BYTES, stream>>>(p);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,268 @@
+// K6 and friends — the small HBM/launch-bound kernels around the UNet: layout conversion at the boundary
+// (the reference's tensors are NCHW, ours NHWC), sinusoidal timestep embedding, nearest-2x upsampling, and the fused
+// per-step kernel (classifier-free-guidance combine + DDIM update + rebuild of the next UNet input).
+//
+// Reference call sites replaced:
+//   pcdm_cfg_ddim_step  : src/pipelines/stage2_inpaint_pipeline.py:499-501 (dup + concat), :510-512 (CFG combine),
+//                         :519 (scheduler.step — diffusers DDIMScheduler, eta = 0)               [SURVEY §8a a1,a11,a12]
+//   pcdm_add_noise      : DDPMScheduler.add_noise, stage2_train_inpaint_model.py:361                          [a12]
+//   pcdm_timestep_embedding : diffusers Timesteps(320, flip_sin_to_cos=True, freq_shift=0),
+//                         src/models/stage2_inpaint_unet_2d_condition.py:677-682                              [a3]
+//   pcdm_upsample_nearest2x : F.interpolate(scale_factor=2, mode="nearest") inside diffusers Upsample2D       [a6]
+//   pcdm_nchw_to_nhwc_pad / pcdm_nhwc_to_nchw : the NCHW <-> NHWC boundary of UNet.forward (:579-595, :822-825)
+#include "common.cuh"
+#include "host_util.h"
+
+namespace pcdm {
+
+// src dtype codes for boundary tensors: 0 = f16, 1 = bf16, 2 = f32
+__device__ __forceinline__ float load_any(const void* p, long long i, int dt) {
+  if (dt == 2) return reinterpret_cast<const float*>(p)[i];
+  if (dt == 0) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_any(void* p, long long i, int dt, float v) {
+  if (dt == 2) reinterpret_cast<float*>(p)[i] = v;
+  else if (dt == 0) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// [B, C, HW] (any float dtype) -> [B, HW, Cpad] 16-bit, channels >= C zero-filled.  One thread per (pixel, 8 ch).
+__global__ void nchw_to_nhwc_pad_kernel(const void* __restrict__ x, int src_dt, void* __restrict__ y, int dst_dt, int B,
+                                        int C, int HW, int Cpad) {
+  const long long total = (long long)B * HW * (Cpad / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (Cpad / 8));
+    const long long bp = i / (Cpad / 8);
+    const int p = (int)(bp % HW);
+    const int b = (int)(bp / HW);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cv * 8 + k;
+      v[k] = (c < C) ? load_any(x, ((long long)b * C + c) * HW + p, src_dt) : 0.f;
+    }
+    uint4 u;
+    if (dst_dt == 0) {
+      u.x = pack2<DT_F16>(v[0], v[1]); u.y = pack2<DT_F16>(v[2], v[3]);
+      u.z = pack2<DT_F16>(v[4], v[5]); u.w = pack2<DT_F16>(v[6], v[7]);
+    } else {
+      u.x = pack2<DT_BF16>(v[0], v[1]); u.y = pack2<DT_BF16>(v[2], v[3]);
+      u.z = pack2<DT_BF16>(v[4], v[5]); u.w = pack2<DT_BF16>(v[6], v[7]);
+    }
+    reinterpret_cast<uint4*>(y)[i] = u;
+  }
+}
+
+// [B, HW, ldc] (src dtype) channels [0, C) -> [B, C, HW] (dst dtype)
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int src_dt, long long ldc, void* __restrict__ y,
+                                    int dst_dt, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long bc = i / HW;
+    const int c = (int)(bc % C);
+    const int b = (int)(bc / C);
+    store_any(y, i, dst_dt, load_any(x, ((long long)b * HW + p) * ldc + c, src_dt));
+  }
+}
+
+// emb[b, :] = [cos(t_b * f_i) | sin(t_b * f_i)], f_i = exp(-ln(10000) * i / half)  (flip_sin_to_cos, freq_shift 0)
+// t may be a single value broadcast to all rows (t_count == 1) or one per row.  fp32 math, 16-bit store.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int t_count, void* __restrict__ out, int dt,
+                                          int B, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const float tv = t[t_count == 1 ? 0 : b];
+  // double-precision libm (immune to --use_fast_math): arguments reach ~1000 rad, where __sinf/__cosf are useless.
+  // The fp32 roundings mirror the reference: f = fp32(exp(.)), a = fp32(t * f), emb = fp32(cos/sin(a)).
+  const float f = (float)exp(-9.210340371976184 * (double)k / (double)half);
+  const float a = tv * f;
+  store_any(out, (long long)b * dim + k, dt, (float)cos((double)a));
+  store_any(out, (long long)b * dim + half + k, dt, (float)sin((double)a));
+}
+
+// y[b, 2h+dy, 2w+dx, :] = x[b, h, w, :]
+__global__ void upsample_nearest2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                          int CV) {
+  const long long total = (long long)B * (2 * H) * (2 * W) * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
+    const int ox = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    y[i] = __ldg(&x[(((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * CV + cv]);
+  }
+}
+
+// Fused per-step kernel.  eps: UNet output rows [2n, HW, ld_eps] (channels 0..3; [uncond ; cond] batch halves).
+// latents: [n, 4, HW] fp32 scheduler state, updated in place:
+//     e      = e_u + g (e_c - e_u)
+//     x0     = (x - sqrt(1 - a_t) e) / sqrt(a_t)
+//     x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) e
+// and the first 4 channels of the next UNet input x9 [2n, HW, ld_x9] (NHWC, 16-bit) are rewritten for both halves.
+// Coefficients come from a device table coef[step] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} indexed
+// by *step_counter, which the kernel's last thread increments — so an identical CUDA graph replays every step; it also
+// publishes the next timestep (t_table[step + 1]) into *t_cur for the next UNet evaluation's embedding.
+__global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, long long ld_eps,
+                                     float* __restrict__ latents, void* __restrict__ x9, int x9_dt, long long ld_x9,
+                                     const float4* __restrict__ coef, int* __restrict__ step_counter, float guidance,
+                                     int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur) {
+  const int step = *step_counter;
+  const float4 cf = coef[step];
+  const long long total = (long long)n * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int b = (int)(i / HW);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float eu = load_any(eps, ((long long)b * HW + p) * ld_eps + c, eps_dt);
+      const float ec = load_any(eps, ((long long)(b + n) * HW + p) * ld_eps + c, eps_dt);
+      const float e = eu + guidance * (ec - eu);
+      const long long li = ((long long)b * 4 + c) * HW + p;
+      const float x = latents[li];
+      const float x0 = (x - cf.y * e) * cf.x;
+      const float xp = cf.z * x0 + cf.w * e;
+      latents[li] = xp;
+      store_any(x9, ((long long)b * HW + p) * ld_x9 + c, x9_dt, xp);
+      store_any(x9, ((long long)(b + n) * HW + p) * ld_x9 + c, x9_dt, xp);
+    }
+  }
+  __syncthreads();
+  // grid-wide "last block" increments the step counter exactly once
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(step_counter + 1), 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    step_counter[1] = 0;
+    step_counter[0] = step + 1;
+    if (t_table && t_cur) *t_cur = t_table[step + 1];  // timestep the next UNet evaluation embeds (table has steps+1 rows)
+  }
+}
+
+// out = sqrt(a_t[b]) x0 + sqrt(1 - a_t[b]) noise      (per-sample timestep)
+__global__ void add_noise_kernel(const void* __restrict__ x0, const void* __restrict__ noise, void* __restrict__ out,
+                                 int dt, const float* __restrict__ alphas_cumprod, const long long* __restrict__ t,
+                                 int B, long long per_sample) {
+  const long long total = (long long)B * per_sample;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const float a = alphas_cumprod[t[b]];
+    const float sa = sqrtf(a), sb = sqrtf(1.f - a);
+    store_any(out, i, dt, sa * load_any(x0, i, dt) + sb * load_any(noise, i, dt));
+  }
+}
+
+// stand-alone scheduler.step: prev = c2 * (x - c1 * eps) * c0 + c3 * eps   (same arithmetic as the fused kernel)
+__global__ void ddim_step_kernel(const void* __restrict__ eps, int eps_dt, const void* __restrict__ x, void* __restrict__ out,
+                                 int dt, float c0, float c1, float c2, float c3, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float e = load_any(eps, i, eps_dt);
+    const float x0 = (load_any(x, i, dt) - c1 * e) * c0;
+    store_any(out, i, dt, c2 * x0 + c3 * e);
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pcdm
+
+using namespace pcdm;
+
+extern "C" int pcdm_nchw_to_nhwc_pad(const void* x, int src_dtype, void* y, int dst_dtype, int B, int C, int HW,
+                                     int Cpad, void* stream_) {
+  if (!x || !y) return set_error(PCDM_ERR_INVALID, "nchw_to_nhwc_pad: null pointer");
+  if (src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 1) return set_error(PCDM_ERR_INVALID, "nchw_to_nhwc_pad: bad dtype");
+  if (B <= 0 || C <= 0 || HW <= 0 || Cpad < C || Cpad % 8) return set_error(PCDM_ERR_INVALID, "nchw_to_nhwc_pad: bad shape");
+  const long long total = (long long)B * HW * (Cpad / 8);
+  nchw_to_nhwc_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, src_dtype, y, dst_dtype, B, C, HW, Cpad);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_nhwc_to_nchw(const void* x, int src_dtype, long long ldc, void* y, int dst_dtype, int B, int C,
+                                 int HW, void* stream_) {
+  if (!x || !y) return set_error(PCDM_ERR_INVALID, "nhwc_to_nchw: null pointer");
+  if (src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 2) return set_error(PCDM_ERR_INVALID, "nhwc_to_nchw: bad dtype");
+  if (B <= 0 || C <= 0 || HW <= 0 || ldc < C) return set_error(PCDM_ERR_INVALID, "nhwc_to_nchw: bad shape");
+  const long long total = (long long)B * C * HW;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, src_dtype, ldc, y, dst_dtype, B, C, HW);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_timestep_embedding(const float* t, int t_count, void* out, int dtype, int B, int dim,
+                                       void* stream_) {
+  if (!t || !out) return set_error(PCDM_ERR_INVALID, "timestep_embedding: null pointer");
+  if (dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "timestep_embedding: bad dtype");
+  if (B <= 0 || dim <= 0 || dim % 2 || (t_count != 1 && t_count != B)) return set_error(PCDM_ERR_INVALID, "timestep_embedding: bad shape");
+  const int total = B * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(t, t_count, out, dtype, B, dim);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, void* stream_) {
+  if (!x || !y) return set_error(PCDM_ERR_INVALID, "upsample: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return set_error(PCDM_ERR_INVALID, "upsample: bad shape (C % 8 == 0)");
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample_nearest2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_cfg_ddim_step(const void* eps, int eps_dtype, long long ld_eps, float* latents, void* x9,
+                                  int x9_dtype, long long ld_x9, const float* coef_table, int* step_counter,
+                                  float guidance_scale, int n, int HW, const float* t_table, float* t_cur,
+                                  void* stream_) {
+  if (!eps || !latents || !x9 || !coef_table || !step_counter) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || x9_dtype < 0 || x9_dtype > 1) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: bad dtype");
+  if (n <= 0 || HW <= 0 || ld_eps < 4 || ld_x9 < 4) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: bad shape");
+  if (reinterpret_cast<uintptr_t>(coef_table) & 15) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: coef table must be 16-byte aligned");
+  const long long total = (long long)n * HW;
+  cfg_ddim_step_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream_>>>(
+      eps, eps_dtype, ld_eps, latents, x9, x9_dtype, ld_x9, reinterpret_cast<const float4*>(coef_table), step_counter,
+      guidance_scale, n, HW, t_table, t_cur);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_add_noise(const void* x0, const void* noise, void* out, int dtype, const float* alphas_cumprod,
+                              const long long* timesteps, int B, long long per_sample, void* stream_) {
+  if (!x0 || !noise || !out || !alphas_cumprod || !timesteps) return set_error(PCDM_ERR_INVALID, "add_noise: null pointer");
+  if (dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "add_noise: bad dtype");
+  if (B <= 0 || per_sample <= 0) return set_error(PCDM_ERR_INVALID, "add_noise: empty problem");
+  const long long total = (long long)B * per_sample;
+  add_noise_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x0, noise, out, dtype, alphas_cumprod,
+                                                                              timesteps, B, per_sample);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
+                              float inv_sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev,
+                              float sqrt_one_minus_a_prev, long long numel, void* stream_) {
+  if (!model_output || !sample || !prev_sample) return set_error(PCDM_ERR_INVALID, "ddim_step: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "ddim_step: bad dtype");
+  if (numel <= 0) return set_error(PCDM_ERR_INVALID, "ddim_step: empty problem");
+  ddim_step_kernel<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream_>>>(
+      model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev,
+      sqrt_one_minus_a_prev, numel);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -32,6 +32,7 @@ struct IGemmParams {
   uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
   const float* bias;
   const float* rowvec;
+  long long ld_rowvec;
   int hw;          // rows per image for rowvec indexing
   const void* residual;
   long long ldr;
@@ -39,6 +40,7 @@ struct IGemmParams {
   long long ldo;
   int geglu;
   int out_f32;
+  int silu;
 };
 
 template <int BN>
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      const float* rv = (p.rowvec && valid) ? p.rowvec + (long long)(m / p.hw) * p.N : nullptr;
+      const float* rv = (p.rowvec && valid) ? p.rowvec + (long long)(m / p.hw) * p.ld_rowvec : nullptr;
       if (!p.geglu) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -204,6 +206,10 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 f = unpack2<DT>(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
                 f = unpack2<DT>(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
               }
+            }
+            if (p.silu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             }
             if (p.out_f32) {
               float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
@@ -335,8 +341,8 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
 using namespace pcdm;
 
 extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w,
-                         void* out, long long ldo, const float* bias, const float* rowvec, int rows_per_image,
-                         const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
+                         void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
+                         int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!a || !w || !out) return set_error(PCDM_ERR_INVALID, "gemm: null pointer");
@@ -368,15 +374,16 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
       PCDM_CHECK(make_tmap(&p.tmA[1], a2, 2, dims2, strides2, box), "A2 tensor map");
     }
   }
-  p.bias = bias; p.rowvec = rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
+  p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
   p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
-  p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0;
+  p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
+  if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: rowvec stride must be a multiple of 4");
   if (p.geglu && p.out_f32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU with fp32 output");
   return dispatch_igemm(p, dtype, bn, w, K, stream);
 }
 
 extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
-                            const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype,
+                            long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype,
                             int flags, int bn, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!x || !w_packed || !out) return set_error(PCDM_ERR_INVALID, "conv3x3: null pointer");
@@ -417,8 +424,9 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
         PCDM_CHECK(make_tmap(&p.tmA[py * 2 + px], base, 4, dims, strides, box), "conv parity tensor map");
       }
   }
-  p.bias = bias; p.rowvec = rowvec; p.hw = hw;
+  p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = hw;
   p.residual = residual; p.ldr = Cout; p.out = out; p.ldo = Cout;
-  p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0;
+  p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
+  if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: rowvec stride must be a multiple of 4");
   return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, stream);
 }

@@ -52,7 +52,7 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # K1/K2
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, bn=0):
+         out_f32=False, silu=False, bn=0):
     """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual)."""
     lib = _l.load()
     M, k1 = a.shape
@@ -67,11 +67,11 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     assert out.shape == (M, n_out) and out.stride(1) == 1
-    flags = (_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0)
+    flags = (_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0)
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
-        C.c_int(rows_per_image), _l.ptr(residual), C.c_longlong(residual.stride(0) if residual is not None else 0),
+        C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), C.c_int(rows_per_image), _l.ptr(residual), C.c_longlong(residual.stride(0) if residual is not None else 0),
         C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(_dt(a)), C.c_int(flags), C.c_int(bn), _stream(a))
     _l.check(rc)
     return out
@@ -91,7 +91,171 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
         assert residual.is_contiguous() and residual.shape == out.shape
     flags = _l.FLAG_OUT_F32 if out_f32 else 0
     rc = lib.pcdm_conv3x3(_l.ptr(x), _l.ptr(w_packed), _l.ptr(out), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
-                          _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
+                          C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
                           C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), _stream(x))
+    _l.check(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K4 / K5 norms
+# ---------------------------------------------------------------------------------------------------------------
+_gn_ws = {}
+
+
+def _gn_workspace(device, B, groups):
+    key = (device, B, groups)
+    ws = _gn_ws.get(key)
+    if ws is None:
+        n = _l.load().pcdm_groupnorm_workspace_bytes(C.c_int(B), C.c_int(groups))
+        ws = torch.empty(int(n), dtype=torch.uint8, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None):
+    """x1: [B, ..., C1] NHWC (x2 optional second channel segment); returns [B, ..., C1+C2]."""
+    lib = _l.load()
+    lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong
+    B = x1.shape[0]
+    C1 = x1.shape[-1]
+    Ct = C1 + (x2.shape[-1] if x2 is not None else 0)
+    HW = x1.numel() // (B * C1)
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty((*x1.shape[:-1], Ct), device=x1.device, dtype=x1.dtype)
+    if workspace is None:
+        workspace = _gn_workspace(x1.device, B, groups)
+    rc = lib.pcdm_groupnorm(_l.ptr(x1), _l.ptr(x2), C.c_int(C1), _l.ptr(out), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)),
+                            C.c_float(eps), C.c_int(B), C.c_int(HW), C.c_int(Ct), C.c_int(groups), C.c_int(_dt(x1)),
+                            C.c_int(_l.FLAG_SILU if silu else 0), _l.ptr(workspace), _stream(x1))
+    _l.check(rc)
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    """x: [M, C] rows (row stride free, unit column stride)."""
+    lib = _l.load()
+    M, Cc = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, Cc), device=x.device, dtype=x.dtype)
+    rc = lib.pcdm_layernorm(_l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(out), C.c_longlong(out.stride(0)),
+                            _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)), C.c_float(eps), C.c_int(M), C.c_int(Cc),
+                            C.c_int(_dt(x)), _stream(x))
+    _l.check(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K3 attention
+# ---------------------------------------------------------------------------------------------------------------
+def attention(q, k, v, B, heads, out=None, scale=0.125):
+    """q: [B*Sq, >=heads*64] view, k/v: [B*Skv, ...] views (unit column stride; may be slices of a fused buffer).
+    Head h of token row r lives at columns [h*64, h*64+64).  Returns [B*Sq, heads*64]."""
+    lib = _l.load()
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    Sq = q.shape[0] // B
+    Skv = k.shape[0] // B
+    if out is None:
+        out = torch.empty((B * Sq, heads * 64), device=q.device, dtype=q.dtype)
+    rc = lib.pcdm_attention(_l.ptr(q), C.c_longlong(q.stride(0)), _l.ptr(k), C.c_longlong(k.stride(0)), _l.ptr(v),
+                            C.c_longlong(v.stride(0)), _l.ptr(out), C.c_longlong(out.stride(0)), C.c_int(B),
+                            C.c_int(heads), C.c_int(Sq), C.c_int(Skv), C.c_float(scale), C.c_int(_dt(q)), _stream(q))
+    _l.check(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K6 and boundary helpers
+# ---------------------------------------------------------------------------------------------------------------
+def _any_dt(t: torch.Tensor) -> int:
+    return {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[t.dtype]
+
+
+def nchw_to_nhwc_pad(x, cpad, dtype, out=None):
+    lib = _l.load()
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((B, H, W, cpad), device=x.device, dtype=dtype)
+    rc = lib.pcdm_nchw_to_nhwc_pad(_l.ptr(x), C.c_int(_any_dt(x)), _l.ptr(out), C.c_int(_any_dt(out)), C.c_int(B),
+                                   C.c_int(Cc), C.c_int(H * W), C.c_int(cpad), _stream(x))
+    _l.check(rc)
+    return out
+
+
+def nhwc_to_nchw(x, channels, out_dtype, out=None):
+    """x: [B, H, W, ld] -> [B, channels, H, W]"""
+    lib = _l.load()
+    B, H, W, ld = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((B, channels, H, W), device=x.device, dtype=out_dtype)
+    rc = lib.pcdm_nhwc_to_nchw(_l.ptr(x), C.c_int(_any_dt(x)), C.c_longlong(ld), _l.ptr(out), C.c_int(_any_dt(out)),
+                               C.c_int(B), C.c_int(channels), C.c_int(H * W), _stream(x))
+    _l.check(rc)
+    return out
+
+
+def timestep_embedding(t, B, dim, dtype, out=None):
+    """t: fp32 device tensor with 1 or B entries."""
+    lib = _l.load()
+    assert t.dtype == torch.float32 and t.is_cuda
+    if out is None:
+        out = torch.empty((B, dim), device=t.device, dtype=dtype)
+    rc = lib.pcdm_timestep_embedding(_l.ptr(t), C.c_int(t.numel()), _l.ptr(out), C.c_int(_any_dt(out)), C.c_int(B),
+                                     C.c_int(dim), _stream(t))
+    _l.check(rc)
+    return out
+
+
+def upsample_nearest2x(x, out=None):
+    lib = _l.load()
+    B, H, W, Cc = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=x.dtype)
+    rc = lib.pcdm_upsample_nearest2x(_l.ptr(x), _l.ptr(out), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cc),
+                                     _stream(x))
+    _l.check(rc)
+    return out
+
+
+def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+    """eps_rows: [2n, H, W, ld] UNet output rows; latents: [n, 4, H, W] fp32 (in place); x9: [2n, H, W, ld9]."""
+    lib = _l.load()
+    n = latents.shape[0]
+    HW = latents.shape[2] * latents.shape[3]
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and eps_rows.is_contiguous()
+    assert coef_table.dtype == torch.float32 and step_counter.dtype == torch.int32 and step_counter.numel() == 2
+    rc = lib.pcdm_cfg_ddim_step(_l.ptr(eps_rows), C.c_int(_any_dt(eps_rows)), C.c_longlong(eps_rows.shape[-1]),
+                                _l.ptr(latents), _l.ptr(x9), C.c_int(_any_dt(x9)), C.c_longlong(x9.shape[-1]),
+                                _l.ptr(coef_table), _l.ptr(step_counter), C.c_float(guidance_scale), C.c_int(n),
+                                C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _stream(latents))
+    _l.check(rc)
+
+
+def add_noise(x0, noise, alphas_cumprod, timesteps, out=None):
+    lib = _l.load()
+    assert x0.is_contiguous() and noise.is_contiguous() and x0.dtype == noise.dtype
+    assert alphas_cumprod.dtype == torch.float32 and timesteps.dtype == torch.int64
+    if out is None:
+        out = torch.empty_like(x0)
+    B = x0.shape[0]
+    rc = lib.pcdm_add_noise(_l.ptr(x0), _l.ptr(noise), _l.ptr(out), C.c_int(_any_dt(x0)), _l.ptr(alphas_cumprod),
+                            _l.ptr(timesteps), C.c_int(B), C.c_longlong(x0.numel() // B), _stream(x0))
+    _l.check(rc)
+    return out
+
+
+def ddim_step(model_output, sample, coefs, out=None):
+    lib = _l.load()
+    assert model_output.is_contiguous() and sample.is_contiguous() and model_output.shape == sample.shape
+    if out is None:
+        out = torch.empty_like(sample)
+    rc = lib.pcdm_ddim_step(_l.ptr(model_output), C.c_int(_any_dt(model_output)), _l.ptr(sample), _l.ptr(out),
+                            C.c_int(_any_dt(sample)), C.c_float(coefs[0]), C.c_float(coefs[1]), C.c_float(coefs[2]),
+                            C.c_float(coefs[3]), C.c_longlong(sample.numel()), _stream(sample))
     _l.check(rc)
     return out

@@ -1,0 +1,265 @@
+"""B200Stage2InpaintPipeline — drop-in for the reference's `Stage2_InpaintDiffusionPipeline`
+(/root/reference/src/pipelines/stage2_inpaint_pipeline.py:71-541): same constructor modules (vae, unet, scheduler),
+same `__call__` keyword surface (:391-417) and `.images` output (:541), same conditioning layout (:427-466, CFG batch
+= [uncond ; cond], only tokens + class embedding zeroed for the unconditional half).
+
+The denoising loop (:496-525) is executed as ONE CUDA graph replayed `num_inference_steps` times: the graph holds the
+whole UNet forward (~600 launches of the sm_100a kernels) plus the fused CFG + DDIM + input-rebuild kernel; step-
+dependent scalars (DDIM coefficients, timestep) are read from device tables indexed by a device-side step counter, so
+the captured graph is step-invariant.  Step-invariant work (cross-attention K/V, pose/mask/masked-latent layout) is
+done once per call.  When handed a foreign unet/scheduler the generic protocol loop is used instead.
+
+Out of scope here (SURVEY.md §8 "next"): the VAE.  `vae` may be any object with diffusers' AutoencoderKL encode /
+decode surface, or None — then `masked_latents=` must be passed and `output_type="latent"` is the only output.
+"""
+from __future__ import annotations
+
+import inspect
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import ops
+from .scheduler import B200DDIMScheduler
+from .unet import B200AttnProcessor, B200UNet2DConditionModel
+
+
+class Stage2PipelineOutput(SimpleNamespace):
+    pass
+
+
+class B200Stage2InpaintPipeline:
+    def __init__(self, vae=None, unet: Optional[B200UNet2DConditionModel] = None, scheduler=None):
+        if unet is None or scheduler is None:
+            raise ValueError("unet and scheduler are required")
+        if hasattr(scheduler, "config") and getattr(scheduler.config, "steps_offset", 1) != 1:
+            raise ValueError("scheduler.config.steps_offset must be 1 (reference :112-123)")
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.vae_scale_factor = (2 ** (len(vae.config.block_out_channels) - 1)) if vae is not None else 8
+        self._graphs = {}
+        self.use_cuda_graph = True
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=torch.float16, **kw):
+        unet = B200UNet2DConditionModel.from_pretrained(pretrained_model_name_or_path, subfolder="unet",
+                                                        torch_dtype=torch_dtype)
+        return cls(vae=kw.get("vae"), unet=unet, scheduler=kw.get("scheduler") or B200DDIMScheduler())
+
+    # -- diffusers pipeline conveniences the reference drivers call ------------------------------------------------
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    @property
+    def _execution_device(self):
+        return self.unet.device
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):  # stage2_batchtest_inpaint_model.py:133
+        return None
+
+    def enable_vae_slicing(self):
+        return None
+
+    def enable_vae_tiling(self):
+        return None
+
+    def set_progress_bar_config(self, **k):
+        return None
+
+    def check_inputs(self, height, width, callback_steps):
+        """reference :324-369"""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
+                             f" {type(callback_steps)}.")
+
+    def prepare_extra_step_kwargs(self, generator, eta):
+        """reference :307-322"""
+        params = set(inspect.signature(self.scheduler.step).parameters.keys())
+        extra = {}
+        if "eta" in params:
+            extra["eta"] = eta
+        if "generator" in params:
+            extra["generator"] = generator
+        return extra
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None, latents=None,
+                 prompt_embeds=None, negative_prompt_embeds=None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback=None, callback_steps: int = 1, cross_attention_kwargs=None,
+                 guidance_rescale: float = 0.0,
+                 vae_image=None, mask=None, s_img_proj_f=None, st_pose_f=None, pred_t_img_embed=None,
+                 masked_latents=None):
+        if cross_attention_kwargs is not None:
+            raise NotImplementedError("cross_attention_kwargs are not supported")
+        if guidance_rescale and guidance_rescale > 0.0:
+            raise NotImplementedError("guidance_rescale > 0 is disabled by the reference drivers and not implemented")
+        self.check_inputs(height, width, callback_steps)
+        dev, dt = self.unet.device, self.unet.dtype
+        bs, num, _ = s_img_proj_f.shape
+        if bs != 1:
+            raise NotImplementedError("the reference drivers run one source/target pair per call (bs == 1)")
+        do_cfg = guidance_scale > 1.0
+        if not do_cfg:
+            raise NotImplementedError("guidance_scale <= 1: the reference's non-CFG branch repeats feature_f twice "
+                                      "(stage2_inpaint_pipeline.py:449,465) and is never used by its drivers")
+        n = bs * num_images_per_prompt
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        B = 2 * n
+
+        # --- conditioning (reference :430-462), built once per call -------------------------------------------
+        pose_cond = torch.cat([st_pose_f.to(dev)] * B).to(dt)                                   # :430-431
+        if mask is None:                                                                         # :434-437
+            m1 = torch.ones((bs, 1, h, w // 2), dtype=torch.float32, device=dev)
+            m0 = torch.zeros((bs, 1, h, w // 2), dtype=torch.float32, device=dev)
+            mask = torch.cat([m1, m0], dim=3)
+        mask = torch.cat([mask.to(dev, torch.float32)] * B)
+        if masked_latents is None:                                                               # :443-444
+            if self.vae is None:
+                raise ValueError("pass masked_latents= when the pipeline has no VAE")
+            masked_latents = self.vae.encode(vae_image.to(device=dev, dtype=dt)).latent_dist.sample(generator=generator)
+            masked_latents = masked_latents * self.vae.config.scaling_factor
+        masked_latents = torch.cat([masked_latents.to(dev, torch.float32)] * B)                  # :445
+        feature_f = torch.cat([s_img_proj_f, pred_t_img_embed], dim=1).to(dev)                   # :448
+        feature_f = feature_f.repeat(n, 1, 1).to(dt)
+        prior_embed = pred_t_img_embed.to(dev).repeat(n, 1, 1).to(dt)                            # :452
+        feature_f = torch.cat([torch.zeros_like(feature_f), feature_f], dim=0)                   # :455-458
+        prior_embed = torch.cat([torch.zeros_like(prior_embed), prior_embed], dim=0)             # :461-462
+
+        # --- timesteps & latents (reference :472-487) -----------------------------------------------------------
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        timesteps = self.scheduler.timesteps
+        if latents is None:
+            latents = torch.randn((n, 4, h, w), generator=generator,
+                                  device=generator.device if generator is not None else dev, dtype=torch.float32)
+        latents = latents.to(device=dev, dtype=torch.float32) * self.scheduler.init_noise_sigma
+
+        fast = (isinstance(self.unet, B200UNet2DConditionModel) and isinstance(self.scheduler, B200DDIMScheduler)
+                and eta == 0.0 and callback is None
+                and all(isinstance(a.processor, B200AttnProcessor) for a in self.unet._attn.values()))
+        if fast:
+            latents = self._denoise_fused(latents.contiguous().clone(), mask, masked_latents, pose_cond, feature_f,
+                                          prior_embed, float(guidance_scale), num_inference_steps)
+        else:
+            latents = self._denoise_generic(latents, mask, masked_latents, pose_cond, feature_f, prior_embed,
+                                            guidance_scale, timesteps, eta, generator, callback, callback_steps)
+
+        if output_type == "latent" or self.vae is None:
+            if output_type != "latent" and self.vae is None:
+                raise ValueError("no VAE: use output_type='latent'")
+            image = latents
+        else:
+            image = self.vae.decode((latents / self.vae.config.scaling_factor).to(dt), return_dict=False)[0]  # :528
+            image = self._postprocess(image, output_type)
+        if not return_dict:
+            return (image, None)
+        return Stage2PipelineOutput(images=image, nsfw_content_detected=None)
+
+    @staticmethod
+    def _postprocess(image, output_type):
+        if output_type == "pt":
+            return image
+        image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).float().numpy()
+        if output_type == "np":
+            return image
+        from PIL import Image
+        return [Image.fromarray((im * 255).round().astype("uint8")) for im in image]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _denoise_fused(self, latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance, steps):
+        unet, sch = self.unet, self.scheduler
+        dev, dt = unet.device, unet.dtype
+        n, _, h, w = latents.shape
+        B = 2 * n
+        # static buffers of the (possibly cached) graph
+        key = (n, h, w, feature_f.shape[1], dt)
+        st = self._graphs.get(key)
+        if st is None:
+            st = SimpleNamespace(
+                x9=torch.zeros((B, h, w, 64), device=dev, dtype=dt),
+                latents=torch.empty((n, 4, h, w), device=dev, dtype=torch.float32),
+                pose=torch.empty((B, h, w, pose_cond.shape[1]), device=dev, dtype=dt),
+                cls=torch.empty((B, prior_embed.shape[-1]), device=dev, dtype=dt),
+                t_cur=torch.zeros(1, device=dev, dtype=torch.float32),
+                counter=torch.zeros(2, device=dev, dtype=torch.int32),
+                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None)
+            self._graphs[key] = st
+        # per-call state
+        x9_nchw = torch.cat([latents, latents], dim=0)
+        x9_nchw = torch.cat([x9_nchw, mask, masked_latents], dim=1).contiguous()                # ref :499-501
+        ops.nchw_to_nhwc_pad(x9_nchw, 64, dt, out=st.x9)
+        st.latents.copy_(latents)
+        ops.nchw_to_nhwc_pad(pose_cond.contiguous(), pose_cond.shape[1], dt, out=st.pose)
+        st.cls.copy_(prior_embed.reshape(B, -1))
+        first = st.kv is None
+        st.kv = unet.context_kv(feature_f, out=st.kv)   # K/V GEMMs write straight into the graph's static buffers
+        coef = sch.coefficient_table(dev)
+        t_table = torch.cat([sch.timesteps.to(dev, torch.float32), torch.zeros(1, device=dev)]).contiguous()
+        st.counter.zero_()
+        st.t_cur.copy_(t_table[:1])
+
+        def one_step():
+            eps_rows = unet.forward_nhwc(st.x9, st.t_cur, st.kv, st.cls, st.pose)
+            ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, guidance, st.t_table, st.t_cur)
+
+        rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps)
+        st.guidance, st.steps = guidance, steps
+        if st.coef is None or st.coef.shape != coef.shape:
+            st.coef, st.t_table = coef, t_table
+            rebuild = True
+        else:
+            st.coef.copy_(coef)
+            st.t_table.copy_(t_table)
+        if not self.use_cuda_graph:
+            for _ in range(steps):
+                one_step()
+            return st.latents.clone()
+        if rebuild:
+            # warm-up on a side stream (allocator + lazy kernel attribute set-up), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                one_step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            # the warm-up consumed step 0: restore state
+            st.latents.copy_(latents)
+            ops.nchw_to_nhwc_pad(x9_nchw, 64, dt, out=st.x9)
+            st.counter.zero_()
+            st.t_cur.copy_(t_table[:1])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()
+            st.graph = g
+            # capture does not execute: state is still at step 0
+        for _ in range(steps):
+            st.graph.replay()
+        return st.latents.clone()
+
+    def _denoise_generic(self, latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance_scale,
+                         timesteps, eta, generator, callback, callback_steps):
+        """Protocol loop (reference :496-525) for foreign unet / scheduler objects."""
+        dt = self.unet.dtype
+        extra = self.prepare_extra_step_kwargs(generator, eta)
+        mask, masked_latents = mask.to(dt), masked_latents.to(dt)
+        latents = latents.to(dt)
+        for i, t in enumerate(timesteps):
+            x = torch.cat([latents] * 2)
+            x = self.scheduler.scale_model_input(x, t)
+            x9 = torch.cat([x, mask, masked_latents], dim=1).to(dt)
+            eps = self.unet(x9, t, class_labels=prior_embed, encoder_hidden_states=feature_f, my_pose_cond=pose_cond,
+                            return_dict=False)[0]
+            eu, ec = eps.chunk(2)
+            eps = eu + guidance_scale * (ec - eu)
+            latents = self.scheduler.step(eps, t, latents, **extra, return_dict=False)[0]
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        return latents.float()

@@ -1,0 +1,143 @@
+"""TEST INFRASTRUCTURE ONLY: torch-CPU stand-ins for the `pcdms_b200.ops` entry points, used to exercise the HOST logic
+(weight packing, topology walk, skip bookkeeping, conditioning layout, step tables) in the CPU-only test run.  They
+follow the documented semantics of each `pcdm_*` C-ABI function (include/pcdm_b200.h).  The product never imports this
+module: without the CUDA library `pcdms_b200.ops` raises.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+from oracle import blocks as OB
+
+
+def _rt(x, dtype):
+    return x.to(dtype)
+
+
+def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
+         out_f32=False, silu=False, bn=0):
+    x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
+    y = x @ w.float().t()
+    if geglu:
+        y = y + (bias if bias is not None else 0)
+        g = y.view(y.shape[0], -1, 64)
+        y = (g[..., :32] * F.gelu(g[..., 32:])).reshape(y.shape[0], -1)
+    else:
+        if bias is not None:
+            y = y + bias
+        if rowvec is not None:
+            y = y + rowvec.repeat_interleave(rows_per_image, 0)[: y.shape[0]]
+        if residual is not None:
+            y = y + residual.float()
+        if silu:
+            y = F.silu(y)
+    y = y if out_f32 else _rt(y, a.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, bn=0):
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    w = w_packed.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    if rowvec is not None:
+        y = y + rowvec[:, None, None, :]
+    if residual is not None:
+        y = y + residual.float()
+    y = y.contiguous()
+    return y if out_f32 else _rt(y, x.dtype)
+
+
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None):
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
+    shp = x.shape
+    y = F.group_norm(x.float().reshape(shp[0], -1, shp[-1]).transpose(1, 2), groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    return _rt(y.transpose(1, 2).reshape(shp).contiguous(), x1.dtype)
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    return _rt(F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps), x.dtype)
+
+
+def attention(q, k, v, B, heads, out=None, scale=0.125):
+    Sq, Skv = q.shape[0] // B, k.shape[0] // B
+    C = heads * 64
+    qh = q[:, :C].float().reshape(B, Sq, heads, 64).transpose(1, 2)
+    kh = k[:, :C].float().reshape(B, Skv, heads, 64).transpose(1, 2)
+    vh = v[:, :C].float().reshape(B, Skv, heads, 64).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return _rt((p @ vh).transpose(1, 2).reshape(B * Sq, C), q.dtype)
+
+
+def nchw_to_nhwc_pad(x, cpad, dtype, out=None):
+    B, C, H, W = x.shape
+    y = torch.zeros(B, H, W, cpad, dtype=dtype)
+    y[..., :C] = x.permute(0, 2, 3, 1).to(dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def nhwc_to_nchw(x, channels, out_dtype, out=None):
+    return x[..., :channels].permute(0, 3, 1, 2).contiguous().to(out_dtype)
+
+
+def timestep_embedding(t, B, dim, dtype, out=None):
+    tt = t.float().reshape(-1)
+    return OB.get_timestep_embedding(tt.expand(B) if tt.numel() == 1 else tt, dim, flip_sin_to_cos=True,
+                                     downscale_freq_shift=0).to(dtype)
+
+
+def upsample_nearest2x(x, out=None):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+
+
+def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+    n = latents.shape[0]
+    step = int(step_counter[0])
+    c = coef_table[step]
+    e = eps_rows[..., :4].float().permute(0, 3, 1, 2)
+    e = e[:n] + guidance_scale * (e[n:] - e[:n])
+    x0 = (latents - c[1] * e) * c[0]
+    latents.copy_(c[2] * x0 + c[3] * e)
+    x9[..., :4] = torch.cat([latents, latents]).permute(0, 2, 3, 1).to(x9.dtype)
+    step_counter[0] = step + 1
+    if t_table is not None and t_cur is not None:
+        t_cur[0] = t_table[step + 1]
+
+
+def add_noise(x0, noise, alphas_cumprod, timesteps, out=None):
+    a = alphas_cumprod[timesteps].view(-1, *([1] * (x0.dim() - 1)))
+    return (a.sqrt() * x0.float() + (1 - a).sqrt() * noise.float()).to(x0.dtype)
+
+
+def ddim_step(model_output, sample, coefs, out=None):
+    x0 = (sample.float() - coefs[1] * model_output.float()) * coefs[0]
+    return (coefs[2] * x0 + coefs[3] * model_output.float()).to(sample.dtype)
+
+
+_NAMES = ["gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
+          "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step"]
+
+
+@contextlib.contextmanager
+def patched():
+    """Temporarily route pcdms_b200.ops.<fn> to the CPU stand-ins above (tests only)."""
+    from pcdms_b200 import ops
+    saved = {n: getattr(ops, n) for n in _NAMES}
+    try:
+        for n in _NAMES:
+            setattr(ops, n, globals()[n])
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

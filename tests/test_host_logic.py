@@ -1,0 +1,144 @@
+"""CPU tests of the HOST side of the product: weight packing, topology walk, skip bookkeeping, conditioning layout and
+step tables — with the CUDA kernels replaced by the torch stand-ins of tests/mock_ops.py (each follows the documented
+semantics of its C-ABI entry point).  What these tests prove is that *given correct kernels* the orchestration in
+pcdms_b200/{unet,pipeline,scheduler}.py reproduces the oracle; the kernels themselves are checked on the GPU
+(tests/test_*_gpu.py)."""
+from dataclasses import asdict
+
+import pytest
+import torch
+
+from oracle.factory import make_inputs, make_unet, make_unet_inputs
+from oracle.pipeline import denoise_loop, prepare_conditioning
+from oracle.schedulers import OracleDDIMScheduler
+from oracle.unet import UNetConfig
+from pcdms_b200.pipeline import B200Stage2InpaintPipeline
+from pcdms_b200.scheduler import B200DDIMScheduler
+from pcdms_b200.unet import B200AttnProcessor, B200UNet2DConditionModel
+from tests import mock_ops
+
+
+def _models(cfg, dtype=torch.float32, seed=0):
+    o = make_unet(cfg, seed=seed)
+    m = B200UNet2DConditionModel(dtype=dtype, device="cpu", **asdict(cfg))
+    m.load_state_dict(o.state_dict())
+    return o, m
+
+
+def _forward(m, cfg, i, t):
+    x = mock_ops.nchw_to_nhwc_pad(i["sample"], 64, m.dtype)
+    kv = m.context_kv(i["encoder_hidden_states"])
+    pose = mock_ops.nchw_to_nhwc_pad(i["my_pose_cond"], i["my_pose_cond"].shape[1], m.dtype) if cfg.use_pose_cond else None
+    rows = m.forward_nhwc(x, torch.tensor([float(t)]), kv, i.get("class_labels"), pose)
+    return mock_ops.nhwc_to_nchw(rows, cfg.out_channels, torch.float32)
+
+
+@pytest.mark.parametrize("stage2", [True, False])
+def test_unet_orchestration_matches_oracle(stage2):
+    cfg = UNetConfig.tiny() if stage2 else UNetConfig.tiny(in_channels=8, stage2=False)
+    o, m = _models(cfg)
+    i = make_unet_inputs(cfg, batch=2, h=16, w=32, s_kv=9)
+    want = o(i["sample"], 981, i["encoder_hidden_states"], class_labels=i.get("class_labels"),
+             my_pose_cond=i.get("my_pose_cond"))[0]
+    with mock_ops.patched():
+        got = _forward(m, cfg, i, 981)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_unet_surface():
+    cfg = UNetConfig.tiny()
+    _, m = _models(cfg)
+    assert m.config.in_channels == 9 and m.config.class_embed_type == "projection"
+    assert m.config._diffusers_version and m.config.sample_size == 32
+    assert len(m.attn_processors) == 32
+    assert all(k.endswith(".processor") for k in m.attn_processors)
+    m.set_default_attn_processor()
+    m.set_attn_processor({k: B200AttnProcessor() for k in m.attn_processors})
+    with pytest.raises(ValueError):
+        m.set_attn_processor({"x": B200AttnProcessor()})
+    m.enable_xformers_memory_efficient_attention()
+    assert m.dtype == torch.float32 and m.device.type == "cpu"
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 9, 8, 16), 1, torch.zeros(1, 3, 128), attention_mask=torch.ones(1, 3))
+    with pytest.raises(RuntimeError):  # no CPU compute path
+        m(torch.zeros(1, 9, 8, 16), 1, torch.zeros(1, 3, 128), class_labels=torch.zeros(1, 1, 128),
+          my_pose_cond=torch.zeros(1, 64, 8, 16))
+    sd = make_unet(cfg).state_dict()
+    sd.pop("conv_out.bias")
+    with pytest.raises(RuntimeError):
+        B200UNet2DConditionModel(dtype=torch.float16, device="cpu", **asdict(cfg)).load_state_dict(sd)
+    with pytest.raises(NotImplementedError):
+        B200UNet2DConditionModel(device="cpu", use_linear_projection=False)
+
+
+def test_full_size_topology_keys():
+    for cfg, n in ((UNetConfig.stage2(), 690), (UNetConfig.stage3(), 686)):
+        m = B200UNet2DConditionModel(device="cpu", **asdict(cfg))
+        assert len(m.expected_keys()) == n
+        assert m._temb_total == 20160
+        assert [c for _, _, c in m._resnets].count(320) == 5  # 2 down + 3 up at the 320 level
+
+
+def test_custom_attention_processor_is_called():
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg)
+    calls = []
+
+    class Spy:
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+            calls.append(encoder_hidden_states is not None)
+            return attn.fused_forward(hidden_states, encoder_hidden_states)
+
+    m.set_attn_processor(Spy())
+    i = make_unet_inputs(cfg, batch=1, h=8, w=16, s_kv=5)
+    want = o(i["sample"], 5, i["encoder_hidden_states"], class_labels=i["class_labels"],
+             my_pose_cond=i["my_pose_cond"])[0]
+    with mock_ops.patched():
+        got = _forward(m, cfg, i, 5)
+    assert len(calls) == 32 and sum(calls) == 16
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_pipeline_orchestration_matches_oracle_loop():
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg)
+    pin = make_inputs(cfg, n=2, h=8, w=16, s_kv=6)
+    cond = prepare_conditioning(s_img_proj_f=pin["s_img_proj_f"], pred_t_img_embed=pin["pred_t_img_embed"],
+                                st_pose_f=pin["st_pose_f"], masked_latents=pin["masked_latents"], height=pin["height"],
+                                width=pin["width"], num_images_per_prompt=2, guidance_scale=2.0)
+    want = denoise_loop(o, OracleDDIMScheduler(), latents=pin["latents"], cond=cond, num_inference_steps=5,
+                        guidance_scale=2.0)
+    pipe = B200Stage2InpaintPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    pipe.use_cuda_graph = False
+    with mock_ops.patched():
+        for _ in range(2):  # second call re-uses the cached static buffers
+            got = pipe(height=pin["height"], width=pin["width"], num_inference_steps=5, guidance_scale=2.0,
+                       num_images_per_prompt=2, latents=pin["latents"], output_type="latent",
+                       s_img_proj_f=pin["s_img_proj_f"], st_pose_f=pin["st_pose_f"],
+                       pred_t_img_embed=pin["pred_t_img_embed"], masked_latents=pin["masked_latents"]).images
+            torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-5)
+    with pytest.raises(ValueError):
+        pipe(height=65, width=128, s_img_proj_f=pin["s_img_proj_f"], guidance_scale=2.0)
+    with pytest.raises(NotImplementedError):
+        pipe(height=64, width=128, s_img_proj_f=pin["s_img_proj_f"], guidance_scale=1.0)
+
+
+def test_scheduler_protocol_and_tables():
+    s, o = B200DDIMScheduler(), OracleDDIMScheduler()
+    s.set_timesteps(50)
+    o.set_timesteps(50)
+    assert s.timesteps.tolist() == o.timesteps.tolist() == list(range(981, 0, -20))
+    assert s.init_noise_sigma == 1.0 and s.order == 1 and s.config.steps_offset == 1 and not s.config.clip_sample
+    import inspect
+    assert {"eta", "generator"} <= set(inspect.signature(s.step).parameters)
+    x, e = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
+    tab = s.coefficient_table("cpu")
+    assert tab.shape == (50, 4)
+    for row, t in ((0, 981), (49, 1)):
+        c = tab[row]
+        want = o.step(e, t, x, return_dict=False)[0]
+        got = c[2] * (x - c[1] * e) * c[0] + c[3] * e
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        s.step(e, 981, x)  # CPU tensors: no fallback
+    assert torch.equal(s.scale_model_input(x, 3), x)
