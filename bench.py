@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — stage-2 256x256 50-step DDIM images/sec on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200-native path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+A bench "step" is one pass of the hot path over one batch: ONE pipeline call of BASELINE config 2 — 8 images
+(num_images_per_prompt = 8, CFG => UNet batch 16), 256x256 targets (512x256 canvas => 32x64 latents), 258 conditioning
+tokens, 50 DDIM steps, guidance 2.0, bf16, synthetic inputs + random weights of the real SD-2.1 stage-2 architecture.
+
+  value : images/sec with inputs resident in HBM (50 CUDA-graph replays per step + state reset), CUDA events.
+  e2e   : the same through the public `B200Stage2InpaintPipeline.__call__` with HOST (pinned) inputs — H2D of every
+          input, conditioning set-up (cross-attention K/V projection), 50 replays, D2H of the final latents.
+  roofline : the dominant kernel (implicit-GEMM conv3x3 on tcgen05): algorithmic FLOPs / CUDA-event time per launch,
+          measured live in an instrumented eager pass over one UNet evaluation (events on the launching stream).
+  cpu_baseline : the CPU oracle port (torch fp32, all host threads) on a bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): rank 0 packs the weights, ONE NCCL broadcast ships the arena to the other ranks,
+then every rank denoises its own independent batch (weak scaling, no collective in the loop); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_IMAGES, LAT_H, LAT_W, S_KV, DDIM_STEPS, GUIDANCE = 8, 32, 64, 258, 50, 2.0
+TFLOP_PER_UNET_FWD = 6.192           # B = 16 rows at 32x64, S_kv 258
+WORKLOAD = "stage2 inpaint, batch 8, 256x256 (32x64 latents), 258 tokens, 50 DDIM steps, guidance 2.0"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p.get("bf16_tflops"), sustained=p.get("bf16_tflops_sustained"), hbm=p.get("hbm_gbs"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline leg (the only places bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_unet_step_seconds(n_timed: int, n_warm: int, batch_images: int = N_IMAGES):
+    """Time CFG UNet evaluations of the CPU oracle (torch fp32, all host threads) at the bench workload's shapes."""
+    from oracle.factory import make_unet, make_unet_inputs
+    from oracle.unet import UNetConfig
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = UNetConfig.stage2()
+    model = make_unet(cfg, seed=0)
+    i = make_unet_inputs(cfg, batch=2 * batch_images, h=LAT_H, w=LAT_W, s_kv=S_KV)
+    times = []
+    with torch.no_grad():
+        for k in range(n_warm + n_timed):
+            t0 = time.perf_counter()
+            model(i["sample"], 981 - 20 * k, i["encoder_hidden_states"], class_labels=i["class_labels"],
+                  my_pose_cond=i["my_pose_cond"])
+            dt = time.perf_counter() - t0
+            if k >= n_warm:
+                times.append(dt)
+    return times, cores
+
+
+def run_reference(args):
+    """`--impl reference`: the reference algorithm's CPU implementation (the oracle port: the reference itself needs
+    diffusers==0.24.0, which is not installable here) on the same config and metric.  Each step is a bounded sample:
+    ONE CFG UNet evaluation of the 8-image batch (1/50 of a full 50-step pipeline call); images/sec extrapolates x50
+    (per-step cost is timestep-invariant; the scheduler update is < 1e-4 of it)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1)
+    times, cores = cpu_unet_step_seconds(args.steps, warm)
+    total = sum(times)
+    per_call = total / len(times) * DDIM_STEPS
+    value = N_IMAGES / per_call
+    sample = f"{len(times)} CFG UNet evaluations at B=16 (8 images), extrapolated x{DDIM_STEPS} DDIM steps"
+    line = {
+        "impl": "reference", "metric": "stage2_256x256_ddim50_images_per_sec", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": per_call * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": N_IMAGES, "ddim_steps": DDIM_STEPS,
+                   "device": "host CPU (torch fp32)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "unet_step_ms": total / len(times) * 1e3, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def host_inputs(rank: int, d: int, c0: int):
+    g = torch.Generator().manual_seed(42 + 1000 * rank)
+
+    def pin(t):
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    masked = torch.randn((1, 4, LAT_H, LAT_W), generator=g)
+    masked[..., LAT_W // 2:] = 0.0
+    return dict(latents=pin(torch.randn((N_IMAGES, 4, LAT_H, LAT_W), generator=g)), masked_latents=pin(masked),
+                st_pose_f=pin(0.1 * torch.randn((1, c0, LAT_H, LAT_W), generator=g)),
+                s_img_proj_f=pin(torch.randn((1, S_KV - 1, d), generator=g)),
+                pred_t_img_embed=pin(torch.randn((1, 1, d), generator=g)))
+
+
+def roofline_probe(unet, pipe_state, peaks):
+    """Instrumented eager pass over ONE UNet evaluation: CUDA events around every conv / GEMM / attention launch on the
+    launching stream; returns per-class algorithmic FLOPs and time."""
+    from pcdms_b200 import ops
+    stats = {}
+    stream = torch.cuda.current_stream()
+    pending = []
+
+    def wrap(name, fn, flops_of):
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = fn(*a, **k)
+            e1.record(stream)
+            pending.append((name, flops_of(*a, **k), e0, e1))
+            return out
+        return inner
+
+    def conv_flops(x, w, *a, **k):
+        B, H, W, cin = x.shape
+        s = k.get("stride", 1)
+        real_cin = 9 if cin == 64 and w.shape[0] == unet.config.block_out_channels[0] and unet.config.in_channels < 64 and x is pipe_state.x9 else cin
+        real_cout = unet.config.out_channels if k.get("out_f32") else w.shape[0]
+        return 2.0 * B * (H // s) * (W // s) * real_cout * 9 * real_cin
+
+    def gemm_flops(a_, w, *a, **k):
+        return 2.0 * a_.shape[0] * w.shape[0] * w.shape[1]
+
+    def attn_flops(q, k_, v, B, heads, *a, **k):
+        return 4.0 * B * heads * (q.shape[0] // B) * (k_.shape[0] // B) * 64
+
+    saved = (ops.conv3x3, ops.gemm, ops.attention)
+    ops.conv3x3 = wrap("conv3x3_igemm", saved[0], conv_flops)
+    ops.gemm = wrap("linear_gemm", saved[1], gemm_flops)
+    ops.attention = wrap("attention", saved[2], attn_flops)
+    try:
+        for _ in range(2):
+            pending.clear()
+            unet.forward_nhwc(pipe_state.x9, pipe_state.t_cur, pipe_state.kv, pipe_state.cls, pipe_state.pose)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3, ops.gemm, ops.attention = saved
+    for name, fl, e0, e1 in pending:
+        s = stats.setdefault(name, dict(flops=0.0, ms=0.0, launches=0))
+        s["flops"] += fl
+        s["ms"] += e0.elapsed_time(e1)
+        s["launches"] += 1
+    for s in stats.values():
+        s["tflops"] = s["flops"] / (s["ms"] * 1e-3) / 1e12 if s["ms"] > 0 else None
+        s["frac_of_burst_peak"] = s["tflops"] / peaks["burst"] if s["tflops"] else None
+    return stats
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from pcdms_b200 import lib as plib
+    from pcdms_b200.pipeline import B200Stage2InpaintPipeline
+    from pcdms_b200.scheduler import B200DDIMScheduler
+    from pcdms_b200.unet import B200UNet2DConditionModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    dt = torch.bfloat16
+
+    stage2 = dict(in_channels=9, class_embed_type="projection", projection_class_embeddings_input_dim=1024)
+    unet = B200UNet2DConditionModel(dtype=dt, device=dev, **stage2)
+    t0 = time.perf_counter()
+    if rank == 0:
+        unet.load_state_dict(unet.synthetic_state_dict(seed=0))
+        unet.consolidate()
+    bcast_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        nbytes = unet.broadcast_weights(src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+    load_s = time.perf_counter() - t0
+    pipe = B200Stage2InpaintPipeline(vae=None, unet=unet, scheduler=B200DDIMScheduler())
+    hin = host_inputs(rank, unet.config.cross_attention_dim, unet.config.block_out_channels[0])
+    h2d = sum(t.numel() * t.element_size() for t in hin.values())
+    d2h = N_IMAGES * 4 * LAT_H * LAT_W * 4
+    out_host = torch.empty((N_IMAGES, 4, LAT_H, LAT_W), dtype=torch.float32).pin_memory()
+
+    def e2e_call():
+        out = pipe(height=LAT_H * 8, width=LAT_W * 8, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE,
+                   num_images_per_prompt=N_IMAGES, latents=hin["latents"], output_type="latent",
+                   s_img_proj_f=hin["s_img_proj_f"], st_pose_f=hin["st_pose_f"],
+                   pred_t_img_embed=hin["pred_t_img_embed"], masked_latents=hin["masked_latents"]).images
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - w0) * 1e3
+        ms = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t[0]), float(t[1])
+
+    # ---- warm-up: also builds + captures the graph --------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        e2e_call()
+    torch.cuda.synchronize()
+    state = next(iter(pipe._graphs.values()))
+    launches_per_unet_step = state.launches_per_step
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- e2e: host inputs -> pipeline __call__ -> host latents ------------------------------------------------------
+    launches0 = plib.launch_count
+    e2e_ms, e2e_wall = timed(e2e_call, args.steps)
+    setup_launches = (plib.launch_count - launches0) // max(args.steps, 1)
+    # ---- value: inputs resident in HBM, the denoising loop only ---------------------------------------------------------
+    res_ms, _ = timed(lambda: pipe.replay_fused(state), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    images = N_IMAGES * world * args.steps
+    value = images / (res_ms * 1e-3)
+    e2e_value = images / (max(e2e_ms, e2e_wall) * 1e-3)   # events can miss host-side gaps: take the slower clock
+    unet_step_ms = res_ms / args.steps / DDIM_STEPS
+    step_tflops = TFLOP_PER_UNET_FWD / (unet_step_ms * 1e-3)
+
+    probe = roofline_probe(unet, state, peaks)
+    conv = probe.get("conv3x3_igemm", {})
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("conv3x3_igemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "igemm_kernel (conv3x3 implicit GEMM, tcgen05)", "bound": "tensor",
+        "achieved": conv.get("tflops"), "peak": peaks["burst"], "unit": "TFLOP/s",
+        "frac": (conv.get("tflops") / peaks["burst"]) if conv.get("tflops") else None, "traffic": traffic,
+        "peak_source": peaks["source"] + "; burst bf16 figure (kernels timed one launch at a time)",
+        "launches_per_unet_step": conv.get("launches"),
+        "algorithmic_flops_per_unet_step": conv.get("flops"),
+        "avg_launch_ms": (conv.get("ms") / conv.get("launches")) if conv.get("launches") else None,
+        "other_kernels": {k: {kk: v[kk] for kk in ("tflops", "frac_of_burst_peak", "launches", "ms")}
+                          for k, v in probe.items() if k != "conv3x3_igemm"},
+        "whole_unet_step": {"tflops": step_tflops, "frac_of_sustained_peak": step_tflops / peaks["sustained"],
+                            "peak_sustained": peaks["sustained"]},
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            times, cores = cpu_unet_step_seconds(1, 0)
+            per_call = times[0] * DDIM_STEPS
+            cpu = {"value": N_IMAGES / per_call, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"1 CFG UNet evaluation at B=16 (8 images) = {times[0]:.1f} s, extrapolated x{DDIM_STEPS} "
+                             f"DDIM steps (oracle port, torch fp32)"}
+        except Exception as ex:  # the baseline must never take the measured line down with it
+            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {type(ex).__name__}: {ex}"}
+
+    line = {
+        "metric": "stage2_256x256_ddim50_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": N_IMAGES * world, "images_per_rank": N_IMAGES,
+                   "ddim_steps": DDIM_STEPS, "parallelism": f"replicas x{world} (independent batch per rank)",
+                   "l2": "no flush needed: each UNet evaluation streams 1.74 GB of weights + >0.5 GB of activations, "
+                         ">> 126 MB L2",
+                   "weights": "random init, real SD-2.1 stage-2 architecture (868.9 M params)"},
+        "unet_step_ms": unet_step_ms,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": max(e2e_ms, e2e_wall) / args.steps,
+                "what": "B200Stage2InpaintPipeline.__call__: pinned host inputs -> H2D -> conditioning + K/V "
+                        "projection -> 50 graph replays -> D2H of the final latents"},
+        "gpu_launches": (launches_per_unet_step * DDIM_STEPS + setup_launches) * args.steps * 2,
+        "gpu_launches_detail": {"kernels_per_unet_step_graph": launches_per_unet_step,
+                                "graph_replays_per_step": DDIM_STEPS, "setup_kernels_per_call": setup_launches,
+                                "timed_regions": 2},
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "weights_broadcast_ms": bcast_ms, "model_build_s": load_s,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

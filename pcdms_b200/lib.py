@@ -26,6 +26,12 @@ class PcdmError(RuntimeError):
 
 
 _lib = None
+launch_count = 0  # kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
+
+
+def count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
 
 
 def declared_symbols() -> list[str]:
@@ -52,7 +58,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     return lib
 
 
-def check(rc: int) -> None:
+def check(rc: int, kernels: int = 1) -> None:
+    global launch_count
+    launch_count += kernels
     if rc != 0:
         raise PcdmError(rc, load().pcdm_last_error().decode(errors="replace"))
 

@@ -129,7 +129,7 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None,
     rc = lib.pcdm_groupnorm(_l.ptr(x1), _l.ptr(x2), C.c_int(C1), _l.ptr(out), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)),
                             C.c_float(eps), C.c_int(B), C.c_int(HW), C.c_int(Ct), C.c_int(groups), C.c_int(_dt(x1)),
                             C.c_int(_l.FLAG_SILU if silu else 0), _l.ptr(workspace), _stream(x1))
-    _l.check(rc)
+    _l.check(rc, kernels=2)
     return out
 
 

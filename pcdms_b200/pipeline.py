@@ -175,41 +175,42 @@ class B200Stage2InpaintPipeline:
 
     # ------------------------------------------------------------------------------------------------------------
     def _denoise_fused(self, latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance, steps):
+        st = self.prepare_fused(latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance, steps)
+        self.replay_fused(st)
+        return st.latents.clone()
+
+    def prepare_fused(self, latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance, steps):
+        """Per-call set-up of the fused loop: lays the conditioning out in the graph's static buffers (NHWC, 16-bit),
+        projects the cross-attention K/V once, uploads the step tables and (re)captures the one-step CUDA graph when
+        the shapes / guidance / step count changed.  Returns the state object `replay_fused` consumes."""
         unet, sch = self.unet, self.scheduler
         dev, dt = unet.device, unet.dtype
         n, _, h, w = latents.shape
         B = 2 * n
-        # static buffers of the (possibly cached) graph
         key = (n, h, w, feature_f.shape[1], dt)
         st = self._graphs.get(key)
         if st is None:
             st = SimpleNamespace(
                 x9=torch.zeros((B, h, w, 64), device=dev, dtype=dt),
+                x9_init=torch.zeros((B, h, w, 64), device=dev, dtype=dt),
                 latents=torch.empty((n, 4, h, w), device=dev, dtype=torch.float32),
+                latents_init=torch.empty((n, 4, h, w), device=dev, dtype=torch.float32),
                 pose=torch.empty((B, h, w, pose_cond.shape[1]), device=dev, dtype=dt),
                 cls=torch.empty((B, prior_embed.shape[-1]), device=dev, dtype=dt),
                 t_cur=torch.zeros(1, device=dev, dtype=torch.float32),
                 counter=torch.zeros(2, device=dev, dtype=torch.int32),
-                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None)
+                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None, launches_per_step=0)
             self._graphs[key] = st
-        # per-call state
         x9_nchw = torch.cat([latents, latents], dim=0)
         x9_nchw = torch.cat([x9_nchw, mask, masked_latents], dim=1).contiguous()                # ref :499-501
-        ops.nchw_to_nhwc_pad(x9_nchw, 64, dt, out=st.x9)
-        st.latents.copy_(latents)
+        ops.nchw_to_nhwc_pad(x9_nchw, 64, dt, out=st.x9_init)
+        st.latents_init.copy_(latents)
         ops.nchw_to_nhwc_pad(pose_cond.contiguous(), pose_cond.shape[1], dt, out=st.pose)
         st.cls.copy_(prior_embed.reshape(B, -1))
         first = st.kv is None
         st.kv = unet.context_kv(feature_f, out=st.kv)   # K/V GEMMs write straight into the graph's static buffers
         coef = sch.coefficient_table(dev)
         t_table = torch.cat([sch.timesteps.to(dev, torch.float32), torch.zeros(1, device=dev)]).contiguous()
-        st.counter.zero_()
-        st.t_cur.copy_(t_table[:1])
-
-        def one_step():
-            eps_rows = unet.forward_nhwc(st.x9, st.t_cur, st.kv, st.cls, st.pose)
-            ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, guidance, st.t_table, st.t_cur)
-
         rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps)
         st.guidance, st.steps = guidance, steps
         if st.coef is None or st.coef.shape != coef.shape:
@@ -218,31 +219,43 @@ class B200Stage2InpaintPipeline:
         else:
             st.coef.copy_(coef)
             st.t_table.copy_(t_table)
-        if not self.use_cuda_graph:
-            for _ in range(steps):
-                one_step()
-            return st.latents.clone()
-        if rebuild:
+        if self.use_cuda_graph and rebuild:
             # warm-up on a side stream (allocator + lazy kernel attribute set-up), then capture
+            self._reset_state(st)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                one_step()
+                self._one_step(st)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            # the warm-up consumed step 0: restore state
-            st.latents.copy_(latents)
-            ops.nchw_to_nhwc_pad(x9_nchw, 64, dt, out=st.x9)
-            st.counter.zero_()
-            st.t_cur.copy_(t_table[:1])
+            from . import lib as _l
+            before = _l.launch_count
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                one_step()
+                self._one_step(st)
+            st.launches_per_step = _l.launch_count - before
             st.graph = g
-            # capture does not execute: state is still at step 0
-        for _ in range(steps):
-            st.graph.replay()
-        return st.latents.clone()
+        return st
+
+    def _one_step(self, st):
+        eps_rows = self.unet.forward_nhwc(st.x9, st.t_cur, st.kv, st.cls, st.pose)
+        ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
+
+    def _reset_state(self, st):
+        st.x9.copy_(st.x9_init)
+        st.latents.copy_(st.latents_init)
+        st.counter.zero_()
+        st.t_cur.copy_(st.t_table[:1])
+
+    def replay_fused(self, st):
+        """The denoising loop proper (reference :496-525): `steps` replays of the captured one-step graph."""
+        self._reset_state(st)
+        if self.use_cuda_graph:
+            for _ in range(st.steps):
+                st.graph.replay()
+        else:
+            for _ in range(st.steps):
+                self._one_step(st)
 
     def _denoise_generic(self, latents, mask, masked_latents, pose_cond, feature_f, prior_embed, guidance_scale,
                          timesteps, eta, generator, callback, callback_steps):

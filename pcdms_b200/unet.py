@@ -344,6 +344,75 @@ class B200UNet2DConditionModel:
                 keys += [f"{op[1]}.weight", f"{op[1]}.bias"]
         return keys
 
+    def state_dict_shapes(self) -> Dict[str, tuple]:
+        """diffusers key -> shape for this config (what a checkpoint must contain)."""
+        cfg = self.config
+        ch0 = cfg.block_out_channels[0]
+        ted = 4 * ch0
+        D = cfg.cross_attention_dim
+        sh: Dict[str, tuple] = {}
+
+        def wb(name, wshape):
+            sh[f"{name}.weight"] = tuple(wshape)
+            sh[f"{name}.bias"] = (wshape[0],)
+
+        wb("conv_in", (ch0, cfg.in_channels, 3, 3))
+        wb("conv_out", (cfg.out_channels, ch0, 3, 3))
+        wb("conv_norm_out", (ch0,))
+        wb("time_embedding.linear_1", (ted, ch0))
+        wb("time_embedding.linear_2", (ted, ted))
+        if cfg.class_embed_type == "projection":
+            wb("class_embedding.linear_1", (ted, cfg.projection_class_embeddings_input_dim))
+            wb("class_embedding.linear_2", (ted, ted))
+        for op in self._plan:
+            if op[0] == "res":
+                _, p, cin, cout = op
+                wb(f"{p}.norm1", (cin,))
+                wb(f"{p}.conv1", (cout, cin, 3, 3))
+                wb(f"{p}.time_emb_proj", (cout, ted))
+                wb(f"{p}.norm2", (cout,))
+                wb(f"{p}.conv2", (cout, cout, 3, 3))
+                if cin != cout:
+                    wb(f"{p}.conv_shortcut", (cout, cin, 1, 1))
+            elif op[0] == "attn":
+                p, c = op[1], op[2]
+                t = f"{p}.transformer_blocks.0"
+                wb(f"{p}.norm", (c,))
+                wb(f"{p}.proj_in", (c, c))
+                wb(f"{p}.proj_out", (c, c))
+                for n in ("norm1", "norm2", "norm3"):
+                    wb(f"{t}.{n}", (c,))
+                wb(f"{t}.ff.net.0.proj", (8 * c, c))
+                wb(f"{t}.ff.net.2", (c, 4 * c))
+                for a_, kdim in (("attn1", c), ("attn2", D)):
+                    sh[f"{t}.{a_}.to_q.weight"] = (c, c)
+                    sh[f"{t}.{a_}.to_k.weight"] = (c, kdim)
+                    sh[f"{t}.{a_}.to_v.weight"] = (c, kdim)
+                    wb(f"{t}.{a_}.to_out.0", (c, c))
+            elif op[0] in ("down", "up"):
+                wb(op[1], (op[2], op[2], 3, 3))
+        return sh
+
+    def synthetic_state_dict(self, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
+        """Random weights of the real shapes, generated on `device` (default: the model's): fan-in scaled normals for
+        weights, small biases, near-identity norm affines.  Stand-in for the SD-2.1 / PCDMs checkpoints, which cannot
+        be downloaded here; used by bench.py and smoke tests (NOT the oracle's factory, which is test infrastructure)."""
+        dev = torch.device(device) if device is not None else self._device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd = {}
+        for k, shp in self.state_dict_shapes().items():
+            is_norm = (".norm" in k or k.startswith("conv_norm_out"))
+            if k.endswith(".weight") and not is_norm:
+                fan_in = 1
+                for d in shp[1:]:
+                    fan_in *= d
+                sd[k] = torch.randn(shp, generator=g, device=dev) * (fan_in ** -0.5)
+            elif k.endswith(".weight"):
+                sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g, device=dev)
+            else:
+                sd[k] = 0.05 * torch.randn(shp, generator=g, device=dev)
+        return sd
+
     # ------------------------------------------------------------------------------------------------------------
     # weights: diffusers state dict -> packed device tensors
     # ------------------------------------------------------------------------------------------------------------
@@ -356,6 +425,12 @@ class B200UNet2DConditionModel:
         if strict and (missing or unexpected):
             raise RuntimeError(f"Error(s) in loading state_dict for B200UNet2DConditionModel: missing {missing[:5]}"
                                f"{'...' if len(missing) > 5 else ''} unexpected {unexpected[:5]}")
+        shapes = self.state_dict_shapes()
+        for k, shp in shapes.items():
+            if k in state_dict and tuple(state_dict[k].shape) != shp:
+                if k == "conv_in.weight" and ignore_mismatched_sizes:
+                    continue
+                raise RuntimeError(f"size mismatch for {k}: checkpoint {tuple(state_dict[k].shape)} vs model {shp}")
         sd = state_dict
         w = self._w
 
@@ -432,6 +507,50 @@ class B200UNet2DConditionModel:
 
     def weight_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._w.values())
+
+    # -- packed weight arena: one contiguous device buffer, so N ranks need ONE ncclBroadcast ----------------------
+    def consolidate(self):
+        """Move every packed tensor into one contiguous arena (256-byte aligned slots); returns the arena."""
+        layout, off = [], 0
+        for k, t in self._w.items():
+            nbytes = t.numel() * t.element_size()
+            layout.append((k, tuple(t.shape), t.dtype, off, nbytes))
+            off = (off + nbytes + 255) // 256 * 256
+        arena = torch.empty(off, dtype=torch.uint8, device=self._device)
+        self._adopt(arena, layout, copy_from=self._w)
+        return arena
+
+    def _adopt(self, arena, layout, copy_from=None):
+        new = {}
+        for k, shape, dtype, off, nbytes in layout:
+            view = arena[off:off + nbytes].view(dtype).view(shape)
+            if copy_from is not None:
+                view.copy_(copy_from[k])
+            new[k] = view
+        self._w = new
+        self._arena, self._arena_layout = arena, layout
+        self._loaded = True
+        self._ctx_cache = None
+        self._pose_cache = None
+
+    def broadcast_weights(self, src: int = 0, group=None):
+        """Replaces the reference's per-rank `torch.load` of the full checkpoint (stage2_batchtest_inpaint_model.py:
+        103-104): rank `src` holds packed weights, every other rank receives the layout (object broadcast) and then
+        the arena itself with ONE NCCL broadcast over NVLink.  No collective is used after this."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        if rank == src:
+            if getattr(self, "_arena", None) is None:
+                self.consolidate()
+            meta = [self._arena_layout, self._arena.numel()]
+        else:
+            meta = [None, None]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        if rank != src:
+            arena = torch.empty(meta[1], dtype=torch.uint8, device=self._device)
+            self._adopt(arena, meta[0])
+        dist.broadcast(self._arena, src=src, group=group)
+        return self._arena.numel()
 
     # ------------------------------------------------------------------------------------------------------------
     # forward
