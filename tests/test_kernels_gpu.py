@@ -1,0 +1,201 @@
+"""GPU parity of every sm_100a kernel against the CPU oracle ops (torch fp32 on the SAME 16-bit-rounded inputs), called
+through the C ABI (pcdms_b200.ops -> libpcdm_b200.so).  Tolerance: rtol 1e-3 / atol 1e-4 (BASELINE north_star) for
+fp16 kernels whose only rounding is the final 16-bit store; attention additionally rounds the probabilities P to
+16 bits before the PV product (as every tensor-core flash attention does), so it gets 3x that; bf16 has 8x coarser
+mantissa than fp16, so bf16 runs use 8x the fp16 tolerance."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-4
+DTS = [torch.float16, torch.bfloat16]
+
+
+def tol(dt, mult=1.0):
+    k = mult * (8.0 if dt == torch.bfloat16 else 1.0)
+    return dict(rtol=RTOL * k, atol=ATOL * k)
+
+
+def close(got, want, dt, mult=1.0):
+    torch.testing.assert_close(got.float().cpu(), want.float(), **tol(dt, mult))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pcdms_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N,K,bn,kw", [
+    (256, 256, 128, 128, {}), (1000, 320, 320, 0, {"resid": True}), (4096, 1280, 1024, 256, {}),
+    (516, 640, 1024, 64, {"bias": False}), (300, 2560, 320, 0, {"geglu": True}), (512, 320, 960, 160, {"split": 640}),
+    (2, 1280, 320, 0, {"silu": True}), (4128, 640, 1024, 0, {"bias": False}),
+])
+def test_gemm(ops, dt, M, N, K, bn, kw):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dt)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt)
+    b = torch.randn(N, generator=g) if kw.get("bias", True) else None
+    r = torch.randn(M, N, generator=g).to(dt) if kw.get("resid") else None
+    ref = a.float() @ w.float().t()
+    if b is not None:
+        ref = ref + b
+    if r is not None:
+        ref = ref + r.float()
+    if kw.get("silu"):
+        ref = F.silu(ref)
+    wd, bd = w, b
+    if kw.get("geglu"):
+        h, gate = ref.chunk(2, dim=1)
+        ref = h * F.gelu(gate)
+        perm = ops.geglu_row_permutation(N // 2)
+        wd, bd = w[perm].contiguous(), b[perm].contiguous()
+    ad = a.cuda()
+    extra = {}
+    if kw.get("split"):
+        extra["a2"] = ad[:, kw["split"]:]
+        ad = ad[:, :kw["split"]]
+    out = ops.gemm(ad, wd.cuda(), bias=bd.cuda() if bd is not None else None,
+                   residual=r.cuda() if r is not None else None, geglu=bool(kw.get("geglu")),
+                   silu=bool(kw.get("silu")), bn=bn, **extra)
+    close(out, ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,extra", [
+    (2, 32, 64, 320, 320, 1, True), (2, 16, 32, 640, 640, 1, True), (2, 4, 8, 1280, 1280, 1, True),
+    (6, 4, 8, 128, 64, 1, True), (1, 64, 128, 64, 64, 1, False), (2, 16, 32, 320, 320, 2, False),
+    (3, 4, 8, 128, 128, 2, False), (2, 8, 16, 1920, 1280, 1, True), (2, 2, 4, 64, 32, 1, False),
+])
+def test_conv3x3(ops, dt, B, H, W, Cin, Cout, stride, extra):
+    g = torch.Generator().manual_seed(B * H + Cin)
+    x = torch.randn(B, Cin, H * stride, W * stride, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dt)
+    b = torch.randn(Cout, generator=g)
+    t = torch.randn(B, 3 * Cout, generator=g) if extra else None
+    r = torch.randn(B, Cout, H, W, generator=g).to(dt) if extra else None
+    ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1)
+    if extra:
+        ref = ref + t[:, Cout:2 * Cout, None, None] + r.float()
+    out = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_conv3x3_weight(w, dt).cuda(), bias=b.cuda(),
+                      rowvec=t.cuda()[:, Cout:2 * Cout] if extra else None,
+                      residual=r.permute(0, 2, 3, 1).contiguous().cuda() if extra else None, stride=stride)
+    close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+def test_conv3x3_rejects_unsupported_shapes(ops):
+    from pcdms_b200.lib import PcdmError
+    x = torch.zeros(1, 8, 24, 64, device="cuda", dtype=torch.float16)  # W = 24 does not divide 128
+    with pytest.raises(PcdmError):
+        ops.conv3x3(x, torch.zeros(64, 9 * 64, device="cuda", dtype=torch.float16))
+    with pytest.raises(PcdmError):  # Cin not a multiple of 64
+        ops.conv3x3(torch.zeros(1, 8, 16, 48, device="cuda", dtype=torch.float16),
+                    torch.zeros(64, 9 * 48, device="cuda", dtype=torch.float16))
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,H,W,C1,C2", [(2, 32, 64, 320, 0), (2, 16, 32, 1280, 640), (3, 4, 8, 1280, 1280),
+                                          (2, 8, 16, 640, 320), (1, 64, 128, 320, 0), (2, 2, 4, 64, 0)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_groupnorm(ops, dt, B, H, W, C1, C2, silu):
+    g = torch.Generator().manual_seed(C1 + C2 + H)
+    C = C1 + C2
+    x1 = (torch.randn(B, C1, H, W, generator=g) * 2 + 0.5).to(dt)
+    x2 = (torch.randn(B, C2, H, W, generator=g) - 0.3).to(dt) if C2 else None
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xc = torch.cat([x1, x2], 1) if C2 else x1
+    ref = F.group_norm(xc.float(), 32, gamma, beta, 1e-5)   # straddling groups: 1920/32 = 60 ch, 1280/60 not integral
+    if silu:
+        ref = F.silu(ref)
+    out = ops.groupnorm(x1.permute(0, 2, 3, 1).contiguous().cuda(), gamma.cuda(), beta.cuda(), 1e-5,
+                        x2=x2.permute(0, 2, 3, 1).contiguous().cuda() if C2 else None, silu=silu)
+    close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (77, 1280), (33, 64)])
+def test_layernorm(ops, dt, M, C):
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 3 + 1).to(dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    close(ops.layernorm(x.cuda(), gamma.cuda(), beta.cuda()), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,heads,Sq,Skv,sc", [
+    (2, 5, 2048, 2048, 1.0), (2, 10, 512, 512, 1.0), (2, 20, 128, 128, 1.0), (3, 20, 32, 32, 1.0),  # self (a9)
+    (2, 5, 2048, 258, 1.0), (2, 10, 512, 95, 1.0), (1, 20, 128, 257, 1.0),                          # cross
+    (1, 2, 384, 300, 4.0), (1, 1, 200, 130, 8.0), (1, 5, 8192, 8192, 1.0),                          # ragged / sharp / cfg 3
+])
+def test_attention(ops, dt, B, heads, Sq, Skv, sc):
+    g = torch.Generator().manual_seed(Sq + Skv + heads)
+    C = heads * 64
+    q = (torch.randn(B, Sq, C, generator=g) * sc).to(dt)
+    k = (torch.randn(B, Skv, C, generator=g) * sc).to(dt)
+    v = torch.randn(B, Skv, C, generator=g).to(dt)
+    qh, kh, vh = (t.float().view(B, -1, heads, 64).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, Sq, C)
+    if Sq == Skv:  # q/k/v as column slices of one fused projection buffer, like the UNet's self-attention
+        qkv = torch.cat([q, k, v], dim=-1).reshape(B * Sq, 3 * C).cuda()
+        out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
+    else:
+        out = ops.attention(q.reshape(B * Sq, C).cuda(), k.reshape(B * Skv, C).cuda(), v.reshape(B * Skv, C).cuda(),
+                            B, heads)
+    close(out.view(B, Sq, C), ref, dt, mult=3.0)
+
+
+def test_boundary_and_misc_kernels(ops):
+    from oracle import blocks as OB
+    for t in ([981.0], [1.0, 21.0, 501.0, 999.0]):
+        tt = torch.tensor(t)
+        ref = OB.Timesteps(320, True, 0)(tt.expand(4) if len(t) == 1 else tt)
+        out = ops.timestep_embedding(tt.cuda(), 4, 320, torch.float32)
+        torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+        out = ops.timestep_embedding(tt.cuda(), 4, 320, torch.float16)
+        torch.testing.assert_close(out.float().cpu(), ref, rtol=RTOL, atol=5e-4)  # fp16 store near |x| = 1
+    x = torch.randn(3, 9, 16, 32)
+    out = ops.nchw_to_nhwc_pad(x.cuda(), 64, torch.float16).cpu()
+    assert torch.equal(out[..., :9], x.permute(0, 2, 3, 1).half()) and out[..., 9:].abs().sum() == 0
+    y = torch.randn(3, 16, 32, 32)
+    assert torch.equal(ops.nhwc_to_nchw(y.cuda(), 4, torch.float32).cpu(), y[..., :4].permute(0, 3, 1, 2))
+    x = torch.randn(2, 4, 8, 128).half()
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(ops.upsample_nearest2x(x.cuda()).float().cpu(), ref)
+
+
+def test_fused_step_and_schedulers_match_oracle(ops):
+    from oracle.pipeline import cfg_combine
+    from oracle.schedulers import OracleDDIMScheduler, ddpm_add_noise
+    from pcdms_b200.scheduler import B200DDIMScheduler, B200DDPMScheduler
+    n, h, w = 2, 16, 32
+    sch, osch = B200DDIMScheduler(), OracleDDIMScheduler()
+    sch.set_timesteps(10)
+    osch.set_timesteps(10)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(n, 4, h, w, generator=g)
+    eps_rows = torch.randn(2 * n, h, w, 32, generator=g)
+    x9 = torch.zeros(2 * n, h, w, 64, dtype=torch.float16, device="cuda")
+    coef = sch.coefficient_table("cuda")
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    t_table = torch.cat([sch.timesteps.float(), torch.zeros(1)]).cuda()
+    t_cur = torch.zeros(1, device="cuda")
+    lat_d = lat.clone().cuda()
+    ref = lat.clone()
+    eps_nchw = eps_rows[..., :4].permute(0, 3, 1, 2)
+    for i, t in enumerate(osch.timesteps[:4]):
+        ops.cfg_ddim_step(eps_rows.cuda(), lat_d, x9, coef, counter, 2.0, t_table, t_cur)
+        ref = osch.step(cfg_combine(eps_nchw, 2.0), t, ref, return_dict=False)[0]
+        torch.testing.assert_close(lat_d.cpu(), ref, rtol=1e-5, atol=1e-5)
+        want9 = torch.cat([ref, ref]).permute(0, 2, 3, 1).half()
+        torch.testing.assert_close(x9[..., :4].cpu(), want9, rtol=RTOL, atol=ATOL)
+        assert counter.tolist() == [i + 1, 0] and t_cur.item() == float(osch.timesteps[i + 1])
+    e, s = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    out = sch.step(e.cuda(), 901, s.cuda(), return_dict=False)[0]
+    torch.testing.assert_close(out.cpu(), osch.step(e, 901, s, return_dict=False)[0], rtol=1e-5, atol=1e-5)
+    ts = torch.tensor([0, 500])
+    out = B200DDPMScheduler().add_noise(s.cuda(), e.cuda(), ts.cuda())
+    torch.testing.assert_close(out.cpu(), ddpm_add_noise(s, e, ts), rtol=1e-5, atol=1e-6)
