@@ -50,6 +50,10 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
               long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
               const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn, void* stream);
 
+/* Tuning / test hook for the two calls above: 0 = automatic, 1 = single-CTA 128-row tiles only, 2 = CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
+int pcdm_set_gemm_cta_group(int mode);
+
 /* torch.nn.Conv2d(Cin, Cout, 3, stride, padding=1) on NHWC activations, implicit GEMM (no im2col buffer).
  * Replaces conv_in, conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2), Upsample2D.conv and conv_out
  * (SURVEY.md §8a a4-a6, a10).
@@ -62,7 +66,9 @@ int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bi
 
 /* torch.nn.GroupNorm(groups, C, eps) (+ SiLU with PCDM_FLAG_SILU) over NHWC x = [x1 | x2] (x2 may be NULL; x1 then has
  * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out
- * (reference :817-819).  y: [B, HW, C].  workspace: pcdm_groupnorm_workspace_bytes(). */
+ * (reference :817-819).  y: [B, HW, C].  workspace: pcdm_groupnorm_workspace_bytes() bytes,
+ * zero-initialised once by the caller (it holds device counters the kernels return to zero); results are
+ * bit-reproducible run to run (fixed reduction order, no floating-point atomics). */
 long long pcdm_groupnorm_workspace_bytes(int B, int groups);
 int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta, float eps,
                    int B, int HW, int C, int groups, int dtype, int flags, void* workspace, void* stream);

@@ -1,15 +1,18 @@
 // K3 — fused multi-head attention, head_dim 64, no mask:  O = softmax(Q K^T / 8) V   (flash-style, online softmax).
 //
-// One CTA per (batch, head, 128-query tile).  Warp roles: warp 0 = TMA producer (Q once, then a 3-deep K/V ring),
-// warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = softmax (thread t owns query row t: with the
-// 32x32b TMEM access pattern a row's scores sit in one thread's registers, so row max / row sum need no shuffles).
+// One CTA per (batch, head, 128-query tile), TWO CTAs resident per SM: while one CTA's softmax warps work through a
+// score tile, the other CTA's MMAs own the tensor pipe (at d = 64 the exponentials, not the MMAs, are the scarce
+// resource: 16 ex2/clk/SM vs 128x128 scores per 512 tensor cycles).  192 threads: warp 0 = TMA producer (Q once, then
+// a 2-deep K/V ring) + TMEM allocator, warp 1 = tcgen05.mma issuer, warps 2-5 = softmax (thread t owns query row t:
+// with the 32x32b TMEM access pattern a row's scores sit in one thread, so row max / row sum need no shuffles).
 //
-// TMEM (512 columns):  S0,S1 : 2 x 128 fp32 score tiles (QK^T of block j+1 overlaps softmax of block j)
-//                      P0,P1 : 2 x 64 columns = 128 x 128 fp16/bf16 probabilities, fed to the PV MMA straight from
-//                              tensor memory (A operand in TMEM) — P never touches shared memory
-//                      O     : 64 fp32 columns, accumulated across KV blocks inside the tensor core
-// The running maximum is applied lazily: O/l are rescaled (by the softmax warps, TMEM round trip) only when a row's
-// maximum grows by more than 2^8, so most KV blocks need no correction; the final normalisation divides by l.
+// TMEM (256 columns per CTA):  S : 128 fp32 score columns            (QK^T, SS MMA)
+//                              P : 64 columns = 128 x 128 fp16/bf16 probabilities, consumed by the PV MMA straight
+//                                  from tensor memory (A operand in TMEM) — P never touches shared memory
+//                              O : 64 fp32 columns, accumulated across KV blocks inside the tensor core
+// Softmax is two passes over the TMEM score tile (row max, then exp/sum/pack) so the row never has to live in
+// registers at once (<= 128 registers/thread -> 2 CTAs/SM).  The running maximum is applied lazily: O and l are
+// rescaled (TMEM round trip by the softmax warps) only when a row's maximum grows by more than 2^8.
 // V is consumed in its natural [kv, d] layout as an MN-major B operand, K as a K-major B operand.
 //
 // Replaces xformers.memory_efficient_attention / F.scaled_dot_product_attention as enabled by the reference at
@@ -29,25 +32,28 @@ struct AttnParams {
   float scale_log2;    // softmax scale * log2(e)
 };
 
-constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
 constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + 1024 + 256;
-constexpr int ATT_TMEM_S = 0, ATT_TMEM_P = 256, ATT_TMEM_O = 384;
+constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_TMEM_S = 0, ATT_TMEM_P = 128, ATT_TMEM_O = 192;
 
 template <int DT>
-__global__ void __launch_bounds__(256, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + ATT_TILE_BYTES;  // stage s: K at s*2*TILE, V at s*2*TILE + TILE
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + ATT_KV_STAGES;
-  uint64_t* s_full = kv_empty + ATT_KV_STAGES;  // [2]
-  uint64_t* p_full = s_full + 2;                // [2]
-  uint64_t* pv_done = p_full + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* kv_full = bars + 1;                  // [2]
+  uint64_t* kv_empty = kv_full + ATT_KV_STAGES;  // [2]
+  uint64_t* s_full = kv_empty + ATT_KV_STAGES;   // MMA -> softmax: S_j landed
+  uint64_t* s_free = s_full + 1;                 // softmax -> MMA: S_j fully read (4 warp arrivals)
+  uint64_t* p_full = s_free + 1;                 // softmax -> MMA: P_j written, O corrected (4 warp arrivals)
+  uint64_t* pv_done = p_full + 1;                // MMA -> softmax: PV_j retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -55,68 +61,74 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(const __grid_constant
   const int h = bh % p.heads, b = bh / p.heads;
   const int n_kv = (p.Skv + 127) / 128;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    mbar_expect_tx(q_full, ATT_TILE_BYTES);
-    tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 128, h, b);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
-      mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-      tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
-      tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
-      if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 128, h, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int stage = j & 1;
+        mbar_wait(&kv_empty[stage], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
+        tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
+      }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
-    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
-    const uint32_t q_addr = smem_u32(sQ);
-    mbar_wait(q_full, 0);
-    auto issue_qk = [&](int j) {
-      const int stage = j % ATT_KV_STAGES;
-      mbar_wait(&kv_full[stage], (uint32_t)((j / ATT_KV_STAGES) & 1));
-      tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
+      constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      mbar_wait(q_full, 0);
+      auto issue_qk = [&](int j) {
+        const int stage = j & 1;
+        mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
+        if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax has read S_{j-1} out of the score columns
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + ATT_TMEM_S + (j & 1) * 128, make_desc_sw128(q_addr + k * 32, 1024, 16),
-                make_desc_sw128(k_addr + k * 32, 1024, 16), idesc_qk, k != 0);
-      tc_commit(&s_full[j & 1]);
-    };
-    issue_qk(0);
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) issue_qk(j + 1);
-      mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      const int stage = j % ATT_KV_STAGES;
-      const uint32_t v_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + ATT_TMEM_S, make_desc_sw128(q_addr + k * 32, 1024, 16),
+                  make_desc_sw128(k_addr + k * 32, 1024, 16), idesc_qk, k != 0);
+        tc_commit(s_full);
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        mbar_wait(p_full, (uint32_t)(j & 1));
+        tc_fence_after();
+        const int stage = j & 1;
+        const uint32_t v_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
-        umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + (j & 1) * 64 + k * 8,
-                make_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
-      tc_commit(&kv_empty[stage]);
-      tc_commit(&pv_done[j & 1]);
+        for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
+          umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, make_desc_sw128(v_addr + k * 2048, 1024, 1024),
+                  idesc_pv, (j | k) != 0);
+        tc_commit(&kv_empty[stage]);
+        tc_commit(pv_done);
+      }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax / correction / epilogue =====================
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ==========
     using T = typename TypeOf<DT>::T;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -124,85 +136,94 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(const __grid_constant
     float m_ref = -INFINITY;  // reference maximum (log2 domain) the accumulators are relative to
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t (&chunk)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
-        tmem_ld32(tmem + lane_off + ATT_TMEM_S + (j & 1) * 128 + c * 32, chunk);
-      }
-      tc_wait_ld();
       const int kv_left = p.Skv - j * 128;  // valid columns in this block
+      // ---- pass 1: row maximum ----
       float mx = -INFINITY;
-      if (kv_left >= 128) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S + c * 32, s);
+        tc_wait_ld();
+        if (kv_left - c * 32 >= 32) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-      } else {
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          if (i >= kv_left) s[i] = __float_as_uint(-INFINITY);
-          mx = fmaxf(mx, __uint_as_float(s[i]));
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
         }
       }
       mx *= p.scale_log2;
-      // P buffer (j & 1) was last read by PV_{j-2}: make sure that MMA has retired before overwriting it
-      if (j >= 2) mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
+      // P (and O, if a rescale is needed) may only be touched once PV_{j-1} has retired
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
       if (j == 0) {
         m_ref = mx;
       } else {
         const bool grow = mx > m_ref + 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
-          // rescale O and l to the new reference maximum (needs PV_{j-1} to have landed in TMEM)
-          mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
-          tc_fence_after();
           const float m_new = grow ? mx : m_ref;
           const float alpha = exp2f(m_ref - m_new);
-          uint32_t o[32];
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
             tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            {
-              uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
-              uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
-              tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32, lo);
-              tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32 + 16, hi);
-            }
+            uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
+            uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
+            tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32, lo);
+            tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32 + 16, hi);
           }
           l *= alpha;
           m_ref = m_new;
         }
       }
+      // ---- pass 2: p = exp2(s * scale - m_ref), row sum, 16-bit pack into the P columns ----
       float sum = 0.f;
-      const uint32_t p_addr = tmem + lane_off + ATT_TMEM_P + (j & 1) * 64;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S + c * 32, s);
+        tc_wait_ld();
+        if (c == 3) {  // S_j fully consumed: the MMA warp may overwrite the score columns with Q K_{j+1}^T
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+        }
         uint32_t pk[16];
+        const int left = kv_left - c * 32;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
-          const float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
+          float a = exp2f(__uint_as_float(s[2 * i]) * p.scale_log2 - m_ref);
+          float bq = exp2f(__uint_as_float(s[2 * i + 1]) * p.scale_log2 - m_ref);
+          if (left < 32) {
+            if (2 * i >= left) a = 0.f;
+            if (2 * i + 1 >= left) bq = 0.f;
+          }
           sum += a + bq;
           pk[i] = pack2<DT>(a, bq);
         }
-        tmem_st16(p_addr + c * 16, pk);
+        tmem_st16(tmem + lane_off + ATT_TMEM_P + c * 16, pk);
       }
       l += sum;
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l
-    mbar_wait(&pv_done[(n_kv - 1) & 1], (uint32_t)(((n_kv - 1) >> 1) & 1));
+    mbar_wait(pv_done, (uint32_t)((n_kv - 1) & 1));
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const long long qrow = (long long)qt * 128 + row;
     T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
@@ -223,9 +244,9 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, ATT_TMEM_COLS);
   }
 }
 
@@ -267,8 +288,8 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
     configured = true;
   }
   const int grid = B * heads * p.q_tiles;
-  if (dtype == DT_F16) attention_kernel<DT_F16><<<grid, 256, ATT_SMEM_BYTES, stream>>>(p);
-  else attention_kernel<DT_BF16><<<grid, 256, ATT_SMEM_BYTES, stream>>>(p);
+  if (dtype == DT_F16) attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(p);
+  else attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(p);
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

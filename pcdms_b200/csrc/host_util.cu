@@ -43,7 +43,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+              const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(PCDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -57,7 +57,10 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   if (reinterpret_cast<uintptr_t>(base) & 15)
     return set_error(PCDM_ERR_INVALID, "tensor map: base pointer must be 16-byte aligned");
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(PCDM_ERR_CUDA,

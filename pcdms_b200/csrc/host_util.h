@@ -14,7 +14,7 @@ int num_sms();
 // rank-D tiled tensor map over a 16-bit tensor, 128-byte swizzle, zero OOB fill.
 // dims/box are innermost-first; strides_bytes has rank-1 entries (stride of dims 1..rank-1).
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box);
+              const uint32_t* box, int swizzle_bytes = 128);
 
 #define PCDM_CUDA(expr)                                                                      \
   do {                                                                                       \

@@ -19,9 +19,16 @@
 
 namespace pcdm {
 
+constexpr int IG_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
+constexpr int IG_EPI_WARPS = 8;
+constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
+constexpr int IG_MAX_STAGES = 8;
+
 struct IGemmParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmOut;   // [M, N_out] 16-bit output, box 32 x 32, 64B swizzle (unused for fp32 output)
+  CUtensorMap tmRes;   // residual, same geometry
   int M, N;
   int num_kb;      // K / 64
   int m_tiles, n_tiles;
@@ -30,61 +37,78 @@ struct IGemmParams {
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
   uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
+  int stages;      // smem ring depth (runtime: depends on BN and on whether residual staging is needed)
+  int nbuf;        // staging slots per epilogue warp (2, or 3 with a residual: one slot is being prefetched)
   const float* bias;
   const float* rowvec;
   long long ld_rowvec;
   int hw;          // rows per image for rowvec indexing
-  const void* residual;
-  long long ldr;
-  void* out;
+  int has_res;
+  void* out;       // only dereferenced for fp32 output
   long long ldo;
   int geglu;
   int out_f32;
   int silu;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct IGemmCfg {
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (BN / CG) * 128;   // a CTA pair splits the weight tile: each CTA stages BN/2 rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int DT>
-__global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ IGemmParams p) {
-  using Cfg = IGemmCfg<BN>;
+// byte offset of 16-byte chunk j of row r inside a [rows x 64 B] tile written with the TMA 64-byte swizzle
+__device__ __forceinline__ uint32_t sw64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
+// each CTA loads its own 128 activation rows and HALF of the weight tile, the leader CTA issues the M = 256 MMAs, each
+// CTA's TMEM receives (and each CTA's epilogue stores) its own 128 rows.
+template <int BN, int DT, int CG>
+__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IGemmParams p) {
+  using Cfg = IGemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty = full + Cfg::STAGES;
-  uint64_t* tfull = empty + Cfg::STAGES;
+  uint8_t* epi_smem = smem + p.stages * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES);
+  uint64_t* empty = full + IG_MAX_STAGES;
+  uint64_t* tfull = empty + IG_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_bar = tempty + 2;                 // [IG_EPI_WARPS][3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + IG_EPI_WARPS * 3);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles;   // m_tiles counts 128*CG-row tiles
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int first_tile = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA[0]);
-    for (int i = 0; i < Cfg::STAGES; ++i) {
+    if (!p.out_f32) tma_prefetch_desc(&p.tmOut);
+    if (p.has_res) tma_prefetch_desc(&p.tmRes);
+    for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], IG_EPI_WARPS * CG);
     }
+    for (int i = 0; i < IG_EPI_WARPS * 3; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // peer barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -93,9 +117,9 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     int stage = 0;
     uint32_t phase = 0;
     const int hw = p.H * p.W;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-      const int m0 = m_blk * 128;
+      const int m0 = (m_blk * CG + (int)rank) * 128;
       int b0 = 0, y0 = 0;
       if (p.mode != 0) {
         b0 = m0 / hw;
@@ -106,34 +130,54 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
-        if (p.mode == 0) {
-          if (kb < p.kb_split) tma_load_2d(sa, &p.tmA[0], &full[stage], kb * 64, m0);
-          else tma_load_2d(sa, &p.tmA[1], &full[stage], (kb - p.kb_split) * 64, m0);
-        } else {
-          const int r = tap / 3, s = tap - r * 3;
-          if (p.mode == 1) {
-            tma_load_4d(sa, &p.tmA[0], &full[stage], cb * 64, s - 1, y0 + r - 1, b0);
+        if (CG == 1) {
+          mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+          if (p.mode == 0) {
+            if (kb < p.kb_split) tma_load_2d(sa, &p.tmA[0], &full[stage], kb * 64, m0);
+            else tma_load_2d(sa, &p.tmA[1], &full[stage], (kb - p.kb_split) * 64, m0);
           } else {
-            // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
-            const int py = (r != 1), px = (s != 1);
-            tma_load_4d(sa, &p.tmA[py * 2 + px], &full[stage], cb * 64, (s == 0) ? -1 : 0, y0 + ((r == 0) ? -1 : 0),
-                        b0);
+            const int r = tap / 3, s = tap - r * 3;
+            if (p.mode == 1) {
+              tma_load_4d(sa, &p.tmA[0], &full[stage], cb * 64, s - 1, y0 + r - 1, b0);
+            } else {
+              // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
+              const int py = (r != 1), px = (s != 1);
+              tma_load_4d(sa, &p.tmA[py * 2 + px], &full[stage], cb * 64, (s == 0) ? -1 : 0,
+                          y0 + ((r == 0) ? -1 : 0), b0);
+            }
+            if (++cb == p.cblocks) { cb = 0; ++tap; }
           }
-          if (++cb == p.cblocks) { cb = 0; ++tap; }
+          tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+        } else {
+          // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+          if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
+          const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
+          if (p.mode == 0) {
+            if (kb < p.kb_split) tma_load_2d_cg2(sa, &p.tmA[0], fbar, kb * 64, m0);
+            else tma_load_2d_cg2(sa, &p.tmA[1], fbar, (kb - p.kb_split) * 64, m0);
+          } else {
+            const int r = tap / 3, s = tap - r * 3;
+            if (p.mode == 1) {
+              tma_load_4d_cg2(sa, &p.tmA[0], fbar, cb * 64, s - 1, y0 + r - 1, b0);
+            } else {
+              const int py = (r != 1), px = (s != 1);
+              tma_load_4d_cg2(sa, &p.tmA[py * 2 + px], fbar, cb * 64, (s == 0) ? -1 : 0, y0 + ((r == 0) ? -1 : 0), b0);
+            }
+            if (++cb == p.cblocks) { cb = 0; ++tap; }
+          }
+          tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
         }
-        tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(DT, 128, BN, 0, 0);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA of a pair) =====================
+    constexpr uint32_t idesc = make_idesc(DT, 128 * CG, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
@@ -144,36 +188,51 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          umma_ss(d_tmem, make_desc_sw128(a_addr + k * 32, 1024, 16), make_desc_sw128(b_addr + k * 32, 1024, 16), idesc,
-                  (kb | k) != 0);
+          const uint64_t da = make_desc_sw128(a_addr + k * 32, 1024, 16);
+          const uint64_t db = make_desc_sw128(b_addr + k * 32, 1024, 16);
+          if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+          else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
         }
-        tc_commit(&empty[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (CG == 2) tc_commit_cg2(&empty[stage]);   // frees the stage in both CTAs
+        else tc_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tfull[acc]);
+      if (CG == 2) tc_commit_cg2(&tfull[acc]);        // both CTAs' epilogues
+      else tc_commit(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (8 warps: TMEM quadrant q, column-chunk parity `half`) =====================
     using T = typename TypeOf<DT>::T;
-    const int q = warp & 3;
+    const int e = warp - 4;
+    const int q = e & 3;      // == warp % 4: the TMEM lane quadrant this warp may touch
+    const int half = e >> 2;
     const int row = q * 32 + lane;
+    uint8_t* slots = epi_smem + e * p.nbuf * IG_SLOT_BYTES;
+    uint64_t* rbar = res_bar + e * 3;
+    uint32_t cnt = 0;         // chunks staged by this warp so far (slot rotation + residual barrier parity)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int nbuf = p.nbuf;
+    const uint32_t tempty_addr[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-      const long long m = (long long)m_blk * 128 + row;
+      const int m_cta0 = (m_blk * CG + (int)rank) * 128;
+      const int m_warp0 = m_cta0 + q * 32;
+      const long long m = (long long)m_cta0 + row;
       const bool valid = m < p.M;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
+      const int n_tile0 = n_blk * BN;
+      const int cols_here = min(BN, p.N - n_tile0);
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const float* rv = (p.rowvec && valid) ? p.rowvec + (long long)(m / p.hw) * p.ld_rowvec : nullptr;
-      if (!p.geglu) {
+      if (p.out_f32) {
+        // ---- fp32 output (conv_out, stacked time-embedding projection): direct per-row stores ----
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = n_blk * BN + c * 32;
-          if (n0 >= p.N) break;
+        for (int c = half; c * 32 < cols_here; c += 2) {
+          const int n0 = n_tile0 + c * 32;
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tc_wait_ld();
@@ -195,101 +254,199 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
               }
             }
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(rp + j);
-                float2 f;
-                f = unpack2<DT>(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
-                f = unpack2<DT>(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
-                f = unpack2<DT>(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
-                f = unpack2<DT>(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
-              }
-            }
             if (p.silu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             }
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + m * p.ldo + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
-                u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
-                u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
-                u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
-                op[j] = u;
-              }
-            }
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
           }
         }
-      } else {
-        // GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate)
+      } else if (!p.geglu) {
+        // ---- 16-bit output: TMEM -> registers -> (+bias, +rowvec, +residual, act) -> swizzled smem slot -> TMA store.
+        //      The residual chunk is TMA-prefetched into the slot one chunk ahead. ----
+        if (p.has_res && half * 32 < cols_here) {
+          if (lane == 0) {
+            bulk_wait_read<1>();
+            const uint32_t slot = cnt % nbuf;
+            mbar_expect_tx(&rbar[slot], IG_SLOT_BYTES);
+            tma_load_2d(slots + slot * IG_SLOT_BYTES, &p.tmRes, &rbar[slot], n_tile0 + half * 32, m_warp0);
+          }
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          const int n0 = n_blk * BN + c * 64;
-          if (n0 >= p.N) break;
+        for (int c = half; c * 32 < cols_here; c += 2) {
+          const int n0 = n_tile0 + c * 32;
+          const uint32_t slot = cnt % nbuf;
+          uint8_t* sl = slots + slot * IG_SLOT_BYTES;
+          if (lane == 0) {
+            bulk_wait_read<1>();   // every store but the most recent has finished reading its slot
+            if (p.has_res && (c + 2) * 32 < cols_here) {
+              const uint32_t ns = (cnt + 1) % nbuf;
+              mbar_expect_tx(&rbar[ns], IG_SLOT_BYTES);
+              tma_load_2d(slots + ns * IG_SLOT_BYTES, &p.tmRes, &rbar[ns], n0 + 64, m_warp0);
+            }
+          }
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tc_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.has_res) {
+            mbar_wait(&rbar[slot], (cnt / nbuf) & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(sl + sw64(lane, j));
+              float2 f;
+              f = unpack2<DT>(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
+              f = unpack2<DT>(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
+              f = unpack2<DT>(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
+              f = unpack2<DT>(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+            }
+          }
+          if (p.silu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
+            u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
+            u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
+            u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = u;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
+            bulk_commit();
+          }
+          ++cnt;
+        }
+      } else {
+        // ---- GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate) ----
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c * 64 < cols_here; c += 2) {
+          const int n0 = n_tile0 + c * 64;
+          const uint32_t slot = cnt % nbuf;
+          uint8_t* sl = slots + slot * IG_SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
           uint32_t rh[32], rg[32];
           tmem_ld32(t_row + c * 64, rh);
           tmem_ld32(t_row + c * 64 + 32, rg);
           tc_wait_ld();
-          if (valid) {
-            float v[32];
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float h = __uint_as_float(rh[j]), g = __uint_as_float(rg[j]);
-              if (p.bias) { h += __ldg(p.bias + n0 + j); g += __ldg(p.bias + n0 + 32 + j); }
-              v[j] = h * gelu_erf_f(g);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + m * p.ldo + (n0 >> 1));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
-              u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
-              u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
-              u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
-              op[j] = u;
-            }
+          for (int j = 0; j < 32; ++j) {
+            float h = __uint_as_float(rh[j]), g = __uint_as_float(rg[j]);
+            if (p.bias) { h += __ldg(p.bias + n0 + j); g += __ldg(p.bias + n0 + 32 + j); }
+            v[j] = h * gelu_erf_f(g);
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
+            u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
+            u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
+            u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = u;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, sl, n0 >> 1, m_warp0);
+            bulk_commit();
+          }
+          ++cnt;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_addr[acc]);   // the MMA issuer lives in the leader CTA
+        else mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait<0>();   // all TMA stores have landed before the CTA (and its shared memory) goes away
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal / read this CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int DT>
-static int launch_igemm(const IGemmParams& p, cudaStream_t stream) {
-  using Cfg = IGemmCfg<BN>;
+constexpr int IG_SMEM_LIMIT = 227 * 1024;
+
+template <int BN, int DT, int CG>
+static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
+  using Cfg = IGemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
     configured = true;
   }
+  p.nbuf = p.has_res ? 3 : 2;
+  const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
+  int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
+  if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
+  if (stages < 2) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: not enough shared memory for a 2-stage ring");
+  p.stages = stages;
+  const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  igemm_kernel<BN, DT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  if (CG == 1) {
+    const int grid = total < num_sms() ? total : num_sms();
+    igemm_kernel<BN, DT, CG><<<grid, IG_THREADS, smem_bytes, stream>>>(p);
+  } else {
+    const int pairs = num_sms() / 2;
+    const int grid = 2 * (total < pairs ? total : pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(IG_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PCDM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DT, CG>, p));
+  }
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -313,10 +470,34 @@ static int pick_bn(int m_tiles, int N, int geglu) {
   return best;
 }
 
-static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, cudaStream_t stream) {
+static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
+
+static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, const void* residual, long long ldr,
+                          cudaStream_t stream) {
   if (bn == 0) bn = pick_bn(p.m_tiles, p.N, p.geglu);
+  // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles and the N tile can be halved on 8-row groups
+  int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0) ? 2 : 1;
+  if (g_force_cg == 1) cg = 1;
+  if (g_force_cg == 2 && bn >= 128) cg = 2;
+  if (cg == 2) p.m_tiles = (p.M + 255) / 256;
+  p.has_res = residual ? 1 : 0;
+  if (p.has_res && (p.geglu || p.out_f32))
+    return set_error(PCDM_ERR_UNSUPPORTED, "igemm: residual cannot be combined with GEGLU or fp32 output");
+  if (!p.out_f32) {
+    const uint64_t n_out = p.geglu ? (uint64_t)p.N / 2 : (uint64_t)p.N;
+    const uint64_t dims[2] = {n_out, (uint64_t)p.M};
+    const uint64_t strides[1] = {(uint64_t)p.ldo * 2};
+    const uint32_t box[2] = {32, 32};
+    PCDM_CHECK(make_tmap(&p.tmOut, p.out, 2, dims, strides, box, 64), "output tensor map");
+    if (p.has_res) {
+      const uint64_t rdims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+      const uint64_t rstrides[1] = {(uint64_t)ldr * 2};
+      PCDM_CHECK(make_tmap(&p.tmRes, residual, 2, rdims, rstrides, box, 64), "residual tensor map");
+    }
+  }
   p.n_tiles = (p.N + bn - 1) / bn;
-  const int brows = p.N < bn ? p.N : bn;
+  const int bbox = bn / cg;
+  const int brows = p.N < bbox ? p.N : bbox;
   p.b_bytes = (uint32_t)brows * 128u;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)p.N};
@@ -324,13 +505,13 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     const uint32_t box[2] = {64, (uint32_t)brows};
     PCDM_CHECK(make_tmap(&p.tmB, w, 2, dims, strides, box), "weight tensor map");
   }
-#define PCDM_LAUNCH(BN_)                                                      \
-  (dt == DT_F16 ? launch_igemm<BN_, DT_F16>(p, stream) : launch_igemm<BN_, DT_BF16>(p, stream))
+#define PCDM_LAUNCH(BN_, CG_)                                                      \
+  (dt == DT_F16 ? launch_igemm<BN_, DT_F16, CG_>(p, stream) : launch_igemm<BN_, DT_BF16, CG_>(p, stream))
   switch (bn) {
-    case 64: return PCDM_LAUNCH(64);
-    case 128: return PCDM_LAUNCH(128);
-    case 160: return PCDM_LAUNCH(160);
-    case 256: return PCDM_LAUNCH(256);
+    case 64: return PCDM_LAUNCH(64, 1);
+    case 128: return cg == 2 ? PCDM_LAUNCH(128, 2) : PCDM_LAUNCH(128, 1);
+    case 160: return cg == 2 ? PCDM_LAUNCH(160, 2) : PCDM_LAUNCH(160, 1);
+    case 256: return cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1);
     default: return set_error(PCDM_ERR_INVALID, "igemm: BN must be 0, 64, 128, 160 or 256");
   }
 #undef PCDM_LAUNCH
@@ -375,11 +556,11 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
     }
   }
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
-  p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
+  p.out = out; p.ldo = ldo;
   p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: rowvec stride must be a multiple of 4");
   if (p.geglu && p.out_f32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU with fp32 output");
-  return dispatch_igemm(p, dtype, bn, w, K, stream);
+  return dispatch_igemm(p, dtype, bn, w, K, residual, ldr, stream);
 }
 
 extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
@@ -425,8 +606,15 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
       }
   }
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = hw;
-  p.residual = residual; p.ldr = Cout; p.out = out; p.ldo = Cout;
+  p.out = out; p.ldo = Cout;
   p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: rowvec stride must be a multiple of 4");
-  return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, stream);
+  return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, residual, Cout, stream);
+}
+
+/* tuning / test hook: 0 = choose automatically, 1 = single-CTA tiles only, 2 = CTA pairs wherever BN >= 128 */
+extern "C" int pcdm_set_gemm_cta_group(int mode) {
+  if (mode < 0 || mode > 2) return set_error(PCDM_ERR_INVALID, "gemm cta group mode must be 0, 1 or 2");
+  g_force_cg = mode;
+  return 0;
 }

@@ -14,16 +14,28 @@
 namespace pcdm {
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm pass 1: per-(image, group) sum / sum-of-squares into stats[B][G][2] (double, pre-zeroed)
-// block = (C/8, PY); thread (cv, py) owns 8 consecutive channels of pixels py, py+PY, ... within the CTA's chunk
+// GroupNorm pass 1: statistics.  block = (C/8, PY); thread (cv, py) owns 8 consecutive channels of pixels py, py+PY, ...
+// of the CTA's pixel chunk.  Reduction order is fixed at every level (registers -> smem over py -> channels of a group
+// -> chunks of an image), so results are bit-reproducible run to run: no floating-point atomics anywhere.  The last
+// CTA of an image (device counter) folds the per-chunk partials into (mean, rstd) per group.
 // ---------------------------------------------------------------------------------------------------------------
+struct GnWorkspace {
+  float2* final_stats;   // [B][groups] (mean, rstd)
+  unsigned* counters;    // [B], zero between launches
+  double2* partial;      // [B][chunks][groups] (sum, sumsq)
+};
+
+__host__ __device__ inline size_t gn_align(size_t x) { return (x + 255) / 256 * 256; }
+
 template <int DT>
 __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1, int C, int HW,
-                                int groups, int pix_per_cta, double* __restrict__ stats) {
+                                int groups, int pix_per_cta, float eps, GnWorkspace ws) {
   using T = typename TypeOf<DT>::T;
-  extern __shared__ float sm[];  // [2][C] per-channel partials, then [2][groups]
+  extern __shared__ float sm[];  // [2][PY][C] per-(py, channel) partials; then [2][C] per-channel sums
   const int b = blockIdx.y;
   const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = py * blockDim.x + cv;
   const int c0 = cv * 8;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
@@ -44,74 +56,94 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
       s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
     }
   }
-  float* ssum = sm;
-  float* ssq = sm + C;
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) sm[i] = 0.f;
+  float* ps = sm;                   // [PY][C]
+  float* pq = sm + (size_t)PY * C;  // [PY][C]
+  *reinterpret_cast<float4*>(ps + (size_t)py * C + c0) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(ps + (size_t)py * C + c0 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(pq + (size_t)py * C + c0) = make_float4(q[0], q[1], q[2], q[3]);
+  *reinterpret_cast<float4*>(pq + (size_t)py * C + c0 + 4) = make_float4(q[4], q[5], q[6], q[7]);
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(&ssum[c0 + i], s[i]);
-    atomicAdd(&ssq[c0 + i], q[i]);
+  // per-channel totals over py (fixed order), written back into row 0
+  for (int c = tid; c < C; c += nthreads) {
+    float a = ps[c], bq = pq[c];
+    for (int y = 1; y < PY; ++y) { a += ps[(size_t)y * C + c]; bq += pq[(size_t)y * C + c]; }
+    ps[c] = a;
+    pq[c] = bq;
   }
   __syncthreads();
   const int cpg = C / groups;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int chunks = gridDim.x;
   if (tid < groups) {
     double a = 0.0, bq = 0.0;
-    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { a += (double)ssum[c]; bq += (double)ssq[c]; }
-    atomicAdd(&stats[((size_t)b * groups + tid) * 2 + 0], a);
-    atomicAdd(&stats[((size_t)b * groups + tid) * 2 + 1], bq);
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { a += (double)ps[c]; bq += (double)pq[c]; }
+    ws.partial[((size_t)b * chunks + blockIdx.x) * groups + tid] = make_double2(a, bq);
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (tid == 0) is_last = (atomicAdd(&ws.counters[b], 1u) == (unsigned)(chunks - 1));
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (tid < groups) {
+      double a = 0.0, bq = 0.0;
+      for (int k = 0; k < chunks; ++k) {
+        const double2 v = ws.partial[((size_t)b * chunks + k) * groups + tid];
+        a += v.x; bq += v.y;
+      }
+      const double inv_n = 1.0 / ((double)cpg * (double)HW);
+      const double mean = a * inv_n;
+      double var = bq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      ws.final_stats[(size_t)b * groups + tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    if (tid == 0) ws.counters[b] = 0;  // ready for the next launch (and for CUDA-graph replays)
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta (+ SiLU); per-image per-channel scale/shift staged in smem
+// GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta (+ SiLU).  Same (C/8, PY) thread layout as pass 1: a thread
+// owns 8 fixed channels, so its 8 scale/shift pairs live in registers and the pixel loop is pure streaming.
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT>
 __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1, int C, int HW,
-                                int groups, int pix_per_cta, const double* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                int groups, int pix_per_cta, const float2* __restrict__ final_stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 void* __restrict__ y) {
   using T = typename TypeOf<DT>::T;
-  extern __shared__ float sm[];  // scale[C], shift[C]
-  float* scale = sm;
-  float* shift = sm + C;
   const int b = blockIdx.y;
+  const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
+  const int c0 = cv * 8;
   const int cpg = C / groups;
-  const double inv_n = 1.0 / ((double)cpg * (double)HW);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double mean = stats[((size_t)b * groups + g) * 2 + 0] * inv_n;
-    double var = stats[((size_t)b * groups + g) * 2 + 1] * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const float2 st = __ldg(final_stats + (size_t)b * groups + c / cpg);
+    const float s_ = st.y * __ldg(gamma + c);
+    sc[i] = s_;
+    sh[i] = __ldg(beta + c) - st.x * s_;
   }
-  __syncthreads();
-  const int cvs = C / 8;
+  const T* src;
+  int cs, coff;
+  if (c0 < C1) { src = reinterpret_cast<const T*>(x1); cs = C1; coff = c0; }
+  else { src = reinterpret_cast<const T*>(x2); cs = C - C1; coff = c0 - C1; }
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
-  const int total = (p_end - p_begin) * cvs;
-  const int C2 = C - C1;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p_begin + i / cvs;
-    const int c0 = (i % cvs) * 8;
-    const T* src = (c0 < C1) ? reinterpret_cast<const T*>(x1) + ((size_t)b * HW + p) * C1 + c0
-                             : reinterpret_cast<const T*>(x2) + ((size_t)b * HW + p) * C2 + (c0 - C1);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+  T* dst = reinterpret_cast<T*>(y);
+  for (int p = p_begin + py; p < p_end; p += PY) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * cs + coff));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack2<DT>(w[k]);
-      float a = f.x * scale[c0 + 2 * k] + shift[c0 + 2 * k];
-      float bb = f.y * scale[c0 + 2 * k + 1] + shift[c0 + 2 * k + 1];
+      float a = f.x * sc[2 * k] + sh[2 * k];
+      float bb = f.y * sc[2 * k + 1] + sh[2 * k + 1];
       if (silu) { a = silu_f(a); bb = silu_f(bb); }
       o[k] = pack2<DT>(a, bb);
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(y) + ((size_t)b * HW + p) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(dst + ((size_t)b * HW + p) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -183,7 +215,29 @@ __global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, void
 
 using namespace pcdm;
 
-extern "C" long long pcdm_groupnorm_workspace_bytes(int B, int groups) { return (long long)B * groups * 2 * 8; }
+static void gn_grid(int B, int HW, int C, int* PY_, int* pix_per_cta_, int* chunks_) {
+  const int cvs = C / 8;
+  int PY = 512 / cvs;
+  if (PY < 1) PY = 1;
+  // >= ~4 CTAs per SM across the batch (these kernels are latency/bandwidth bound: parallelism first), but keep at
+  // least one pixel per thread row
+  const int chunks_wanted = (4 * num_sms() + B - 1) / B;
+  int pix_per_cta = (HW + chunks_wanted - 1) / chunks_wanted;
+  if (pix_per_cta < PY) pix_per_cta = PY;
+  if (pix_per_cta > HW) pix_per_cta = HW;
+  if (PY > pix_per_cta) PY = pix_per_cta;
+  *PY_ = PY;
+  *pix_per_cta_ = pix_per_cta;
+  *chunks_ = (HW + pix_per_cta - 1) / pix_per_cta;
+}
+
+// workspace = [final (mean, rstd) float2 x B x groups][counters x B][partials double2 x B x max_chunks x groups];
+// it must be zero-initialised ONCE by the caller (the counters), afterwards the kernels keep it consistent.
+extern "C" long long pcdm_groupnorm_workspace_bytes(int B, int groups) {
+  const long long max_cta = 4LL * num_sms() + 2LL * B;   // B * chunks never exceeds this (see gn_grid)
+  return (long long)(gn_align((size_t)B * groups * sizeof(float2)) + gn_align((size_t)B * sizeof(unsigned)) +
+                     gn_align((size_t)max_cta * groups * sizeof(double2)));
+}
 
 extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta,
                               float eps, int B, int HW, int C, int groups, int dtype, int flags, void* workspace,
@@ -196,26 +250,28 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
   if (!x2) C1 = C;
   if (C1 % 8 || C1 <= 0 || C1 > C) return set_error(PCDM_ERR_INVALID, "groupnorm: bad channel split");
   if (groups > 256) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm: groups > 256");
-  double* stats = reinterpret_cast<double*>(workspace);
-  PCDM_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * groups * 2 * sizeof(double), stream));
-  const int cvs = C / 8;
-  int PY = 512 / cvs;
-  if (PY < 1) PY = 1;
-  // ~4096 elements per thread-row pass; keep >= 2 waves of CTAs when the tensor is big
-  int pix_per_cta = (64 * 1024) / C;
-  if (pix_per_cta < PY) pix_per_cta = PY;
-  if (pix_per_cta > HW) pix_per_cta = HW;
-  const int chunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  int PY, pix_per_cta, chunks;
+  gn_grid(B, HW, C, &PY, &pix_per_cta, &chunks);
+  GnWorkspace ws;
+  char* base = reinterpret_cast<char*>(workspace);
+  ws.final_stats = reinterpret_cast<float2*>(base);
+  base += gn_align((size_t)B * groups * sizeof(float2));
+  ws.counters = reinterpret_cast<unsigned*>(base);
+  base += gn_align((size_t)B * sizeof(unsigned));
+  ws.partial = reinterpret_cast<double2*>(base);
   const dim3 grid(chunks, B);
-  const size_t smem = (size_t)2 * C * sizeof(float);
+  const dim3 block(C / 8, PY);
+  const size_t smem = (size_t)2 * PY * C * sizeof(float);
+  if (smem > 48 * 1024) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm: statistics staging exceeds 48 KB");
+  const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   if (dtype == DT_F16) {
-    gn_stats_kernel<DT_F16><<<grid, dim3(cvs, PY), smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, stats);
-    gn_apply_kernel<DT_F16><<<grid, 256, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, stats, gamma, beta,
-                                                          eps, (flags & PCDM_FLAG_SILU) ? 1 : 0, y);
+    gn_stats_kernel<DT_F16><<<grid, block, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, eps, ws);
+    gn_apply_kernel<DT_F16><<<grid, block, 0, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, ws.final_stats, gamma,
+                                                        beta, silu, y);
   } else {
-    gn_stats_kernel<DT_BF16><<<grid, dim3(cvs, PY), smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, stats);
-    gn_apply_kernel<DT_BF16><<<grid, 256, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, stats, gamma, beta,
-                                                           eps, (flags & PCDM_FLAG_SILU) ? 1 : 0, y);
+    gn_stats_kernel<DT_BF16><<<grid, block, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, eps, ws);
+    gn_apply_kernel<DT_BF16><<<grid, block, 0, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, ws.final_stats, gamma,
+                                                         beta, silu, y);
   }
   PCDM_CUDA(cudaGetLastError());
   return 0;

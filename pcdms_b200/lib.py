@@ -7,6 +7,7 @@ check that every symbol declared in the header is exported); compute calls need 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -54,6 +55,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib = C.CDLL(str(LIB_PATH))
     lib.pcdm_last_error.restype = C.c_char_p
     lib.pcdm_abi_version.restype = C.c_int
+    lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong
+    mode = os.environ.get("PCDM_GEMM_CTA_GROUP")  # tuning hook: 1 = single-CTA tiles, 2 = CTA pairs, unset = auto
+    if mode:
+        lib.pcdm_set_gemm_cta_group(C.c_int(int(mode)))
     _lib = lib
     return lib
 

@@ -107,8 +107,10 @@ def _gn_workspace(device, B, groups):
     key = (device, B, groups)
     ws = _gn_ws.get(key)
     if ws is None:
-        n = _l.load().pcdm_groupnorm_workspace_bytes(C.c_int(B), C.c_int(groups))
-        ws = torch.empty(int(n), dtype=torch.uint8, device=device)
+        lib = _l.load()
+        lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong
+        n = lib.pcdm_groupnorm_workspace_bytes(C.c_int(B), C.c_int(groups))
+        ws = torch.zeros(int(n), dtype=torch.uint8, device=device)  # zero ONCE: the kernels keep the counters at 0
         _gn_ws[key] = ws
     return ws
 

@@ -56,6 +56,59 @@ def run_conv(B, H, W, Cin, Cout, dt, stride=1, bn=0, temb=True, resid=True):
     print(res[-1], flush=True)
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+from pcdms_b200 import lib as _plib
+def set_cg(mode):
+    _plib.check(_plib.load().pcdm_set_gemm_cta_group(mode), kernels=0)
+
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+if which == "cg2":
+    set_cg(2)
+    for dt in (torch.float16, torch.bfloat16):
+        run_gemm(256, 256, 128, dt, bn=128)
+        run_gemm(1000, 320, 320, dt, bn=160, resid=True)
+        run_gemm(4096, 1280, 1024, dt, bn=256)
+        run_gemm(300, 2560, 320, dt, bn=256, geglu=True)
+        run_gemm(512, 320, 960, dt, bn=160, split=640)
+        run_gemm(4128, 640, 1024, dt, bn=0, bias=False)
+        run_conv(2, 32, 64, 320, 320, dt)
+        run_conv(2, 16, 32, 640, 640, dt, bn=128)
+        run_conv(16, 4, 8, 1280, 1280, dt)
+        run_conv(6, 4, 8, 128, 128, dt, bn=128)
+        run_conv(1, 64, 128, 64, 256, dt, resid=False, bn=256)
+        run_conv(2, 16, 32, 320, 320, dt, stride=2, temb=False, resid=False)
+    dt = torch.bfloat16
+    shapes = [("conv320@32x64", lambda bn: ops.conv3x3(x320, w320, bn=bn), 2 * 16 * 2048 * 320 * 2880, (160, 256)),
+              ("conv640@16x32", lambda bn: ops.conv3x3(x640, w640, bn=bn), 2 * 16 * 512 * 640 * 5760, (160, 128, 256)),
+              ("conv1280@8x16", lambda bn: ops.conv3x3(x1280, w1280, bn=bn), 2 * 16 * 128 * 1280 * 11520, (160, 128, 256)),
+              ("conv1280@4x8", lambda bn: ops.conv3x3(x1280s, w1280, bn=bn), 2 * 16 * 32 * 1280 * 11520, (160, 128, 64)),
+              ("geglu 32768x2560x320", lambda bn: ops.gemm(a320, wg, bias=bg, geglu=True, bn=bn), 2 * 32768 * 2560 * 320, (256, 128)),
+              ("ffout 32768x320x1280", lambda bn: ops.gemm(a1280, wf, residual=r320, bn=bn), 2 * 32768 * 320 * 1280, (160,)),
+              ("qkv 32768x960x320", lambda bn: ops.gemm(a320, wq, bn=bn), 2 * 32768 * 960 * 320, (160, 128)),
+              ("toout 32768x320x320", lambda bn: ops.gemm(a320, wo, residual=r320, bn=bn), 2 * 32768 * 320 * 320, (160,)),
+              ("gemm 8192^3", lambda bn: ops.gemm(a8k, w8k, bn=bn), 2 * 8192 ** 3, (256,))]
+    x320 = torch.randn(16, 32, 64, 320, device=dev, dtype=dt); w320 = torch.randn(320, 2880, device=dev, dtype=dt)
+    x640 = torch.randn(16, 16, 32, 640, device=dev, dtype=dt); w640 = torch.randn(640, 5760, device=dev, dtype=dt)
+    x1280 = torch.randn(16, 8, 16, 1280, device=dev, dtype=dt); w1280 = torch.randn(1280, 11520, device=dev, dtype=dt)
+    x1280s = torch.randn(16, 4, 8, 1280, device=dev, dtype=dt)
+    a320 = torch.randn(32768, 320, device=dev, dtype=dt); wg = torch.randn(2560, 320, device=dev, dtype=dt); bg = torch.randn(2560, device=dev)
+    a1280 = torch.randn(32768, 1280, device=dev, dtype=dt); wf = torch.randn(320, 1280, device=dev, dtype=dt); r320 = torch.randn(32768, 320, device=dev, dtype=dt)
+    wq = torch.randn(960, 320, device=dev, dtype=dt); wo = torch.randn(320, 320, device=dev, dtype=dt)
+    a8k = torch.randn(8192, 8192, device=dev, dtype=dt); w8k = torch.randn(8192, 8192, device=dev, dtype=dt)
+    for name, fn, fl, bns in shapes:
+        for bn in bns:
+            for cg in (1, 2):
+                if cg == 2 and bn < 128: continue
+                set_cg(cg)
+                ms = timeit(lambda: fn(bn))
+                res.append(dict(op="perf", name=name, bn=bn, cg=cg, ms=ms, tflops=fl / ms / 1e9)); print(res[-1], flush=True)
+    set_cg(0)
 if which in ("gemm", "all"):
     for dt in (torch.float16, torch.bfloat16):
         run_gemm(256, 256, 128, dt, bn=128)
