@@ -296,7 +296,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 // two-branch polynomial — the GEGLU epilogue evaluates this 42 M times per UNet step.
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;   // rcp.approx: a bare MUFU.RCP (1 ulp) — __frcp_rn would add a range check + slow-path call per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -359,12 +359,23 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           tmem_ld32(t_row + c * 64 + 32, rg);
           tc_wait_ld();
           float v[32];
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h = __uint_as_float(rh[j]), g = __uint_as_float(rg[j]);
-            if (p.bias) { h += __ldg(p.bias + n0 + j); g += __ldg(p.bias + n0 + 32 + j); }
-            v[j] = h * gelu_erf_f(g);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
+              rh[j] = __float_as_uint(__uint_as_float(rh[j]) + bh.x);
+              rh[j + 1] = __float_as_uint(__uint_as_float(rh[j + 1]) + bh.y);
+              rh[j + 2] = __float_as_uint(__uint_as_float(rh[j + 2]) + bh.z);
+              rh[j + 3] = __float_as_uint(__uint_as_float(rh[j + 3]) + bh.w);
+              rg[j] = __float_as_uint(__uint_as_float(rg[j]) + bg.x);
+              rg[j + 1] = __float_as_uint(__uint_as_float(rg[j + 1]) + bg.y);
+              rg[j + 2] = __float_as_uint(__uint_as_float(rg[j + 2]) + bg.z);
+              rg[j + 3] = __float_as_uint(__uint_as_float(rg[j + 3]) + bg.w);
+            }
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) * gelu_erf_f(__uint_as_float(rg[j]));
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -476,7 +487,9 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
                           cudaStream_t stream) {
   if (bn == 0) bn = pick_bn(p.m_tiles, p.N, p.geglu);
   // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles and the N tile can be halved on 8-row groups
-  int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0) ? 2 : 1;
+  // (measured on B200: pairs win ~2-12% once the K loop is long enough to be operand-delivery bound, and lose on
+  //  short-K GEMMs whose time is epilogue + prologue: K >= 2048 is the crossover)
+  int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0 && p.num_kb >= 32) ? 2 : 1;
   if (g_force_cg == 1) cg = 1;
   if (g_force_cg == 2 && bn >= 128) cg = 2;
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
