@@ -53,6 +53,12 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
 /* Tuning / test hook for the two calls above: 0 = automatic, 1 = single-CTA 128-row tiles only, 2 = CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
 int pcdm_set_gemm_cta_group(int mode);
+int pcdm_set_gemm_max_stages(int n); /* experiment hook: cap the smem ring depth (2..8, default 8 = as deep as fits) */
+
+/* Caller-owned fp32 scratch for pcdm_gemm / pcdm_conv3x3 split-K (used for tile-starved shapes: few output tiles, long
+ * K — the 4x8 and 8x16 UNet levels): process-wide, single-stream use; must outlive every launch (and every captured
+ * CUDA graph) that may use it.  NULL / 0 disables split-K.  64 MiB covers every BASELINE configuration. */
+int pcdm_set_workspace(void* ptr, long long bytes);
 
 /* torch.nn.Conv2d(Cin, Cout, 3, stride, padding=1) on NHWC activations, implicit GEMM (no im2col buffer).
  * Replaces conv_in, conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2), Upsample2D.conv and conv_out

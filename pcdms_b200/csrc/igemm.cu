@@ -37,6 +37,8 @@ struct IGemmParams {
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
   uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
+  int splits;      // split-K factor (1 = off): tile index also enumerates the K slice; partials go to fp32 scratch
+  int kb_per_split;
   int stages;      // smem ring depth (runtime: depends on BN and on whether residual staging is needed)
   int nbuf;        // staging slots per epilogue warp (2, or 3 with a residual: one slot is being prefetched)
   const float* bias;
@@ -81,7 +83,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;   // m_tiles counts 128*CG-row tiles
+  const int mn_tiles = p.m_tiles * p.n_tiles;       // m_tiles counts 128*CG-row tiles
+  const int total_tiles = mn_tiles * p.splits;      // split-K: tile = split * mn_tiles + m_blk * n_tiles + n_blk
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int first_tile = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -118,15 +121,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     uint32_t phase = 0;
     const int hw = p.H * p.W;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int m_blk = mn / p.n_tiles, n_blk = mn % p.n_tiles;
       const int m0 = (m_blk * CG + (int)rank) * 128;
       int b0 = 0, y0 = 0;
       if (p.mode != 0) {
         b0 = m0 / hw;
         y0 = (m0 - b0 * hw) / p.W;
       }
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      int tap = 0, cb = kb_begin;
+      if (p.mode != 0) { tap = kb_begin / p.cblocks; cb = kb_begin - tap * p.cblocks; }
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
@@ -181,7 +188,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int split = tile / mn_tiles;
+      const int nkb = min(p.num_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -217,7 +226,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     const int nbuf = p.nbuf;
     const uint32_t tempty_addr[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int m_blk = mn / p.n_tiles, n_blk = mn % p.n_tiles;
       const int m_cta0 = (m_blk * CG + (int)rank) * 128;
       const int m_warp0 = m_cta0 + q * 32;
       const long long m = (long long)m_cta0 + row;
@@ -258,7 +268,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             }
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                   ((long long)split * p.M + m) * p.ldo + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
           }
@@ -416,10 +427,59 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   }
 }
 
+// Split-K finish: out[m, n] = act( sum_s part[s][m][n] + bias[n] + rowvec[m / hw][n] + residual[m][n] ), fixed
+// summation order (bit-reproducible); 8 columns per thread.
+template <int DT>
+__global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                     const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                     long long ld_rowvec, int hw, const void* __restrict__ residual, long long ldr,
+                                     void* __restrict__ out, long long ldo, int silu) {
+  using T = typename TypeOf<DT>::T;
+  const int nv = N / 8;
+  const long long total = (long long)M * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n0 = (int)(i % nv) * 8;
+    const long long m = i / nv;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) {
+      const float4* pp = reinterpret_cast<const float4*>(part + ((long long)sidx * M + m) * N + n0);
+      const float4 a = __ldg(pp), b = __ldg(pp + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bias) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n0)), b = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (rowvec) {
+      const float* rv = rowvec + (m / hw) * ld_rowvec + n0;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(rv)), b = __ldg(reinterpret_cast<const float4*>(rv + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (residual) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(residual) + m * ldr + n0));
+      float2 f;
+      f = unpack2<DT>(u.x); v[0] += f.x; v[1] += f.y;
+      f = unpack2<DT>(u.y); v[2] += f.x; v[3] += f.y;
+      f = unpack2<DT>(u.z); v[4] += f.x; v[5] += f.y;
+      f = unpack2<DT>(u.w); v[6] += f.x; v[7] += f.y;
+    }
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    uint4 o;
+    o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_SMEM_LIMIT = 227 * 1024;
+static int g_max_stages = IG_MAX_STAGES;  // tuning hook: cap on the smem ring depth (pcdm_set_gemm_max_stages)
 
 template <int BN, int DT, int CG>
 static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
@@ -433,6 +493,7 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
   if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
+  if (stages > g_max_stages) stages = g_max_stages;
   if (stages < 2) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: not enough shared memory for a 2-stage ring");
   p.stages = stages;
   const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
@@ -482,16 +543,56 @@ static int pick_bn(int m_tiles, int N, int geglu) {
 }
 
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
+static void* g_ws = nullptr;   // caller-owned fp32 scratch for split-K partials (pcdm_set_workspace)
+static long long g_ws_bytes = 0;
+
+struct EpiArgs {   // the fused-epilogue operands as the caller gave them
+  const float* bias;
+  const float* rowvec;
+  long long ld_rowvec;
+  int hw;
+  const void* residual;
+  long long ldr;
+  void* out;
+  long long ldo;
+  int silu;
+};
 
 static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, const void* residual, long long ldr,
                           cudaStream_t stream) {
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
+  // ---- split-K for tile-starved problems (the 4x8 / 8x16 levels: M = 64..2048 rows but K up to 23 040): slice K over
+  //      otherwise idle SMs into fp32 partials, then one small finishing kernel applies the epilogue ----
+  EpiArgs epi = {p.bias, p.rowvec, p.ld_rowvec, p.hw, residual, ldr, p.out, p.ldo, p.silu};
+  bool split = false;
+  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 16 && (p.N % 8) == 0) {
+    const int sbn = (p.N % 160 == 0) ? 160 : 128;
+    const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
+    if (tiles * 2 <= num_sms()) {
+      int splits = num_sms() / tiles;
+      if (splits > 8) splits = 8;
+      while (splits > 1 && p.num_kb / splits < 8) --splits;
+      const int kbps = (p.num_kb + splits - 1) / splits;
+      splits = (p.num_kb + kbps - 1) / kbps;
+      if (splits > 1 && (long long)splits * p.M * p.N * 4 <= g_ws_bytes) {
+        split = true;
+        bn = sbn;
+        p.splits = splits;
+        p.kb_per_split = kbps;
+        p.bias = nullptr; p.rowvec = nullptr; p.silu = 0;
+        p.out = g_ws; p.ldo = p.N; p.out_f32 = 1;
+        residual = nullptr;
+      }
+    }
+  }
   if (bn == 0) bn = pick_bn(p.m_tiles, p.N, p.geglu);
   // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles and the N tile can be halved on 8-row groups
   // (measured on B200: pairs win ~2-12% once the K loop is long enough to be operand-delivery bound, and lose on
   //  short-K GEMMs whose time is epilogue + prologue: K >= 2048 is the crossover)
   int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0 && p.num_kb >= 32) ? 2 : 1;
-  if (g_force_cg == 1) cg = 1;
-  if (g_force_cg == 2 && bn >= 128) cg = 2;
+  if (g_force_cg == 1 || split) cg = 1;
+  if (g_force_cg == 2 && bn >= 128 && !split) cg = 2;
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
   p.has_res = residual ? 1 : 0;
   if (p.has_res && (p.geglu || p.out_f32))
@@ -518,16 +619,31 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     const uint32_t box[2] = {64, (uint32_t)brows};
     PCDM_CHECK(make_tmap(&p.tmB, w, 2, dims, strides, box), "weight tensor map");
   }
+  int rc;
 #define PCDM_LAUNCH(BN_, CG_)                                                      \
   (dt == DT_F16 ? launch_igemm<BN_, DT_F16, CG_>(p, stream) : launch_igemm<BN_, DT_BF16, CG_>(p, stream))
   switch (bn) {
-    case 64: return PCDM_LAUNCH(64, 1);
-    case 128: return cg == 2 ? PCDM_LAUNCH(128, 2) : PCDM_LAUNCH(128, 1);
-    case 160: return cg == 2 ? PCDM_LAUNCH(160, 2) : PCDM_LAUNCH(160, 1);
-    case 256: return cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1);
+    case 64: rc = PCDM_LAUNCH(64, 1); break;
+    case 128: rc = cg == 2 ? PCDM_LAUNCH(128, 2) : PCDM_LAUNCH(128, 1); break;
+    case 160: rc = cg == 2 ? PCDM_LAUNCH(160, 2) : PCDM_LAUNCH(160, 1); break;
+    case 256: rc = cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1); break;
     default: return set_error(PCDM_ERR_INVALID, "igemm: BN must be 0, 64, 128, 160 or 256");
   }
 #undef PCDM_LAUNCH
+  if (rc != 0 || !split) return rc;
+  const long long total = (long long)p.M * (p.N / 8);
+  long long grid = (total + 255) / 256;
+  if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
+  if (dt == DT_F16)
+    splitk_finish_kernel<DT_F16><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N,
+                                                               epi.bias, epi.rowvec, epi.ld_rowvec, epi.hw, epi.residual,
+                                                               epi.ldr, epi.out, epi.ldo, epi.silu);
+  else
+    splitk_finish_kernel<DT_BF16><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g_ws), p.splits, p.M,
+                                                                p.N, epi.bias, epi.rowvec, epi.ld_rowvec, epi.hw,
+                                                                epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu);
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace pcdm
@@ -629,5 +745,21 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
 extern "C" int pcdm_set_gemm_cta_group(int mode) {
   if (mode < 0 || mode > 2) return set_error(PCDM_ERR_INVALID, "gemm cta group mode must be 0, 1 or 2");
   g_force_cg = mode;
+  return 0;
+}
+
+/* caller-owned fp32 scratch for split-K partial sums (process-wide, single-stream use); NULL / 0 disables split-K */
+extern "C" int pcdm_set_workspace(void* ptr, long long bytes) {
+  if (bytes < 0 || (ptr == nullptr && bytes != 0)) return set_error(PCDM_ERR_INVALID, "set_workspace: bad arguments");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(PCDM_ERR_INVALID, "set_workspace: pointer must be 16-byte aligned");
+  g_ws = ptr;
+  g_ws_bytes = bytes;
+  return 0;
+}
+
+/* tuning / experiment hook: cap the shared-memory ring depth of the GEMM/conv mainloop (2..8) */
+extern "C" int pcdm_set_gemm_max_stages(int n) {
+  if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
+  g_max_stages = n;
   return 0;
 }

@@ -33,6 +33,24 @@ def _f32(t):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# split-K scratch (process-wide, kept alive here; see pcdm_set_workspace)
+# ---------------------------------------------------------------------------------------------------------------
+_workspace = None
+
+
+def ensure_workspace(device, nbytes: int = 64 << 20):
+    """Give the library its fp32 split-K scratch on `device` (idempotent)."""
+    global _workspace
+    device = torch.device(device)
+    if device.type != "cuda":
+        return None
+    if _workspace is None or _workspace.device != device or _workspace.numel() < nbytes:
+        _workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _l.check(_l.load().pcdm_set_workspace(_l.ptr(_workspace), C.c_longlong(nbytes)), kernels=0)
+    return _workspace
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # weight packing (host side, done once at load time)
 # ---------------------------------------------------------------------------------------------------------------
 def pack_conv3x3_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

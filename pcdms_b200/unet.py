@@ -145,6 +145,7 @@ class B200UNet2DConditionModel:
         self._ctx_cache = None   # (tensor id, version, shape) -> per-block K/V
         self._pose_cache = None
         self._build_topology()
+        ops.ensure_workspace(self._device)
 
     # ------------------------------------------------------------------------------------------------------------
     # diffusers-style surface

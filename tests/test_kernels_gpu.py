@@ -25,6 +25,7 @@ def close(got, want, dt, mult=1.0):
 @pytest.fixture(scope="module")
 def ops():
     from pcdms_b200 import ops as _ops
+    _ops.ensure_workspace("cuda")   # enables split-K for the tile-starved shapes below
     return _ops
 
 
@@ -84,6 +85,28 @@ def test_conv3x3(ops, dt, B, H, W, Cin, Cout, stride, extra):
                       rowvec=t.cuda()[:, Cout:2 * Cout] if extra else None,
                       residual=r.permute(0, 2, 3, 1).contiguous().cuda() if extra else None, stride=stride)
     close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(16, 4, 8, 1280, 1280), (2, 8, 16, 2560, 1280), (2, 4, 8, 1920, 640)])
+def test_conv3x3_split_k_matches_single_pass(ops, B, H, W, Cin, Cout):
+    """Tile-starved shapes take the split-K route (fp32 partials + finishing kernel); forcing bn disables it.  Both
+    must agree with the oracle, and with each other to fp32-accumulation-order noise."""
+    dt = torch.float16
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dt)
+    b = torch.randn(Cout, generator=g)
+    t = torch.randn(B, Cout, generator=g)
+    r = torch.randn(B, Cout, H, W, generator=g).to(dt)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1) + t[:, :, None, None] + r.float()
+    xd, wd = x.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_conv3x3_weight(w, dt).cuda()
+    rd = r.permute(0, 2, 3, 1).contiguous().cuda()
+    auto = ops.conv3x3(xd, wd, bias=b.cuda(), rowvec=t.cuda(), residual=rd)
+    single = ops.conv3x3(xd, wd, bias=b.cuda(), rowvec=t.cuda(), residual=rd, bn=128)
+    close(auto.permute(0, 3, 1, 2), ref, dt)
+    close(single.permute(0, 3, 1, 2), ref, dt)
+    torch.testing.assert_close(auto.float(), single.float(), rtol=2e-3, atol=2e-3)
+    assert torch.equal(auto, ops.conv3x3(xd, wd, bias=b.cuda(), rowvec=t.cuda(), residual=rd))  # deterministic
 
 
 def test_conv3x3_rejects_unsupported_shapes(ops):

@@ -68,6 +68,36 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
+if which == "stages":
+    dt = torch.bfloat16
+    L = _plib.load()
+    x320 = torch.randn(16, 32, 64, 320, device=dev, dtype=dt); w320 = torch.randn(320, 2880, device=dev, dtype=dt)
+    x1280 = torch.randn(16, 8, 16, 1280, device=dev, dtype=dt); w1280 = torch.randn(1280, 11520, device=dev, dtype=dt)
+    a8k = torch.randn(8192, 8192, device=dev, dtype=dt); w8k = torch.randn(8192, 8192, device=dev, dtype=dt)
+    for name, fn, fl in [("conv320 bn160", lambda: ops.conv3x3(x320, w320, bn=160), 2 * 16 * 2048 * 320 * 2880),
+                         ("conv320 bn256", lambda: ops.conv3x3(x320, w320, bn=256), 2 * 16 * 2048 * 320 * 2880),
+                         ("conv1280@8x16 bn256", lambda: ops.conv3x3(x1280, w1280, bn=256), 2 * 16 * 128 * 1280 * 11520),
+                         ("conv1280@8x16 bn128", lambda: ops.conv3x3(x1280, w1280, bn=128), 2 * 16 * 128 * 1280 * 11520),
+                         ("gemm8k bn256", lambda: ops.gemm(a8k, w8k, bn=256), 2 * 8192 ** 3)]:
+        for cg in (1, 2):
+            set_cg(cg)
+            for st in (2, 3, 4, 5, 6, 8):
+                L.pcdm_set_gemm_max_stages(st)
+                ms = timeit(fn, 10)
+                res.append(dict(op="stages", name=name, cg=cg, max_stages=st, ms=ms, tflops=fl / ms / 1e9)); print(res[-1], flush=True)
+    L.pcdm_set_gemm_max_stages(8); set_cg(0)
+if which == "splitk":
+    ops.ensure_workspace("cuda")
+    dt = torch.bfloat16
+    x = torch.randn(16, 4, 8, 1280, device=dev, dtype=dt); w = torch.randn(1280, 11520, device=dev, dtype=dt)
+    x2 = torch.randn(16, 4, 8, 2560, device=dev, dtype=dt); w2 = torch.randn(1280, 23040, device=dev, dtype=dt)
+    b = torch.randn(1280, device=dev); r = torch.randn(16, 4, 8, 1280, device=dev, dtype=dt)
+    for name, fn, fl in [("conv1280@4x8 auto(splitK)", lambda: ops.conv3x3(x, w, bias=b, residual=r), 2 * 512 * 1280 * 11520),
+                         ("conv1280@4x8 bn64", lambda: ops.conv3x3(x, w, bias=b, residual=r, bn=64), 2 * 512 * 1280 * 11520),
+                         ("conv2560@4x8 auto(splitK)", lambda: ops.conv3x3(x2, w2, bias=b, residual=r), 2 * 512 * 1280 * 23040),
+                         ("conv2560@4x8 bn64", lambda: ops.conv3x3(x2, w2, bias=b, residual=r, bn=64), 2 * 512 * 1280 * 23040)]:
+        ms = timeit(fn, 20)
+        res.append(dict(op="splitk", name=name, ms=ms, tflops=fl / ms / 1e9)); print(res[-1], flush=True)
 if which == "cg2":
     set_cg(2)
     for dt in (torch.float16, torch.bfloat16):
