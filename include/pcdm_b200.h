@@ -36,6 +36,9 @@ extern "C" {
 #define PCDM_FLAG_SILU 4    /* norm kernels: apply SiLU after the affine */
 
 int pcdm_abi_version(void);
+/* 1 (default): every kernel is launched with programmatic dependent launch, so its prologue overlaps the tail of its
+ * stream predecessor (each kernel waits for that predecessor before its first global-memory access).  0: plain. */
+int pcdm_set_pdl(int enabled);
 const char* pcdm_last_error(void);
 
 /* torch.nn.Linear (+ fused epilogues).  Replaces the nn.Linear calls inside diffusers Transformer2DModel /

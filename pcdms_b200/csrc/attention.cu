@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   uint64_t* pv_done = p_full + 1;                // MMA -> softmax: PV_j retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
   const int bh = blockIdx.x / p.q_tiles;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -139,20 +141,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
       const int kv_left = p.Skv - j * 128;  // valid columns in this block
-      // ---- pass 1: row maximum ----
+      // ---- pass 1: row maximum (chunk loads double-buffered against the max reduction) ----
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem + lane_off + ATT_TMEM_S + c * 32, s);
+      const bool full_block = kv_left >= 128;
+      {
+        uint32_t sa[32], sb[32];
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S, sa);
         tc_wait_ld();
-        if (kv_left - c * 32 >= 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? sb : sa;
+          uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
+          if (c < 3) tmem_ld32(tmem + lane_off + ATT_TMEM_S + (c + 1) * 32, nxt);
+          if (full_block) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          }
+          if (c < 3) tc_wait_ld();
         }
       }
       mx *= p.scale_log2;
@@ -184,32 +193,48 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
           m_ref = m_new;
         }
       }
-      // ---- pass 2: p = exp2(s * scale - m_ref), row sum, 16-bit pack into the P columns ----
+      // ---- pass 2: p = exp2(s * scale - m_ref), row sum, 16-bit pack into the P columns (loads double-buffered) ----
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem + lane_off + ATT_TMEM_S + c * 32, s);
+      {
+        uint32_t sa[32], sb[32];
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S, sa);
         tc_wait_ld();
-        if (c == 3) {  // S_j fully consumed: the MMA warp may overwrite the score columns with Q K_{j+1}^T
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);
-        }
-        uint32_t pk[16];
-        const int left = kv_left - c * 32;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = exp2f(__uint_as_float(s[2 * i]) * p.scale_log2 - m_ref);
-          float bq = exp2f(__uint_as_float(s[2 * i + 1]) * p.scale_log2 - m_ref);
-          if (left < 32) {
-            if (2 * i >= left) a = 0.f;
-            if (2 * i + 1 >= left) bq = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? sb : sa;
+          uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
+          if (c < 3) tmem_ld32(tmem + lane_off + ATT_TMEM_S + (c + 1) * 32, nxt);
+          uint32_t pk[16];
+          if (full_block) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = exp2f(__uint_as_float(cur[2 * i]) * p.scale_log2 - m_ref);
+              const float bq = exp2f(__uint_as_float(cur[2 * i + 1]) * p.scale_log2 - m_ref);
+              sum += a + bq;
+              pk[i] = pack2<DT>(a, bq);
+            }
+          } else {
+            const int left = kv_left - c * 32;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = exp2f(__uint_as_float(cur[2 * i]) * p.scale_log2 - m_ref);
+              float bq = exp2f(__uint_as_float(cur[2 * i + 1]) * p.scale_log2 - m_ref);
+              if (2 * i >= left) a = 0.f;
+              if (2 * i + 1 >= left) bq = 0.f;
+              sum += a + bq;
+              pk[i] = pack2<DT>(a, bq);
+            }
           }
-          sum += a + bq;
-          pk[i] = pack2<DT>(a, bq);
+          tmem_st16(tmem + lane_off + ATT_TMEM_P + c * 16, pk);
+          if (c < 3) {
+            tc_wait_ld();
+            if (c == 2) {  // the last score chunk is now in registers: S_j may be overwritten by Q K_{j+1}^T
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_free);
+            }
+          }
         }
-        tmem_st16(tmem + lane_off + ATT_TMEM_P + c * 16, pk);
       }
       l += sum;
       tc_wait_st();
@@ -288,8 +313,10 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
     configured = true;
   }
   const int grid = B * heads * p.q_tiles;
-  if (dtype == DT_F16) attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(p);
-  else attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(p);
+  if (dtype == DT_F16)
+    PCDM_CUDA(launch_kernel(attention_kernel<DT_F16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
+  else
+    PCDM_CUDA(launch_kernel(attention_kernel<DT_BF16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -122,6 +122,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): every kernel lets its successor start early and itself waits for its
+//      predecessor right before the first global-memory access, so launch latency + prologues overlap kernel tails.
+//      Both instructions are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cluster / CTA-pair (cta_group::2) helpers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

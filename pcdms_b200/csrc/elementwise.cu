@@ -30,6 +30,8 @@ __device__ __forceinline__ void store_any(void* p, long long i, int dt, float v)
 // [B, C, HW] (any float dtype) -> [B, HW, Cpad] 16-bit, channels >= C zero-filled.  One thread per (pixel, 8 ch).
 __global__ void nchw_to_nhwc_pad_kernel(const void* __restrict__ x, int src_dt, void* __restrict__ y, int dst_dt, int B,
                                         int C, int HW, int Cpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * HW * (Cpad / 8);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % (Cpad / 8));
@@ -57,6 +59,8 @@ __global__ void nchw_to_nhwc_pad_kernel(const void* __restrict__ x, int src_dt, 
 // [B, HW, ldc] (src dtype) channels [0, C) -> [B, C, HW] (dst dtype)
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int src_dt, long long ldc, void* __restrict__ y,
                                     int dst_dt, int B, int C, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * C * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % HW);
@@ -71,6 +75,8 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int src_dt, long
 // t may be a single value broadcast to all rows (t_count == 1) or one per row.  fp32 math, 16-bit store.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int t_count, void* __restrict__ out, int dt,
                                           int B, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -87,6 +93,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int t_cou
 // y[b, 2h+dy, 2w+dx, :] = x[b, h, w, :]
 __global__ void upsample_nearest2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
                                           int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * (2 * H) * (2 * W) * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -112,6 +120,8 @@ __global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, l
                                      float* __restrict__ latents, void* __restrict__ x9, int x9_dt, long long ld_x9,
                                      const float4* __restrict__ coef, int* __restrict__ step_counter, float guidance,
                                      int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = *step_counter;
   const float4 cf = coef[step];
   const long long total = (long long)n * HW;
@@ -152,6 +162,8 @@ __global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, l
 __global__ void add_noise_kernel(const void* __restrict__ x0, const void* __restrict__ noise, void* __restrict__ out,
                                  int dt, const float* __restrict__ alphas_cumprod, const long long* __restrict__ t,
                                  int B, long long per_sample) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * per_sample;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per_sample);
@@ -164,6 +176,8 @@ __global__ void add_noise_kernel(const void* __restrict__ x0, const void* __rest
 // stand-alone scheduler.step: prev = c2 * (x - c1 * eps) * c0 + c3 * eps   (same arithmetic as the fused kernel)
 __global__ void ddim_step_kernel(const void* __restrict__ eps, int eps_dt, const void* __restrict__ x, void* __restrict__ out,
                                  int dt, float c0, float c1, float c2, float c3, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float e = load_any(eps, i, eps_dt);
     const float x0 = (load_any(x, i, dt) - c1 * e) * c0;
@@ -189,7 +203,7 @@ extern "C" int pcdm_nchw_to_nhwc_pad(const void* x, int src_dtype, void* y, int 
   if (src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 1) return set_error(PCDM_ERR_INVALID, "nchw_to_nhwc_pad: bad dtype");
   if (B <= 0 || C <= 0 || HW <= 0 || Cpad < C || Cpad % 8) return set_error(PCDM_ERR_INVALID, "nchw_to_nhwc_pad: bad shape");
   const long long total = (long long)B * HW * (Cpad / 8);
-  nchw_to_nhwc_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, src_dtype, y, dst_dtype, B, C, HW, Cpad);
+  PCDM_CUDA(launch_kernel(nchw_to_nhwc_pad_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, x, src_dtype, y, dst_dtype, B, C, HW, Cpad));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -200,7 +214,7 @@ extern "C" int pcdm_nhwc_to_nchw(const void* x, int src_dtype, long long ldc, vo
   if (src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 2) return set_error(PCDM_ERR_INVALID, "nhwc_to_nchw: bad dtype");
   if (B <= 0 || C <= 0 || HW <= 0 || ldc < C) return set_error(PCDM_ERR_INVALID, "nhwc_to_nchw: bad shape");
   const long long total = (long long)B * C * HW;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, src_dtype, ldc, y, dst_dtype, B, C, HW);
+  PCDM_CUDA(launch_kernel(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, x, src_dtype, ldc, y, dst_dtype, B, C, HW));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -211,7 +225,7 @@ extern "C" int pcdm_timestep_embedding(const float* t, int t_count, void* out, i
   if (dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "timestep_embedding: bad dtype");
   if (B <= 0 || dim <= 0 || dim % 2 || (t_count != 1 && t_count != B)) return set_error(PCDM_ERR_INVALID, "timestep_embedding: bad shape");
   const int total = B * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(t, t_count, out, dtype, B, dim);
+  PCDM_CUDA(launch_kernel(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream_, 1, t, t_count, out, dtype, B, dim));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -220,8 +234,7 @@ extern "C" int pcdm_upsample_nearest2x(const void* x, void* y, int B, int H, int
   if (!x || !y) return set_error(PCDM_ERR_INVALID, "upsample: null pointer");
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return set_error(PCDM_ERR_INVALID, "upsample: bad shape (C % 8 == 0)");
   const long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample_nearest2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  PCDM_CUDA(launch_kernel(upsample_nearest2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), B, H, W, C / 8));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -235,9 +248,7 @@ extern "C" int pcdm_cfg_ddim_step(const void* eps, int eps_dtype, long long ld_e
   if (n <= 0 || HW <= 0 || ld_eps < 4 || ld_x9 < 4) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: bad shape");
   if (reinterpret_cast<uintptr_t>(coef_table) & 15) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: coef table must be 16-byte aligned");
   const long long total = (long long)n * HW;
-  cfg_ddim_step_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream_>>>(
-      eps, eps_dtype, ld_eps, latents, x9, x9_dtype, ld_x9, reinterpret_cast<const float4*>(coef_table), step_counter,
-      guidance_scale, n, HW, t_table, t_cur);
+  PCDM_CUDA(launch_kernel(cfg_ddim_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, latents, x9, x9_dtype, ld_x9, reinterpret_cast<const float4*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -248,8 +259,7 @@ extern "C" int pcdm_add_noise(const void* x0, const void* noise, void* out, int 
   if (dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "add_noise: bad dtype");
   if (B <= 0 || per_sample <= 0) return set_error(PCDM_ERR_INVALID, "add_noise: empty problem");
   const long long total = (long long)B * per_sample;
-  add_noise_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x0, noise, out, dtype, alphas_cumprod,
-                                                                              timesteps, B, per_sample);
+  PCDM_CUDA(launch_kernel(add_noise_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, x0, noise, out, dtype, alphas_cumprod, timesteps, B, per_sample));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -260,9 +270,7 @@ extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const voi
   if (!model_output || !sample || !prev_sample) return set_error(PCDM_ERR_INVALID, "ddim_step: null pointer");
   if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "ddim_step: bad dtype");
   if (numel <= 0) return set_error(PCDM_ERR_INVALID, "ddim_step: empty problem");
-  ddim_step_kernel<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream_>>>(
-      model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev,
-      sqrt_one_minus_a_prev, numel);
+  PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, numel));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

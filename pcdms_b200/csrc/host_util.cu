@@ -4,6 +4,7 @@
 namespace pcdm {
 
 static thread_local char g_err[512] = "";
+int g_pdl_enabled = 1;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -77,3 +78,8 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 extern "C" const char* pcdm_last_error(void) { return pcdm::g_err; }
 
 extern "C" int pcdm_abi_version(void) { return PCDM_ABI_VERSION; }
+
+extern "C" int pcdm_set_pdl(int enabled) {
+  pcdm::g_pdl_enabled = enabled ? 1 : 0;
+  return 0;
+}

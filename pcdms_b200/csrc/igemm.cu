@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   const int mn_tiles = p.m_tiles * p.n_tiles;       // m_tiles counts 128*CG-row tiles
   const int total_tiles = mn_tiles * p.splits;      // split-K: tile = split * mn_tiles + m_blk * n_tiles + n_blk
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  pdl_launch_dependents();
   const int first_tile = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -435,6 +437,8 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
                                      long long ld_rowvec, int hw, const void* __restrict__ residual, long long ldr,
                                      void* __restrict__ out, long long ldo, int silu) {
   using T = typename TypeOf<DT>::T;
+  pdl_launch_dependents();
+  pdl_wait();
   const int nv = N / 8;
   const long long total = (long long)M * nv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -500,24 +504,11 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles;
   if (CG == 1) {
     const int grid = total < num_sms() ? total : num_sms();
-    igemm_kernel<BN, DT, CG><<<grid, IG_THREADS, smem_bytes, stream>>>(p);
+    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG>, dim3(grid), dim3(IG_THREADS), smem_bytes, stream, 1, p));
   } else {
     const int pairs = num_sms() / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(IG_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PCDM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DT, CG>, p));
+    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG>, dim3(grid), dim3(IG_THREADS), smem_bytes, stream, 2, p));
   }
   PCDM_CUDA(cudaGetLastError());
   return 0;
@@ -635,13 +626,13 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   long long grid = (total + 255) / 256;
   if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
   if (dt == DT_F16)
-    splitk_finish_kernel<DT_F16><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N,
-                                                               epi.bias, epi.rowvec, epi.ld_rowvec, epi.hw, epi.residual,
-                                                               epi.ldr, epi.out, epi.ldo, epi.silu);
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, dim3((int)grid), dim3(256), 0, stream, 1,
+                            reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
   else
-    splitk_finish_kernel<DT_BF16><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g_ws), p.splits, p.M,
-                                                                p.N, epi.bias, epi.rowvec, epi.ld_rowvec, epi.hw,
-                                                                epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu);
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_BF16>, dim3((int)grid), dim3(256), 0, stream, 1,
+                            reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -30,6 +30,8 @@ __host__ __device__ inline size_t gn_align(size_t x) { return (x + 255) / 256 * 
 template <int DT>
 __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1, int C, int HW,
                                 int groups, int pix_per_cta, float eps, GnWorkspace ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T = typename TypeOf<DT>::T;
   extern __shared__ float sm[];  // [2][PY][C] per-(py, channel) partials; then [2][C] per-channel sums
   const int b = blockIdx.y;
@@ -110,6 +112,8 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
                                 int groups, int pix_per_cta, const float2* __restrict__ final_stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 void* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T = typename TypeOf<DT>::T;
   const int b = blockIdx.y;
   const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
@@ -154,6 +158,8 @@ template <int DT, int VPL>  // VPL = 16-byte vectors per lane
 __global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y, long long ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int M,
                                  int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T = typename TypeOf<DT>::T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -265,13 +271,15 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
   if (smem > 48 * 1024) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm: statistics staging exceeds 48 KB");
   const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   if (dtype == DT_F16) {
-    gn_stats_kernel<DT_F16><<<grid, block, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, eps, ws);
-    gn_apply_kernel<DT_F16><<<grid, block, 0, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, ws.final_stats, gamma,
-                                                        beta, silu, y);
+    PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_F16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
+                            pix_per_cta, eps, ws));
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)ws.final_stats, gamma, beta, silu, y));
   } else {
-    gn_stats_kernel<DT_BF16><<<grid, block, smem, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, eps, ws);
-    gn_apply_kernel<DT_BF16><<<grid, block, 0, stream>>>(x1, x2, C1, C, HW, groups, pix_per_cta, ws.final_stats, gamma,
-                                                         beta, silu, y);
+    PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_BF16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
+                            pix_per_cta, eps, ws));
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)ws.final_stats, gamma, beta, silu, y));
   }
   PCDM_CUDA(cudaGetLastError());
   return 0;
@@ -289,8 +297,10 @@ extern "C" int pcdm_layernorm(const void* x, long long ldx, void* y, long long l
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
 #define LN_LAUNCH(V)                                                                                              \
   do {                                                                                                            \
-    if (dtype == DT_F16) layernorm_kernel<DT_F16, V><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, gamma, beta, eps, M, C); \
-    else layernorm_kernel<DT_BF16, V><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, gamma, beta, eps, M, C);          \
+    cudaError_t _le = (dtype == DT_F16)                                                                           \
+        ? launch_kernel(layernorm_kernel<DT_F16, V>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C)  \
+        : launch_kernel(layernorm_kernel<DT_BF16, V>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C); \
+    if (_le != cudaSuccess) return set_error(PCDM_ERR_CUDA, "layernorm launch failed: %s", cudaGetErrorString(_le)); \
   } while (0)
   switch (vpl) {
     case 1: LN_LAUNCH(1); break;

@@ -59,6 +59,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     mode = os.environ.get("PCDM_GEMM_CTA_GROUP")  # tuning hook: 1 = single-CTA tiles, 2 = CTA pairs, unset = auto
     if mode:
         lib.pcdm_set_gemm_cta_group(C.c_int(int(mode)))
+    if os.environ.get("PCDM_PDL") is not None:   # tuning hook: 0 disables programmatic dependent launch
+        lib.pcdm_set_pdl(C.c_int(int(os.environ["PCDM_PDL"])))
     _lib = lib
     return lib
 
