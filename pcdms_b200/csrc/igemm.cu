@@ -501,7 +501,7 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   if (stages < 2) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: not enough shared memory for a 2-stage ring");
   p.stages = stages;
   const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.splits;
   if (CG == 1) {
     const int grid = total < num_sms() ? total : num_sms();
     PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG>, dim3(grid), dim3(IG_THREADS), smem_bytes, stream, 1, p));
