@@ -37,6 +37,7 @@ struct IGemmParams {
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
   uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
+  int split_producer;  // experiment: warp 3 issues the B loads, warp 0 the A loads
   int splits;      // split-K factor (1 = off): tile index also enumerates the K slice; partials go to fp32 scratch
   int kb_per_split;
   int stages;      // smem ring depth (runtime: depends on BN and on whether residual staging is needed)
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             }
             if (++cb == p.cblocks) { cb = 0; ++tap; }
           }
-          tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+          if (!p.split_producer) tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
         } else {
           // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
           if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
@@ -176,6 +177,22 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
         }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3 && lane == 0 && CG == 1 && p.split_producer) {
+    // ===================== second TMA producer (experiment): weight tiles =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int n_blk = mn % p.n_tiles;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sb = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+        tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -515,11 +532,13 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
 }
 
 static int pick_bn(int m_tiles, int N, int geglu) {
-  // minimise (waves x per-tile cost); small-N tiles are shared-memory-bandwidth bound on a single CTA
+  // Measured on B200 (tools/autotune.py): the time of one output tile is nearly independent of its width for
+  // BN in 64..256 (the mainloop is paced per k-block, not per MMA column), so the best BN is the one that needs the
+  // fewest waves of tiles; ties go to the wider tile (fewer A re-reads).  A narrow tile only wins when it avoids
+  // padding waste that costs a whole extra wave.
   const int cand[4] = {256, 160, 128, 64};
-  const float eff[4] = {1.0f, 1.0f, 1.05f, 1.5f};
   int best = 128;
-  float best_cost = 1e30f;
+  long long best_waves = 1LL << 60, best_pad = 1LL << 60;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
     if (geglu && (bn % 64)) continue;
@@ -527,13 +546,14 @@ static int pick_bn(int m_tiles, int N, int geglu) {
     const int n_tiles = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_tiles;
     const long long waves = (tiles + num_sms() - 1) / num_sms();
-    const float cost = (float)waves * bn * eff[i];
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    const long long pad = (long long)n_tiles * bn - N;   // wasted MMA columns
+    if (waves < best_waves || (waves == best_waves && pad < best_pad)) { best_waves = waves; best_pad = pad; best = bn; }
   }
   return best;
 }
 
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
+static int g_split_producer = 0;  // experiment: issue the A and B TMA loads from two different threads
 static void* g_ws = nullptr;   // caller-owned fp32 scratch for split-K partials (pcdm_set_workspace)
 static long long g_ws_bytes = 0;
 
@@ -553,6 +573,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
                           cudaStream_t stream) {
   p.splits = 1;
   p.kb_per_split = p.num_kb;
+  p.split_producer = g_split_producer;
   // ---- split-K for tile-starved problems (the 4x8 / 8x16 levels: M = 64..2048 rows but K up to 23 040): slice K over
   //      otherwise idle SMs into fp32 partials, then one small finishing kernel applies the epilogue ----
   EpiArgs epi = {p.bias, p.rowvec, p.ld_rowvec, p.hw, residual, ldr, p.out, p.ldo, p.silu};
@@ -582,6 +603,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   // (measured on B200: pairs win ~2-12% once the K loop is long enough to be operand-delivery bound, and lose on
   //  short-K GEMMs whose time is epilogue + prologue: K >= 2048 is the crossover)
   int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0 && p.num_kb >= 32) ? 2 : 1;
+  if (g_split_producer) cg = 1;
   if (g_force_cg == 1 || split) cg = 1;
   if (g_force_cg == 2 && bn >= 128 && !split) cg = 2;
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
@@ -752,5 +774,11 @@ extern "C" int pcdm_set_workspace(void* ptr, long long bytes) {
 extern "C" int pcdm_set_gemm_max_stages(int n) {
   if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
   g_max_stages = n;
+  return 0;
+}
+
+/* experiment hook: 1 = issue activation and weight TMA loads from two different threads (single-CTA tiles only) */
+extern "C" int pcdm_set_gemm_split_producer(int on) {
+  g_split_producer = on ? 1 : 0;
   return 0;
 }
