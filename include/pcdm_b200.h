@@ -56,7 +56,6 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
 /* Tuning / test hook for the two calls above: 0 = automatic, 1 = single-CTA 128-row tiles only, 2 = CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
 int pcdm_set_gemm_cta_group(int mode);
-int pcdm_set_gemm_split_producer(int on); /* experiment hook: A and B TMA loads issued by two threads */
 int pcdm_set_gemm_max_stages(int n); /* experiment hook: cap the smem ring depth (2..8, default 8 = as deep as fits) */
 
 /* Caller-owned fp32 scratch for pcdm_gemm / pcdm_conv3x3 split-K (used for tile-starved shapes: few output tiles, long

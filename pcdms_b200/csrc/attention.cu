@@ -2,16 +2,17 @@
 //
 // One CTA per (batch, head, 128-query tile), TWO CTAs resident per SM: while one CTA's softmax warps work through a
 // score tile, the other CTA's MMAs own the tensor pipe (at d = 64 the exponentials, not the MMAs, are the scarce
-// resource: 16 ex2/clk/SM vs 128x128 scores per 512 tensor cycles).  192 threads: warp 0 = TMA producer (Q once, then
-// a 2-deep K/V ring) + TMEM allocator, warp 1 = tcgen05.mma issuer, warps 2-5 = softmax (thread t owns query row t:
-// with the 32x32b TMEM access pattern a row's scores sit in one thread, so row max / row sum need no shuffles).
+// resource: 16 ex2/clk/SM vs 128x128 scores per 512 tensor cycles).  320 threads: warp 0 = TMA producer (Q once, then
+// a 2-deep K/V ring) + TMEM allocator, warp 1 = tcgen05.mma issuer, warps 2-9 = softmax: two warps per TMEM lane
+// quadrant, each owning one query row per thread and HALF of the 128 score columns (with the 32x32b TMEM access
+// pattern a thread reads its row's scores directly; the two half-row maxima / sums meet in shared memory).
 //
 // TMEM (256 columns per CTA):  S : 128 fp32 score columns            (QK^T, SS MMA)
 //                              P : 64 columns = 128 x 128 fp16/bf16 probabilities, consumed by the PV MMA straight
 //                                  from tensor memory (A operand in TMEM) — P never touches shared memory
 //                              O : 64 fp32 columns, accumulated across KV blocks inside the tensor core
-// Softmax is two passes over the TMEM score tile (row max, then exp/sum/pack) so the row never has to live in
-// registers at once (<= 128 registers/thread -> 2 CTAs/SM).  The running maximum is applied lazily: O and l are
+// A warp's 64 scores are read from TMEM once and stay in registers (the score columns are released to the next
+// Q K^T immediately); <= 102 registers/thread keeps 2 CTAs/SM.  The running maximum is applied lazily: O and l are
 // rescaled (TMEM round trip by the softmax warps) only when a row's maximum grows by more than 2^8.
 // V is consumed in its natural [kv, d] layout as an MN-major B operand, K as a K-major B operand.
 //
@@ -32,12 +33,17 @@ struct AttnParams {
   float scale_log2;    // softmax scale * log2(e)
 };
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;   // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax (2 per TMEM quadrant)
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + 1024 + 256;
+constexpr int ATT_XCH_BYTES = 2 * 2 * 128 * 4 + 2 * 128 * 4;   // row-max exchange [parity][half][row] + row-sum [half][row]
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + ATT_XCH_BYTES + 1024 + 256;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_TMEM_S = 0, ATT_TMEM_P = 128, ATT_TMEM_O = 192;
+
+__device__ __forceinline__ void pair_barrier(int q) {   // the two softmax warps that share TMEM quadrant q
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+}
 
 template <int DT>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -45,13 +51,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + ATT_TILE_BYTES;  // stage s: K at s*2*TILE, V at s*2*TILE + TILE
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));
+  float* xmax = reinterpret_cast<float*>(smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));   // [2][2][128]
+  float* xsum = xmax + 2 * 2 * 128;                                                          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + ATT_XCH_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                  // [2]
   uint64_t* kv_empty = kv_full + ATT_KV_STAGES;  // [2]
   uint64_t* s_full = kv_empty + ATT_KV_STAGES;   // MMA -> softmax: S_j landed
-  uint64_t* s_free = s_full + 1;                 // softmax -> MMA: S_j fully read (4 warp arrivals)
-  uint64_t* p_full = s_free + 1;                 // softmax -> MMA: P_j written, O corrected (4 warp arrivals)
+  uint64_t* s_free = s_full + 1;                 // softmax -> MMA: S_j is in registers (8 warp arrivals)
+  uint64_t* p_full = s_free + 1;                 // softmax -> MMA: P_j written, O corrected (8 warp arrivals)
   uint64_t* pv_done = p_full + 1;                // MMA -> softmax: PV_j retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
@@ -69,8 +77,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(p_full, 4);
+    mbar_init(s_free, 8);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       auto issue_qk = [&](int j) {
         const int stage = j & 1;
         mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
-        if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax has read S_{j-1} out of the score columns
+        if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax holds S_{j-1} in registers
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
 #pragma unroll
@@ -130,41 +138,46 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ==========
+    // ===================== softmax / correction / epilogue =====================
+    // warps 2..9: TMEM quadrant q = warp & 3 (rows 32q..32q+31); `half` selects which 64 of the 128 score columns
+    // (and which 32 of the 64 output columns) this warp owns.  The two warps of a quadrant exchange row maxima and,
+    // at the end, row sums through shared memory.
     using T = typename TypeOf<DT>::T;
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float m_ref = -INFINITY;  // reference maximum (log2 domain) the accumulators are relative to
-    float l = 0.f;
+    float l = 0.f;            // this warp's share of the row sum
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
-      const int kv_left = p.Skv - j * 128;  // valid columns in this block
-      // ---- pass 1: row maximum (chunk loads double-buffered against the max reduction) ----
-      float mx = -INFINITY;
-      const bool full_block = kv_left >= 128;
+      const int kv_left = p.Skv - j * 128 - half * 64;  // valid columns among this warp's 64
+      uint32_t s[64];
       {
-        uint32_t sa[32], sb[32];
-        tmem_ld32(tmem + lane_off + ATT_TMEM_S, sa);
+        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S + half * 64, s0);
+        tmem_ld32(tmem + lane_off + ATT_TMEM_S + half * 64 + 32, s1);
         tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? sb : sa;
-          uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
-          if (c < 3) tmem_ld32(tmem + lane_off + ATT_TMEM_S + (c + 1) * 32, nxt);
-          if (full_block) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(cur[i]));
-          }
-          if (c < 3) tc_wait_ld();
-        }
       }
-      mx *= p.scale_log2;
+      // S_j now lives in registers: the MMA warp may overwrite the score columns with Q K_{j+1}^T
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      float mx = -INFINITY;
+      if (kv_left >= 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      float* xm = xmax + (j & 1) * 256;
+      xm[half * 128 + row] = mx;
+      pair_barrier(q);
+      mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]) * p.scale_log2;
       // P (and O, if a rescale is needed) may only be touched once PV_{j-1} has retired
       if (j > 0) {
         mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
@@ -174,67 +187,47 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
         m_ref = mx;
       } else {
         const bool grow = mx > m_ref + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {   // both warps of the pair see the same rows => the same decision
           const float m_new = grow ? mx : m_ref;
           const float alpha = exp2f(m_ref - m_new);
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
+            uint32_t o[16];
+            tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
-            uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
-            tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32, lo);
-            tmem_st16(tmem + lane_off + ATT_TMEM_O + c * 32 + 16, hi);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
           }
           l *= alpha;
           m_ref = m_new;
         }
       }
-      // ---- pass 2: p = exp2(s * scale - m_ref), row sum, 16-bit pack into the P columns (loads double-buffered) ----
+      // p = exp2(s * scale - m_ref), row sum, 16-bit pack into this warp's 32 P columns
       float sum = 0.f;
-      {
-        uint32_t sa[32], sb[32];
-        tmem_ld32(tmem + lane_off + ATT_TMEM_S, sa);
-        tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? sb : sa;
-          uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
-          if (c < 3) tmem_ld32(tmem + lane_off + ATT_TMEM_S + (c + 1) * 32, nxt);
-          uint32_t pk[16];
-          if (full_block) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+        if (kv_left >= 64) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = exp2f(__uint_as_float(cur[2 * i]) * p.scale_log2 - m_ref);
-              const float bq = exp2f(__uint_as_float(cur[2 * i + 1]) * p.scale_log2 - m_ref);
-              sum += a + bq;
-              pk[i] = pack2<DT>(a, bq);
-            }
-          } else {
-            const int left = kv_left - c * 32;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = exp2f(__uint_as_float(cur[2 * i]) * p.scale_log2 - m_ref);
-              float bq = exp2f(__uint_as_float(cur[2 * i + 1]) * p.scale_log2 - m_ref);
-              if (2 * i >= left) a = 0.f;
-              if (2 * i + 1 >= left) bq = 0.f;
-              sum += a + bq;
-              pk[i] = pack2<DT>(a, bq);
-            }
+          for (int i = 0; i < 16; ++i) {
+            const float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
+            const float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
+            sum += a + bq;
+            pk[i] = pack2<DT>(a, bq);
           }
-          tmem_st16(tmem + lane_off + ATT_TMEM_P + c * 16, pk);
-          if (c < 3) {
-            tc_wait_ld();
-            if (c == 2) {  // the last score chunk is now in registers: S_j may be overwritten by Q K_{j+1}^T
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_free);
-            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
+            float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
+            if (c * 32 + 2 * i >= kv_left) a = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_left) bq = 0.f;
+            sum += a + bq;
+            pk[i] = pack2<DT>(a, bq);
           }
         }
+        tmem_st16(tmem + lane_off + ATT_TMEM_P + half * 32 + c * 16, pk);
       }
       l += sum;
       tc_wait_st();
@@ -242,26 +235,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l
+    // epilogue: O / l  (row sum = both halves)
+    xsum[half * 128 + row] = l;
+    pair_barrier(q);
+    const float inv_l = 1.0f / (l + xsum[(half ^ 1) * 128 + row]);
     mbar_wait(pv_done, (uint32_t)((n_kv - 1) & 1));
     tc_fence_after();
-    const float inv_l = 1.0f / l;
     const long long qrow = (long long)qt * 128 + row;
-    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64;
+    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64 + half * 32;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem + lane_off + ATT_TMEM_O + c * 32, o);
+      uint32_t o[16];
+      tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
       tc_wait_ld();
       if (qrow < p.Sq) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           uint4 u;
           u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
           u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
           u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
           u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = u;
+          *reinterpret_cast<uint4*>(op + c * 16 + i * 8) = u;
         }
       }
     }

@@ -37,7 +37,6 @@ struct IGemmParams {
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
   uint32_t a_bytes, b_bytes;  // bytes one A / B box load delivers (boxes are clamped to the tensor extent)
-  int split_producer;  // experiment: warp 3 issues the B loads, warp 0 the A loads
   int splits;      // split-K factor (1 = off): tile index also enumerates the K slice; partials go to fp32 scratch
   int kb_per_split;
   int stages;      // smem ring depth (runtime: depends on BN and on whether residual staging is needed)
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             }
             if (++cb == p.cblocks) { cb = 0; ++tap; }
           }
-          if (!p.split_producer) tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+          tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
         } else {
           // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
           if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
@@ -177,22 +176,6 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 3 && lane == 0 && CG == 1 && p.split_producer) {
-    // ===================== second TMA producer (experiment): weight tiles =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
-      const int n_blk = mn % p.n_tiles;
-      const int kb_begin = split * p.kb_per_split;
-      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sb = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-        tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -553,7 +536,6 @@ static int pick_bn(int m_tiles, int N, int geglu) {
 }
 
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
-static int g_split_producer = 0;  // experiment: issue the A and B TMA loads from two different threads
 static void* g_ws = nullptr;   // caller-owned fp32 scratch for split-K partials (pcdm_set_workspace)
 static long long g_ws_bytes = 0;
 
@@ -573,7 +555,6 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
                           cudaStream_t stream) {
   p.splits = 1;
   p.kb_per_split = p.num_kb;
-  p.split_producer = g_split_producer;
   // ---- split-K for tile-starved problems (the 4x8 / 8x16 levels: M = 64..2048 rows but K up to 23 040): slice K over
   //      otherwise idle SMs into fp32 partials, then one small finishing kernel applies the epilogue ----
   EpiArgs epi = {p.bias, p.rowvec, p.ld_rowvec, p.hw, residual, ldr, p.out, p.ldo, p.silu};
@@ -603,7 +584,6 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   // (measured on B200: pairs win ~2-12% once the K loop is long enough to be operand-delivery bound, and lose on
   //  short-K GEMMs whose time is epilogue + prologue: K >= 2048 is the crossover)
   int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0 && p.num_kb >= 32) ? 2 : 1;
-  if (g_split_producer) cg = 1;
   if (g_force_cg == 1 || split) cg = 1;
   if (g_force_cg == 2 && bn >= 128 && !split) cg = 2;
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
@@ -767,6 +747,13 @@ extern "C" int pcdm_set_workspace(void* ptr, long long bytes) {
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(PCDM_ERR_INVALID, "set_workspace: pointer must be 16-byte aligned");
   g_ws = ptr;
   g_ws_bytes = bytes;
+  return 0;
+}
+
+/* tuning / experiment hook: cap the shared-memory ring depth of the GEMM/conv mainloop (2..8) */
+extern "C" int pcdm_set_gemm_max_stages(int n) {
+  if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
+  g_max_stages = n;
   return 0;
 }
 

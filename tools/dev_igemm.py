@@ -86,22 +86,6 @@ if which == "stages":
                 ms = timeit(fn, 10)
                 res.append(dict(op="stages", name=name, cg=cg, max_stages=st, ms=ms, tflops=fl / ms / 1e9)); print(res[-1], flush=True)
     L.pcdm_set_gemm_max_stages(8); set_cg(0)
-if which == "prod2":
-    dt = torch.bfloat16
-    L = _plib.load()
-    x320 = torch.randn(16, 32, 64, 320, device=dev, dtype=dt); w320 = torch.randn(320, 2880, device=dev, dtype=dt)
-    x1280 = torch.randn(16, 8, 16, 1280, device=dev, dtype=dt); w1280 = torch.randn(1280, 11520, device=dev, dtype=dt)
-    a8k = torch.randn(8192, 8192, device=dev, dtype=dt); w8k = torch.randn(8192, 8192, device=dev, dtype=dt)
-    set_cg(1)
-    for name, fn, fl in [("conv320 bn160", lambda: ops.conv3x3(x320, w320, bn=160), 2 * 16 * 2048 * 320 * 2880),
-                         ("conv320 bn64", lambda: ops.conv3x3(x320, w320, bn=64), 2 * 16 * 2048 * 320 * 2880),
-                         ("conv1280@8x16 bn256", lambda: ops.conv3x3(x1280, w1280, bn=256), 2 * 16 * 128 * 1280 * 11520),
-                         ("gemm8k bn256", lambda: ops.gemm(a8k, w8k, bn=256), 2 * 8192 ** 3)]:
-        for sp in (0, 1):
-            L.pcdm_set_gemm_split_producer(sp)
-            ms = timeit(fn, 10)
-            res.append(dict(op="prod2", name=name, split_producer=sp, ms=ms, tflops=fl / ms / 1e9)); print(res[-1], flush=True)
-    L.pcdm_set_gemm_split_producer(0); set_cg(0)
 if which == "splitk":
     ops.ensure_workspace("cuda")
     dt = torch.bfloat16
