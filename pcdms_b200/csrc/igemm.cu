@@ -756,16 +756,3 @@ extern "C" int pcdm_set_gemm_max_stages(int n) {
   g_max_stages = n;
   return 0;
 }
-
-/* tuning / experiment hook: cap the shared-memory ring depth of the GEMM/conv mainloop (2..8) */
-extern "C" int pcdm_set_gemm_max_stages(int n) {
-  if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
-  g_max_stages = n;
-  return 0;
-}
-
-/* experiment hook: 1 = issue activation and weight TMA loads from two different threads (single-CTA tiles only) */
-extern "C" int pcdm_set_gemm_split_producer(int on) {
-  g_split_producer = on ? 1 : 0;
-  return 0;
-}
