@@ -31,6 +31,8 @@ struct AttnParams {
   void* out;
   long long ldo;       // row stride of O in elements
   float scale_log2;    // softmax scale * log2(e)
+  int num_sms;
+  unsigned stagger_ns; // start-up delay of the second resident CTA per SM (0 = off)
 };
 
 constexpr int ATT_THREADS = 320;   // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax (2 per TMEM quadrant)
@@ -88,6 +90,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
+  // Two CTAs share an SM and both alternate between a TMEM-read-bound phase (pull the score tile) and an SFU-bound
+  // phase (exponentials).  Launched together they run in lock step and fight over the same unit; starting the second
+  // CTA of each SM half a KV-block period late makes the two phases interleave instead.
+  if (p.stagger_ns > 0 && blockIdx.x >= (unsigned)p.num_sms && blockIdx.x < 2u * (unsigned)p.num_sms)
+    __nanosleep(p.stagger_ns);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -274,6 +281,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
 using namespace pcdm;
 
+static unsigned g_attn_stagger_ns = 600;   // tuning hook (pcdm_set_attention_stagger_ns)
+
 static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, int heads, int B, int box_rows) {
   // element (b, s, h, d) at ((b*S + s) * ld + h*64 + d)
   const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)heads, (uint64_t)B};
@@ -301,6 +310,8 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.num_sms = num_sms();
+  p.stagger_ns = g_attn_stagger_ns;
   static bool configured = false;
   if (!configured) {
     PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
@@ -313,5 +324,12 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   else
     PCDM_CUDA(launch_kernel(attention_kernel<DT_BF16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
   PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* tuning hook: start-up delay (ns) of the second co-resident attention CTA of each SM; 0 disables the stagger */
+extern "C" int pcdm_set_attention_stagger_ns(int ns) {
+  if (ns < 0 || ns > 100000) return set_error(PCDM_ERR_INVALID, "attention stagger must be in [0, 100000] ns");
+  g_attn_stagger_ns = (unsigned)ns;
   return 0;
 }
