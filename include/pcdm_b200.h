@@ -93,9 +93,6 @@ int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const f
 int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);
 
-int pcdm_set_attention_variant(int v); /* test hook: 0 auto, 1 one-tile kernel, 2 two-tile (Sq >= 256) kernel */
-int pcdm_set_attention_stagger_ns(int ns); /* tuning hook: start delay of the 2nd resident CTA per SM (default 0: measured no effect) */
-
 /* Boundary layout conversion (the reference's tensors are NCHW).  *_dtype: 0 f16, 1 bf16, 2 f32 (destination of
  * nchw_to_nhwc_pad must be 16-bit).  Replaces nothing arithmetic: forward() entry/exit at reference :579-595,:822-825. */
 int pcdm_nchw_to_nhwc_pad(const void* x, int src_dtype, void* y, int dst_dtype, int B, int C, int HW, int Cpad,

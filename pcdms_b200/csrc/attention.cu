@@ -31,8 +31,6 @@ struct AttnParams {
   void* out;
   long long ldo;       // row stride of O in elements
   float scale_log2;    // softmax scale * log2(e)
-  int num_sms;
-  unsigned stagger_ns; // start-up delay of the second resident CTA per SM (0 = off)
 };
 
 constexpr int ATT_THREADS = 320;   // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax (2 per TMEM quadrant)
@@ -90,11 +88,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
-  // Two CTAs share an SM and both alternate between a TMEM-read-bound phase (pull the score tile) and an SFU-bound
-  // phase (exponentials).  Launched together they run in lock step and fight over the same unit; starting the second
-  // CTA of each SM half a KV-block period late makes the two phases interleave instead.
-  if (p.stagger_ns > 0 && blockIdx.x >= (unsigned)p.num_sms && blockIdx.x < 2u * (unsigned)p.num_sms)
-    __nanosleep(p.stagger_ns);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -277,258 +270,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Long-sequence variant (Sq >= 256): ONE CTA per SM owns TWO 128-row query tiles (A, B) of the same (batch, head).
-// The single MMA thread interleaves the two tiles' MMAs (QK_A, QK_B, PV_A, PV_B per KV block, with QK of block j+1
-// issued as soon as the softmax warps have pulled S_j into registers), and two independent softmax warp-groups
-// (4 warps each, one thread per query row, all 128 scores of a row in registers) work half a phase apart: while one
-// group is in its exponential (SFU-bound) phase the other reads TMEM / reduces maxima / stores P, so the SFU — the
-// scarce unit at head_dim 64 — stays busy.  TMEM (512 columns): S_A S_B | P_A P_B | O_A O_B.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 320;
-constexpr int ATT2_KV_STAGES = 3;
-constexpr int ATT2_SMEM_BYTES = ATT_TILE_BYTES * (2 + 2 * ATT2_KV_STAGES) + 1024 + 256;
-constexpr int ATT2_TMEM_S = 0, ATT2_TMEM_P = 256, ATT2_TMEM_O = 384;
-
-template <int DT>
-__global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                           // tile A then tile B
-  uint8_t* sKV = smem + 2 * ATT_TILE_BYTES;     // stage s: K at s*2*TILE, V at s*2*TILE + TILE
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES * (2 + 2 * ATT2_KV_STAGES));
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                   // [3]
-  uint64_t* kv_empty = kv_full + ATT2_KV_STAGES;  // [3]
-  uint64_t* s_full = kv_empty + ATT2_KV_STAGES;   // [2] MMA -> softmax t: S_t(j) landed
-  uint64_t* s_free = s_full + 2;                  // [2] softmax t -> MMA: S_t(j) is in registers (4 warp arrivals)
-  uint64_t* p_full = s_free + 2;                  // [2] softmax t -> MMA: P_t(j) written, O_t corrected
-  uint64_t* pv_done = p_full + 2;                 // [2] MMA -> softmax t: PV_t(j) retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-  pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.q_tiles;          // index of the 256-row tile pair
-  const int bh = blockIdx.x / p.q_tiles;
-  const int h = bh % p.heads, b = bh / p.heads;
-  const int n_kv = (p.Skv + 127) / 128;
-
-  if (warp == 1 && lane == 0) {
-    tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmK);
-    tma_prefetch_desc(&p.tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < ATT2_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4);
-      mbar_init(&p_full[t], 4);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 256, h, b);
-      tma_load_4d(sQ + ATT_TILE_BYTES, &p.tmQ, q_full, 0, qt * 256 + 128, h, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
-        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
-        tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
-        if (++stage == ATT2_KV_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);
-      mbar_wait(q_full, 0);
-      auto issue_qk = [&](int t, int j) {
-        const int stage = j % ATT2_KV_STAGES;
-        const uint32_t q_addr = smem_u32(sQ + t * ATT_TILE_BYTES);
-        const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + ATT2_TMEM_S + t * 128, make_desc_sw128(q_addr + k * 32, 1024, 16),
-                  make_desc_sw128(k_addr + k * 32, 1024, 16), idesc_qk, k != 0);
-        tc_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j) {
-        const int stage = j % ATT2_KV_STAGES;
-        const uint32_t v_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + ATT2_TMEM_O + t * 64, tmem + ATT2_TMEM_P + t * 64 + k * 8,
-                  make_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
-        tc_commit(&pv_done[t]);
-      };
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          // next block's scores as early as possible: the moment a group has S_t(j) in registers
-          mbar_wait(&kv_full[(j + 1) % ATT2_KV_STAGES], (uint32_t)(((j + 1) / ATT2_KV_STAGES) & 1));
-          mbar_wait(&s_free[0], (uint32_t)(j & 1));
-          tc_fence_after();
-          issue_qk(0, j + 1);
-          mbar_wait(&s_free[1], (uint32_t)(j & 1));
-          tc_fence_after();
-          issue_qk(1, j + 1);
-        }
-        mbar_wait(&p_full[0], (uint32_t)(j & 1));
-        tc_fence_after();
-        issue_pv(0, j);
-        mbar_wait(&p_full[1], (uint32_t)(j & 1));
-        tc_fence_after();
-        issue_pv(1, j);
-        tc_commit(&kv_empty[j % ATT2_KV_STAGES]);
-      }
-    }
-  } else {
-    // ===================== softmax groups: warps 2-5 -> tile A, warps 6-9 -> tile B =====================
-    using T = typename TypeOf<DT>::T;
-    const int t = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem + lane_off + ATT2_TMEM_S + t * 128;
-    const uint32_t tP = tmem + lane_off + ATT2_TMEM_P + t * 64;
-    const uint32_t tO = tmem + lane_off + ATT2_TMEM_O + t * 64;
-    float m_ref = -INFINITY;
-    float l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], (uint32_t)(j & 1));
-      tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t (&chunk)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
-        tmem_ld32(tS + c * 32, chunk);
-      }
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);
-      const int kv_left = p.Skv - j * 128;
-      float mx = -INFINITY;
-      if (kv_left >= 128) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
-      }
-      mx *= p.scale_log2;
-      if (j > 0) {
-        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const bool grow = mx > m_ref + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
-          const float m_new = grow ? mx : m_ref;
-          const float alpha = exp2f(m_ref - m_new);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tO + c * 16, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + c * 16, o);
-          }
-          l *= alpha;
-          m_ref = m_new;
-        }
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t pk[8];
-        if (kv_left >= 128) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = exp2f(__uint_as_float(s[c * 16 + 2 * i]) * p.scale_log2 - m_ref);
-            const float bq = exp2f(__uint_as_float(s[c * 16 + 2 * i + 1]) * p.scale_log2 - m_ref);
-            sum += a + bq;
-            pk[i] = pack2<DT>(a, bq);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a = exp2f(__uint_as_float(s[c * 16 + 2 * i]) * p.scale_log2 - m_ref);
-            float bq = exp2f(__uint_as_float(s[c * 16 + 2 * i + 1]) * p.scale_log2 - m_ref);
-            if (c * 16 + 2 * i >= kv_left) a = 0.f;
-            if (c * 16 + 2 * i + 1 >= kv_left) bq = 0.f;
-            sum += a + bq;
-            pk[i] = pack2<DT>(a, bq);
-          }
-        }
-        tmem_st8(tP + c * 8, pk);
-      }
-      l += sum;
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-    mbar_wait(&pv_done[t], (uint32_t)((n_kv - 1) & 1));
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const long long qrow = (long long)qt * 256 + t * 128 + row;
-    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[16];
-      tmem_ld16(tO + c * 16, o);
-      tc_wait_ld();
-      if (qrow < p.Sq) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          uint4 u;
-          u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-          u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-          u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-          u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(op + c * 16 + i * 8) = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
 }  // namespace pcdm
 
 using namespace pcdm;
-
-static unsigned g_attn_stagger_ns = 0;   // tuning hook (pcdm_set_attention_stagger_ns); measured: no effect, off
-static int g_attn_variant = 0;          // 0 = auto (two-tile kernel for Sq >= 256), 1 = one-tile kernel, 2 = two-tile
 
 static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, int heads, int B, int box_rows) {
   // element (b, s, h, d) at ((b*S + s) * ld + h*64 + d)
@@ -557,30 +301,11 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.num_sms = num_sms();
-  p.stagger_ns = g_attn_stagger_ns;
   static bool configured = false;
   if (!configured) {
     PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     configured = true;
-  }
-  if (g_attn_variant == 2 || (g_attn_variant == 0 && Sq >= 256)) {
-    // long sequences: two 128-row query tiles per CTA, ping-ponged softmax groups, one CTA per SM
-    static bool configured2 = false;
-    if (!configured2) {
-      PCDM_CUDA(cudaFuncSetAttribute(attention2_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM_BYTES));
-      PCDM_CUDA(cudaFuncSetAttribute(attention2_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM_BYTES));
-      configured2 = true;
-    }
-    p.q_tiles = (Sq + 255) / 256;
-    const int grid2 = B * heads * p.q_tiles;
-    if (dtype == DT_F16)
-      PCDM_CUDA(launch_kernel(attention2_kernel<DT_F16>, dim3(grid2), dim3(ATT2_THREADS), ATT2_SMEM_BYTES, stream, 1, p));
-    else
-      PCDM_CUDA(launch_kernel(attention2_kernel<DT_BF16>, dim3(grid2), dim3(ATT2_THREADS), ATT2_SMEM_BYTES, stream, 1, p));
-    PCDM_CUDA(cudaGetLastError());
-    return 0;
   }
   const int grid = B * heads * p.q_tiles;
   if (dtype == DT_F16)
@@ -588,19 +313,5 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   else
     PCDM_CUDA(launch_kernel(attention_kernel<DT_BF16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
   PCDM_CUDA(cudaGetLastError());
-  return 0;
-}
-
-/* tuning hook: start-up delay (ns) of the second co-resident attention CTA of each SM; 0 disables the stagger */
-extern "C" int pcdm_set_attention_stagger_ns(int ns) {
-  if (ns < 0 || ns > 100000) return set_error(PCDM_ERR_INVALID, "attention stagger must be in [0, 100000] ns");
-  g_attn_stagger_ns = (unsigned)ns;
-  return 0;
-}
-
-/* tuning / test hook: 0 = automatic, 1 = always the one-tile (2 CTAs/SM) kernel, 2 = always the two-tile kernel */
-extern "C" int pcdm_set_attention_variant(int v) {
-  if (v < 0 || v > 2) return set_error(PCDM_ERR_INVALID, "attention variant must be 0, 1 or 2");
-  g_attn_variant = v;
   return 0;
 }
