@@ -121,7 +121,9 @@ def test_conv3x3_rejects_unsupported_shapes(ops):
 
 @pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("B,H,W,C1,C2", [(2, 32, 64, 320, 0), (2, 16, 32, 1280, 640), (3, 4, 8, 1280, 1280),
-                                          (2, 8, 16, 640, 320), (1, 64, 128, 320, 0), (2, 2, 4, 64, 0)])
+                                          (2, 8, 16, 640, 320), (1, 64, 128, 320, 0), (2, 2, 4, 64, 0),
+                                          (16, 32, 64, 640, 320), (16, 16, 32, 640, 0), (16, 8, 16, 1280, 0),
+                                          (5, 4, 8, 1280, 0), (1, 1, 8, 512, 0), (3, 12, 20, 96, 160)])
 @pytest.mark.parametrize("silu", [True, False])
 def test_groupnorm(ops, dt, B, H, W, C1, C2, silu):
     g = torch.Generator().manual_seed(C1 + C2 + H)
@@ -136,10 +138,23 @@ def test_groupnorm(ops, dt, B, H, W, C1, C2, silu):
     out = ops.groupnorm(x1.permute(0, 2, 3, 1).contiguous().cuda(), gamma.cuda(), beta.cuda(), 1e-5,
                         x2=x2.permute(0, 2, 3, 1).contiguous().cuda() if C2 else None, silu=silu)
     close(out.permute(0, 3, 1, 2), ref, dt)
+    # the single-pass (register-resident, cluster-reduced) path and the statistics + apply path agree to rounding,
+    # and each is bit-reproducible
+    from pcdms_b200 import lib as L
+    args = (x1.permute(0, 2, 3, 1).contiguous().cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    kw = dict(x2=x2.permute(0, 2, 3, 1).contiguous().cuda() if C2 else None, silu=silu)
+    assert torch.equal(out, ops.groupnorm(*args, **kw))
+    L.load().pcdm_set_groupnorm_two_pass(1)
+    try:
+        two = ops.groupnorm(*args, **kw)
+    finally:
+        L.load().pcdm_set_groupnorm_two_pass(0)
+    close(two.permute(0, 3, 1, 2), ref, dt)
+    torch.testing.assert_close(out.float(), two.float(), rtol=1e-2, atol=1e-2)
 
 
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (77, 1280), (33, 64)])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (77, 1280), (33, 64), (32768, 320), (5000, 1280), (9, 2048)])
 def test_layernorm(ops, dt, M, C):
     g = torch.Generator().manual_seed(M + C)
     x = (torch.randn(M, C, generator=g) * 3 + 1).to(dt)
