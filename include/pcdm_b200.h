@@ -77,12 +77,13 @@ int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bi
  * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out
  * (reference :817-819).  y: [B, HW, C].  workspace: pcdm_groupnorm_workspace_bytes() bytes,
  * zero-initialised once by the caller (it holds device counters the kernels return to zero); results are
- * bit-reproducible run to run (fixed reduction order, no floating-point atomics).  Shapes with >= 8 channels per
- * group run as ONE register-resident pass (one read, one write; pieces of an image share statistics through a
- * thread-block cluster); the rest take a statistics kernel + an apply kernel.
- * pcdm_set_groupnorm_two_pass(1) forces the two-kernel path (tests / A-B timing hook). */
+ * bit-reproducible run to run (fixed reduction order, no floating-point atomics).  Small activations (<= 16 MB, >= 8
+ * channels per group) run as ONE register-resident pass (one read, one write; pieces of an image share statistics
+ * through a thread-block cluster); larger ones take a streaming statistics kernel + an apply kernel.
+ * pcdm_set_groupnorm_two_pass(mode) is the tests / A-B timing hook: 0 automatic, 1 always two kernels, 2 single pass
+ * whenever the shape allows, 2 + T single pass with T threads per CTA. */
 long long pcdm_groupnorm_workspace_bytes(int B, int groups);
-int pcdm_set_groupnorm_two_pass(int enabled);
+int pcdm_set_groupnorm_two_pass(int mode);
 int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta, float eps,
                    int B, int HW, int C, int groups, int dtype, int flags, void* workspace, void* stream);
 

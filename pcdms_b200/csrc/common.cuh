@@ -311,6 +311,29 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// Two SiLUs with the fp32 arithmetic on the packed FFMA2 path (one issue slot per pair); ex2 / rcp stay on the SFU.
+__device__ __forceinline__ float2 silu2_exact(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float e0, e1, r0, r1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t.y));
+  const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+  return __fmul2_rn(x, make_float2(r0, r1));
+}
+// x sigmoid(x) = h + h tanh(h), h = x / 2: ONE SFU op per element instead of two.  tanh.approx is good to 2^-11
+// relative, a quarter of a bf16 ulp of the result — used for bf16 outputs only (fp16 keeps the ex2 / rcp form).
+__device__ __forceinline__ float2 silu2_tanh(float2 x) {
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h.y));
+  return __ffma2_rn(h, make_float2(t0, t1), h);
+}
+template <int DT> __device__ __forceinline__ float2 silu2_f(float2 x) {
+  return DT == DT_BF16 ? silu2_tanh(x) : silu2_exact(x);
+}
 // exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below
 // the 16-bit output rounding): one rcp + one ex2 on the SFU and a degree-5 Horner chain, instead of libm erff's
 // two-branch polynomial — the GEGLU epilogue evaluates this 42 M times per UNet step.

@@ -45,19 +45,30 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
   int cs, coff;
   if (c0 < C1) { src = reinterpret_cast<const T*>(x1); cs = C1; coff = c0; }
   else { src = reinterpret_cast<const T*>(x2); cs = C - C1; coff = c0 - C1; }
-  float s[8], q[8];
+  // four pixels in flight per thread; fp32 sums on the packed FFMA2 path (one add + one fma per 32-bit word)
+  float2 s2[4], q2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  for (int p = p_begin + py; p < p_end; p += PY) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * cs + coff));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int k = 0; k < 4; ++k) { s2[k] = make_float2(0.f, 0.f); q2[k] = make_float2(0.f, 0.f); }
+  const T* sp = src + (size_t)b * HW * cs + coff;
+  for (int p = p_begin + py; p < p_end; p += 4 * PY) {
+    uint4 u[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack2<DT>(w[i]);
-      s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-      s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+    for (int j = 0; j < 4; ++j)
+      u[j] = (p + j * PY < p_end) ? __ldg(reinterpret_cast<const uint4*>(sp + (size_t)(p + j * PY) * cs))
+                                  : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack2<DT>(w[k]);
+        s2[k] = __fadd2_rn(s2[k], f);
+        q2[k] = __ffma2_rn(f, f, q2[k]);
+      }
     }
   }
+  const float s[8] = {s2[0].x, s2[0].y, s2[1].x, s2[1].y, s2[2].x, s2[2].y, s2[3].x, s2[3].y};
+  const float q[8] = {q2[0].x, q2[0].y, q2[1].x, q2[1].y, q2[2].x, q2[2].y, q2[3].x, q2[3].y};
   float* ps = sm;                   // [PY][C]
   float* pq = sm + (size_t)PY * C;  // [PY][C]
   *reinterpret_cast<float4*>(ps + (size_t)py * C + c0) = make_float4(s[0], s[1], s[2], s[3]);
@@ -65,20 +76,23 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
   *reinterpret_cast<float4*>(pq + (size_t)py * C + c0) = make_float4(q[0], q[1], q[2], q[3]);
   *reinterpret_cast<float4*>(pq + (size_t)py * C + c0 + 4) = make_float4(q[4], q[5], q[6], q[7]);
   __syncthreads();
-  // per-channel totals over py (fixed order), written back into row 0
-  for (int c = tid; c < C; c += nthreads) {
-    float a = ps[c], bq = pq[c];
-    for (int y = 1; y < PY; ++y) { a += ps[(size_t)y * C + c]; bq += pq[(size_t)y * C + c]; }
-    ps[c] = a;
-    pq[c] = bq;
-  }
-  __syncthreads();
+  // one warp per group: lanes stride over the group's (py, channel) partials in a fixed order, then a shuffle tree —
+  // no thread ever walks a long dependent chain (the tail of this kernel is pure latency)
   const int cpg = C / groups;
   const int chunks = gridDim.x;
-  if (tid < groups) {
-    double a = 0.0, bq = 0.0;
-    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { a += (double)ps[c]; bq += (double)pq[c]; }
-    ws.partial[((size_t)b * chunks + blockIdx.x) * groups + tid] = make_double2(a, bq);
+  const int warp = tid >> 5, lane = tid & 31, full_warps = nthreads >> 5;   // host guarantees nthreads >= 32
+  if (warp < full_warps) {
+    for (int g = warp; g < groups; g += full_warps) {
+      double a = 0.0, bq = 0.0;
+      for (int idx = lane; idx < PY * cpg; idx += 32) {
+        const int yy = idx / cpg, c = g * cpg + idx - yy * cpg;
+        a += (double)ps[(size_t)yy * C + c];
+        bq += (double)pq[(size_t)yy * C + c];
+      }
+      a = warp_sum(a);
+      bq = warp_sum(bq);
+      if (lane == 0) ws.partial[((size_t)b * chunks + blockIdx.x) * groups + g] = make_double2(a, bq);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -87,17 +101,33 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (tid < groups) {
-      double a = 0.0, bq = 0.0;
-      for (int k = 0; k < chunks; ++k) {
-        const double2 v = ws.partial[((size_t)b * chunks + k) * groups + tid];
-        a += v.x; bq += v.y;
+    if (warp < full_warps) {
+      for (int g0 = warp; g0 < groups; g0 += 4 * full_warps) {   // four groups' loads in flight per warp
+        double a[4], bq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + j * full_warps;
+          a[j] = 0.0; bq[j] = 0.0;
+          if (g < groups) {
+            for (int k = lane; k < chunks; k += 32) {
+              const double2 v = ws.partial[((size_t)b * chunks + k) * groups + g];
+              a[j] += v.x; bq[j] += v.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + j * full_warps;
+          const double sa = warp_sum(a[j]), sq = warp_sum(bq[j]);
+          if (g < groups && lane == 0) {
+            const double inv_n = 1.0 / ((double)cpg * (double)HW);
+            const double mean = sa * inv_n;
+            double var = sq * inv_n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            ws.final_stats[(size_t)b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+          }
+        }
       }
-      const double inv_n = 1.0 / ((double)cpg * (double)HW);
-      const double mean = a * inv_n;
-      double var = bq * inv_n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      ws.final_stats[(size_t)b * groups + tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
     if (tid == 0) ws.counters[b] = 0;  // ready for the next launch (and for CUDA-graph replays)
   }
@@ -113,20 +143,25 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 void* __restrict__ y) {
   pdl_launch_dependents();
-  pdl_wait();
   using T = typename TypeOf<DT>::T;
   const int b = blockIdx.y;
   const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
   const int c0 = cv * 8;
   const int cpg = C / groups;
-  float sc[8], sh[8];
+  // gamma / beta are parameters: fetched before the wait on the statistics kernel
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  pdl_wait();
+  float2 sc2[4], sh2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    const float2 st = __ldg(final_stats + (size_t)b * groups + c / cpg);
-    const float s_ = st.y * __ldg(gamma + c);
-    sc[i] = s_;
-    sh[i] = __ldg(beta + c) - st.x * s_;
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + 2 * k;
+    const float2 sa = __ldg(final_stats + (size_t)b * groups + c / cpg);
+    const float2 sb = __ldg(final_stats + (size_t)b * groups + (c + 1) / cpg);
+    sc2[k] = make_float2(sa.y * gm[2 * k], sb.y * gm[2 * k + 1]);
+    sh2[k] = make_float2(bt[2 * k] - sa.x * sc2[k].x, bt[2 * k + 1] - sb.x * sc2[k].y);
   }
   const T* src;
   int cs, coff;
@@ -134,20 +169,27 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
   else { src = reinterpret_cast<const T*>(x2); cs = C - C1; coff = c0 - C1; }
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
-  T* dst = reinterpret_cast<T*>(y);
-  for (int p = p_begin + py; p < p_end; p += PY) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * cs + coff));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  const T* sp = src + (size_t)b * HW * cs + coff;
+  T* dp = reinterpret_cast<T*>(y) + (size_t)b * HW * C + c0;
+  for (int p = p_begin + py; p < p_end; p += 4 * PY) {   // four pixels in flight per thread
+    uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack2<DT>(w[k]);
-      float a = f.x * sc[2 * k] + sh[2 * k];
-      float bb = f.y * sc[2 * k + 1] + sh[2 * k + 1];
-      if (silu) { a = silu_f(a); bb = silu_f(bb); }
-      o[k] = pack2<DT>(a, bb);
+    for (int j = 0; j < 4; ++j)
+      if (p + j * PY < p_end) u[j] = __ldg(reinterpret_cast<const uint4*>(sp + (size_t)(p + j * PY) * cs));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p + j * PY < p_end) {
+        const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 v = __ffma2_rn(unpack2<DT>(w[k]), sc2[k], sh2[k]);
+          if (silu) v = silu2_f<DT>(v);
+          o[k] = pack2<DT>(v.x, v.y);
+        }
+        *reinterpret_cast<uint4*>(dp + (size_t)(p + j * PY) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
-    *reinterpret_cast<uint4*>(dst + ((size_t)b * HW + p) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -202,18 +244,26 @@ gn_fused_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1
   }
   const int glo = crel / cpg;                         // group (within the set) of this thread's first channel
   const int split = min(8, (glo + 1) * cpg - crel);   // elements [0, split) belong to glo, [split, 8) to glo + 1
-  float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+  // These kernels are issue-bound before they are bandwidth-bound (an SM's share of HBM is ~12 elements per clock),
+  // so the fp32 arithmetic runs on the packed FFMA2 path: per 32-bit word, one add and one fma for both channels.
+  float2 s2[4], q2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s2[k] = make_float2(0.f, 0.f); q2[k] = make_float2(0.f, 0.f); }
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack2<DT>(w[k]);
-      const float a0 = (2 * k < split) ? f.x : 0.f, b0 = (2 * k < split) ? 0.f : f.x;
-      const float a1 = (2 * k + 1 < split) ? f.y : 0.f, b1 = (2 * k + 1 < split) ? 0.f : f.y;
-      s_lo += a0; q_lo += a0 * a0; s_hi += b0; q_hi += b0 * b0;
-      s_lo += a1; q_lo += a1 * a1; s_hi += b1; q_hi += b1 * b1;
+      s2[k] = __fadd2_rn(s2[k], f);
+      q2[k] = __ffma2_rn(f, f, q2[k]);
     }
+  }
+  float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // channel position e = 2k, 2k+1 of the vector -> its group (fixed order)
+    if (2 * k < split) { s_lo += s2[k].x; q_lo += q2[k].x; } else { s_hi += s2[k].x; q_hi += q2[k].x; }
+    if (2 * k + 1 < split) { s_lo += s2[k].y; q_lo += q2[k].y; } else { s_hi += s2[k].y; q_hi += q2[k].y; }
   }
   red[tid] = s_lo;
   red[nthreads + tid] = q_lo;
@@ -238,33 +288,42 @@ gn_fused_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1
     }
   }
   if (S > 1) cluster_sync_all(); else __syncthreads();
-  if (tid < gset) {
-    double a = 0.0, q = 0.0;
-    if (S > 1) {
-      const uint32_t local = smem_u32(&cl[tid]);
-      for (int r = 0; r < S; ++r) {
-        const double2 v = ld_dsmem_f64x2(mapa_u32(local, (uint32_t)r));
-        a += v.x; q += v.y;
+  if (tid < 32) {   // warp 0: lane (g, r) fetches rank r's partial of group g, S lanes fold in a fixed xor tree
+    for (int base = 0; base < gset * S; base += 32) {
+      const int item = base + tid, g = item / S, r = item - g * S;
+      double a = 0.0, q = 0.0;
+      if (item < gset * S) {
+        if (S > 1) {
+          const double2 v = ld_dsmem_f64x2(mapa_u32(smem_u32(&cl[g]), (uint32_t)r));
+          a = v.x; q = v.y;
+        } else {
+          a = cl[g].x; q = cl[g].y;
+        }
       }
-    } else {
-      a = cl[tid].x; q = cl[tid].y;
+      for (int o = 1; o < S; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (item < gset * S && r == 0) {
+        const double inv_n = 1.0 / ((double)cpg * (double)HW);
+        const double mean = a * inv_n;
+        double var = q * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      }
     }
-    const double inv_n = 1.0 / ((double)cpg * (double)HW);
-    const double mean = a * inv_n;
-    double var = q * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stat[tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
   __syncthreads();
-  float sc[8], sh[8];
+  float2 sc2[4], sh2[4];
   {
     const float2 st_lo = stat[glo], st_hi = stat[min(glo + 1, gset - 1)];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float2 st = (e < split) ? st_lo : st_hi;
-      const float s_ = st.y * gam[crel + e];
-      sc[e] = s_;
-      sh[e] = bet[crel + e] - st.x * s_;
+    for (int k = 0; k < 4; ++k) {
+      const float2 sa = (2 * k < split) ? st_lo : st_hi, sb = (2 * k + 1 < split) ? st_lo : st_hi;
+      const float2 g = *reinterpret_cast<const float2*>(gam + crel + 2 * k);
+      const float2 bt = *reinterpret_cast<const float2*>(bet + crel + 2 * k);
+      sc2[k] = make_float2(sa.y * g.x, sb.y * g.y);
+      sh2[k] = make_float2(bt.x - sa.x * sc2[k].x, bt.y - sb.x * sc2[k].y);
     }
   }
   T* dp = reinterpret_cast<T*>(y) + ((size_t)b * HW + p_begin + py) * C + c0;
@@ -275,11 +334,9 @@ gn_fused_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack2<DT>(w[k]);
-        float a = f.x * sc[2 * k] + sh[2 * k];
-        float bb = f.y * sc[2 * k + 1] + sh[2 * k + 1];
-        if (silu) { a = silu_f(a); bb = silu_f(bb); }
-        o[k] = pack2<DT>(a, bb);
+        float2 v = __ffma2_rn(unpack2<DT>(w[k]), sc2[k], sh2[k]);
+        if (silu) v = silu2_f<DT>(v);
+        o[k] = pack2<DT>(v.x, v.y);
       }
       *reinterpret_cast<uint4*>(dp + (size_t)i * PY * C) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -288,16 +345,27 @@ gn_fused_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, rows strided over a grid of ~4 CTAs per SM.  gamma/beta are staged in shared memory
-// before the programmatic-dependency wait (they are parameters), the row lives in registers (two-pass variance), and
-// the NEXT row of the warp is already in flight while the current one is reduced and stored.  C <= 2048, C % 8 == 0.
+// LayerNorm.  LPR lanes share a row (32 / LPR rows per warp) and each lane keeps VPL 16-byte vectors of it, chosen so
+// that LPR * VPL covers C / 8 with the least idle lanes (C = 320, 640, 1280 -> 8, 16, 32 lanes x 5 vectors exactly).
+// Row groups are strided over a grid of ~4 CTAs per SM; gamma/beta are staged in shared memory before the
+// programmatic-dependency wait (they are parameters); the NEXT row group of the warp is already in flight while the
+// current one is reduced (two-pass variance, xor-shuffles within the LPR lanes), normalised and stored.  The fp32
+// arithmetic is on the packed FFMA2 path: the kernel is issue-bound before it is bandwidth-bound.
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT, int VPL>  // VPL = 16-byte vectors per lane
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int DT, int VPL, int LPR>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y, long long ldy,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int M, int C) {
   pdl_launch_dependents();
   using T = typename TypeOf<DT>::T;
+  constexpr int RPW = 32 / LPR;                  // rows per warp
   extern __shared__ __align__(16) float lsm[];   // gamma[C] | beta[C]
   for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {
     reinterpret_cast<float4*>(lsm)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
@@ -306,71 +374,70 @@ layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y
   pdl_wait();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
   const int wpc = blockDim.x >> 5;
-  const long long nwarps = (long long)gridDim.x * wpc;
+  const long long stride = (long long)gridDim.x * wpc * RPW;
   const int nvec = C / 8;
   const T* xb = reinterpret_cast<const T*>(x);
   T* yb = reinterpret_cast<T*>(y);
-  long long row = (long long)blockIdx.x * wpc + warp;
+  long long row = ((long long)blockIdx.x * wpc + warp) * RPW + lane / LPR;
   uint4 cur[VPL], nxt[VPL];
-  if (row < M) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    cur[i] = (row < M && sub + i * LPR < nvec) ? __ldg(reinterpret_cast<const uint4*>(xb + row * ldx + (sub + i * LPR) * 8))
+                                               : make_uint4(0u, 0u, 0u, 0u);
+  const float inv_c = 1.0f / (float)C;
+  // every lane of the warp runs the same number of iterations (the shuffles need all 32): bound by the warp's first row
+  for (long long base = row - lane / LPR; base < M; base += stride, row += stride) {
+    const long long rn = row + stride;
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
-      cur[i] = (lane + i * 32 < nvec) ? __ldg(reinterpret_cast<const uint4*>(xb + row * ldx + (lane + i * 32) * 8))
-                                      : make_uint4(0u, 0u, 0u, 0u);
-  }
-  const float inv_c = 1.0f / (float)C;
-  for (; row < M; row += nwarps) {
-    const long long rn = row + nwarps;
-    if (rn < M) {
+      nxt[i] = (rn < M && sub + i * LPR < nvec) ? __ldg(reinterpret_cast<const uint4*>(xb + rn * ldx + (sub + i * LPR) * 8))
+                                                : make_uint4(0u, 0u, 0u, 0u);
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
-        nxt[i] = (lane + i * 32 < nvec) ? __ldg(reinterpret_cast<const uint4*>(xb + rn * ldx + (lane + i * 32) * 8))
-                                        : make_uint4(0u, 0u, 0u, 0u);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
+    for (int i = 0; i < VPL; ++i) {   // out-of-range vectors are zeros
       const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack2<DT>(w[k]);
-        sum += f.x + f.y;
-      }
+      for (int k = 0; k < 4; ++k) sum2 = __fadd2_rn(sum2, unpack2<DT>(w[k]));
     }
-    const float mean = warp_sum(sum) * inv_c;
-    float sq = 0.f;
+    const float mean = row_sum<LPR>(sum2.x + sum2.y) * inv_c;
+    const float2 nmean2 = make_float2(-mean, -mean);
+    float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + i * 32 < nvec) {
+      if (sub + i * LPR < nvec) {
         const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack2<DT>(w[k]);
-          const float d0 = f.x - mean, d1 = f.y - mean;
-          sq += d0 * d0 + d1 * d1;
+          const float2 d = __fadd2_rn(unpack2<DT>(w[k]), nmean2);
+          sq2 = __ffma2_rn(d, d, sq2);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+    const float rstd = rsqrtf(row_sum<LPR>(sq2.x + sq2.y) * inv_c + eps);
+    const float2 rstd2 = make_float2(rstd, rstd), shift2 = make_float2(-mean * rstd, -mean * rstd);
+    if (row < M) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        const float4 g0 = *reinterpret_cast<const float4*>(lsm + vi * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(lsm + vi * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(lsm + C + vi * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(lsm + C + vi * 8 + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
-        uint32_t o[4];
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = sub + i * LPR;
+        if (vi < nvec) {
+          const float4 g0 = *reinterpret_cast<const float4*>(lsm + vi * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(lsm + vi * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(lsm + C + vi * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(lsm + C + vi * 8 + 4);
+          const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+          const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+          const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+          uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack2<DT>(w[k]);
-          o[k] = pack2<DT>((f.x - mean) * rstd * g[2 * k] + bb[2 * k], (f.y - mean) * rstd * g[2 * k + 1] + bb[2 * k + 1]);
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = __ffma2_rn(unpack2<DT>(w[k]), rstd2, shift2);   // (x - mean) * rstd
+            const float2 v = __ffma2_rn(t, g[k], bb[k]);
+            o[k] = pack2<DT>(v.x, v.y);
+          }
+          *reinterpret_cast<uint4*>(yb + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<uint4*>(yb + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
 #pragma unroll
@@ -386,13 +453,15 @@ static void gn_grid(int B, int HW, int C, int* PY_, int* pix_per_cta_, int* chun
   const int cvs = C / 8;
   int PY = 512 / cvs;
   if (PY < 1) PY = 1;
-  // >= ~4 CTAs per SM across the batch (these kernels are latency/bandwidth bound: parallelism first), but keep at
-  // least one pixel per thread row
-  const int chunks_wanted = (4 * num_sms() + B - 1) / B;
+  // ~2 CTAs of ~480 threads per SM across the batch, four 16-byte loads in flight per thread (~60 KB per SM); keep
+  // at least one pixel per thread row
+  int chunks_wanted = (2 * num_sms()) / B;   // rounded DOWN: one CTA over the resident capacity is a whole second wave
+  if (chunks_wanted < 1) chunks_wanted = 1;
   int pix_per_cta = (HW + chunks_wanted - 1) / chunks_wanted;
   if (pix_per_cta < PY) pix_per_cta = PY;
   if (pix_per_cta > HW) pix_per_cta = HW;
   if (PY > pix_per_cta) PY = pix_per_cta;
+  while (cvs * PY < 32) ++PY;   // the group reductions are warp-wide: at least one full warp
   *PY_ = PY;
   *pix_per_cta_ = pix_per_cta;
   *chunks_ = (HW + pix_per_cta - 1) / pix_per_cta;
@@ -401,36 +470,43 @@ static void gn_grid(int B, int HW, int C, int* PY_, int* pix_per_cta_, int* chun
 struct GnFusedCfg { int gset, nv, PY, S, pix_per_cta, K; };
 
 // Shape of the single-pass launch, or false when the problem needs the two-kernel path (cpg < 8, pieces too large).
+// Measured (tools/dev_norm_perf.py): the single pass wins while the whole activation is a wave or two of CTAs
+// (<= 16 MB: one launch, one read); above that its load / reduce+cluster-sync / store phases run in lockstep across
+// the chip and the two streaming kernels (statistics, then apply) are faster.
+static int g_gn_max_threads = 0;   // pcdm_set_groupnorm_two_pass(2 + T): experiment hook, force T threads per CTA
 static bool gn_fused_config(int B, int HW, int C, int C1, int groups, GnFusedCfg* c) {
   const int cpg = C / groups;
   if (cpg < 8 || (C1 % 8)) return false;
   int gmin = 1;
   while (gmin <= 8 && (gmin * cpg) % 8) gmin *= 2;
   if (gmin > 8 || groups % gmin) return false;
-  int gset = gmin;
-  for (int g = 8; g > gmin; g /= 2) {   // wider sets = longer contiguous runs per pixel, while >= 128 pieces remain
-    if (g % gmin || groups % g || g * cpg / 8 > 64) continue;
-    if ((long long)B * (groups / g) >= 128) { gset = g; break; }
-  }
-  const int nv = gset * cpg / 8;
-  if (nv > 128) return false;
-  int PYmax = 1024 / nv;
-  int S = 1;
-  for (;;) {
-    const int ppc = (HW + S - 1) / S;
-    int PY = ppc < PYmax ? ppc : PYmax;
-    const int PYmin = (32 + nv - 1) / nv;
-    if (PY < PYmin) PY = PYmin;
-    const int K = (ppc + PY - 1) / PY;
-    const bool more_parallel = (long long)B * (groups / gset) * S < 128 && ppc >= 2 * PY;
-    if (K > 6 || more_parallel) {
-      if (S >= 8) { if (K > 6) return false; }
-      else { S *= 2; continue; }
+  static const int kThreads[3] = {1024, 512, 256};
+  for (int ti = 0; ti < 3; ++ti) {
+    const int T = kThreads[ti];
+    if (g_gn_max_threads && T != g_gn_max_threads) continue;
+    for (int gset = 8; gset >= gmin; gset /= 2) {   // wider sets = longer contiguous runs per pixel
+      if (gset % gmin || groups % gset) continue;
+      const int nv = gset * cpg / 8;
+      if (nv > 64 || (gset > gmin && (long long)B * (groups / gset) < 128)) continue;
+      const int PYmax = T / nv;
+      if (PYmax < 1) continue;
+      for (int S = 1; S <= 8; S *= 2) {
+        const int ppc = (HW + S - 1) / S;
+        int PY = ppc < PYmax ? ppc : PYmax;
+        const int PYmin = (32 + nv - 1) / nv;
+        if (PY < PYmin) PY = PYmin;
+        if (PY * nv > 1024) break;
+        const int K = (ppc + PY - 1) / PY;
+        if (K > 6) continue;
+        // spread a small batch over more CTAs while every thread keeps >= 2 vectors
+        if ((long long)B * (groups / gset) * S < 128 && S < 8 && K >= 4) continue;
+        c->gset = gset; c->nv = nv; c->PY = PY; c->S = S; c->pix_per_cta = ppc;
+        c->K = K <= 4 ? K : 6;
+        return true;
+      }
     }
-    c->gset = gset; c->nv = nv; c->PY = PY; c->S = S; c->pix_per_cta = ppc;
-    c->K = K <= 4 ? K : 6;
-    return true;
   }
+  return false;
 }
 
 template <int DT>
@@ -453,9 +529,13 @@ static cudaError_t launch_gn_fused(const GnFusedCfg& c, cudaStream_t stream, con
 #undef GN_FUSED
 }
 
+static long long g_gn_fused_max_bytes = 16LL << 20;
 static int g_gn_two_pass = 0;   // pcdm_set_groupnorm_two_pass(): force the two-kernel path (tests / A-B timing)
-extern "C" int pcdm_set_groupnorm_two_pass(int enabled) {
-  g_gn_two_pass = enabled ? 1 : 0;
+// 0: automatic; 1: always statistics + apply kernels; 2: single pass whenever the shape allows; 2 + T: single pass
+// with T threads per CTA (256 / 512 / 1024)
+extern "C" int pcdm_set_groupnorm_two_pass(int mode) {
+  g_gn_two_pass = mode;
+  g_gn_max_threads = mode > 2 ? mode - 2 : 0;
   return 0;
 }
 
@@ -480,7 +560,9 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
   if (groups > 256) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm: groups > 256");
   const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   GnFusedCfg fc;
-  if (!g_gn_two_pass && gn_fused_config(B, HW, C, C1, groups, &fc)) {
+  const long long in_bytes = 2LL * B * HW * C;
+  const bool want_fused = g_gn_two_pass >= 2 || (g_gn_two_pass == 0 && in_bytes <= g_gn_fused_max_bytes);
+  if (want_fused && gn_fused_config(B, HW, C, C1, groups, &fc)) {
     PCDM_CUDA(dtype == DT_F16
                   ? launch_gn_fused<DT_F16>(fc, stream, x1, x2, C1, C, HW, groups, B, eps, gamma, beta, silu, y)
                   : launch_gn_fused<DT_BF16>(fc, stream, x1, x2, C1, C, HW, groups, B, eps, gamma, beta, silu, y));
@@ -522,28 +604,38 @@ extern "C" int pcdm_layernorm(const void* x, long long ldx, void* y, long long l
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "layernorm: bad dtype");
   if (M <= 0 || C <= 0) return set_error(PCDM_ERR_INVALID, "layernorm: empty problem");
   if (C % 8 || C > 2048 || (ldx % 8) || (ldy % 8)) return set_error(PCDM_ERR_UNSUPPORTED, "layernorm: C % 8 == 0, C <= 2048, strides % 8 == 0");
-  const int vpl = (C / 8 + 31) / 32;
-  const int rows_per_cta = 8;   // warps per CTA
+  // lanes per row / vectors per lane with the fewest idle lanes (ties -> more lanes per row)
+  const int nvec = C / 8;
+  int lpr = 32, vpl = (nvec + 31) / 32;
+  for (int l = 16; l >= 8; l /= 2) {
+    const int v = (nvec + l - 1) / l;
+    if (v <= 6 && v * l < vpl * lpr) { lpr = l; vpl = v; }
+  }
+  const int warps_per_cta = 8, rows_per_cta = warps_per_cta * (32 / lpr);
   int grid = (M + rows_per_cta - 1) / rows_per_cta;
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
   const size_t ln_smem = (size_t)2 * C * sizeof(float);
-#define LN_LAUNCH(V)                                                                                              \
-  do {                                                                                                            \
-    cudaError_t _le = (dtype == DT_F16)                                                                           \
-        ? launch_kernel(layernorm_kernel<DT_F16, V>, dim3(grid), dim3(256), ln_smem, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C)  \
-        : launch_kernel(layernorm_kernel<DT_BF16, V>, dim3(grid), dim3(256), ln_smem, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C); \
-    if (_le != cudaSuccess) return set_error(PCDM_ERR_CUDA, "layernorm launch failed: %s", cudaGetErrorString(_le)); \
-  } while (0)
-  switch (vpl) {
-    case 1: LN_LAUNCH(1); break;
-    case 2: LN_LAUNCH(2); break;
-    case 3: LN_LAUNCH(3); break;
-    case 4: LN_LAUNCH(4); break;
-    case 5: LN_LAUNCH(5); break;
-    case 6: LN_LAUNCH(6); break;
-    case 7: LN_LAUNCH(7); break;
-    default: LN_LAUNCH(8); break;
+  cudaError_t le = cudaErrorInvalidValue;
+#define LN_LAUNCH(V, LP)                                                                                          \
+  le = (dtype == DT_F16)                                                                                          \
+      ? launch_kernel(layernorm_kernel<DT_F16, V, LP>, dim3(grid), dim3(256), ln_smem, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C)  \
+      : launch_kernel(layernorm_kernel<DT_BF16, V, LP>, dim3(grid), dim3(256), ln_smem, stream, 1, x, ldx, y, ldy, gamma, beta, eps, M, C)
+#define LN_CASES(LP)                                                                                              \
+  switch (vpl) {                                                                                                  \
+    case 1: LN_LAUNCH(1, LP); break;                                                                              \
+    case 2: LN_LAUNCH(2, LP); break;                                                                              \
+    case 3: LN_LAUNCH(3, LP); break;                                                                              \
+    case 4: LN_LAUNCH(4, LP); break;                                                                              \
+    case 5: LN_LAUNCH(5, LP); break;                                                                              \
+    default: LN_LAUNCH(6, LP); break;                                                                             \
   }
+  if (lpr == 8) { LN_CASES(8) }
+  else if (lpr == 16) { LN_CASES(16) }
+  else if (vpl <= 6) { LN_CASES(32) }
+  else if (vpl == 7) { LN_LAUNCH(7, 32); }
+  else { LN_LAUNCH(8, 32); }
+  if (le != cudaSuccess) return set_error(PCDM_ERR_CUDA, "layernorm launch failed: %s", cudaGetErrorString(le));
+#undef LN_CASES
 #undef LN_LAUNCH
   PCDM_CUDA(cudaGetLastError());
   return 0;

@@ -144,13 +144,17 @@ def test_groupnorm(ops, dt, B, H, W, C1, C2, silu):
     args = (x1.permute(0, 2, 3, 1).contiguous().cuda(), gamma.cuda(), beta.cuda(), 1e-5)
     kw = dict(x2=x2.permute(0, 2, 3, 1).contiguous().cuda() if C2 else None, silu=silu)
     assert torch.equal(out, ops.groupnorm(*args, **kw))
-    L.load().pcdm_set_groupnorm_two_pass(1)
     try:
+        L.load().pcdm_set_groupnorm_two_pass(1)
         two = ops.groupnorm(*args, **kw)
+        L.load().pcdm_set_groupnorm_two_pass(2)
+        one = ops.groupnorm(*args, **kw)
+        assert torch.equal(one, ops.groupnorm(*args, **kw))
     finally:
         L.load().pcdm_set_groupnorm_two_pass(0)
     close(two.permute(0, 3, 1, 2), ref, dt)
-    torch.testing.assert_close(out.float(), two.float(), rtol=1e-2, atol=1e-2)
+    close(one.permute(0, 3, 1, 2), ref, dt)
+    torch.testing.assert_close(one.float(), two.float(), rtol=1e-2, atol=1e-2)
 
 
 @pytest.mark.parametrize("dt", DTS)
