@@ -89,53 +89,66 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
 
+  // The TMA and MMA warps stay converged and elect one lane at each issue: operands then sit in uniform registers
+  // (a `lane == 0` branch costs ~80 cycles of vector->uniform moves per tcgen05.mma, measured in igemm.cu).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 128, h, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int stage = j & 1;
-        mbar_wait(&kv_empty[stage], (uint32_t)(((j >> 1) & 1) ^ 1));
-        uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int stage = j & 1;
+      mbar_wait(&kv_empty[stage], (uint32_t)(((j >> 1) & 1) ^ 1));
+      uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
         tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
         tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
-      constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      mbar_wait(q_full, 0);
-      auto issue_qk = [&](int j) {
-        const int stage = j & 1;
-        mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
-        if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax holds S_{j-1} in registers
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES);
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
+    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
+    // shared-memory descriptors: constant high word (SBO 1024 B, version 1, 128-byte swizzle), low word = addr >> 4
+    // | LBO >> 4 << 16, advanced by plain adds
+    constexpr uint64_t kDescHi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
+    const uint32_t kv_lo0 = (smem_u32(sKV) >> 4) & 0x3FFFu;
+    mbar_wait(q_full, 0);
+    auto issue_qk = [&](int j) {
+      const int stage = j & 1;
+      mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
+      if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax holds S_{j-1} in registers
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + ATT_TMEM_S, make_desc_sw128(q_addr + k * 32, 1024, 16),
-                  make_desc_sw128(k_addr + k * 32, 1024, 16), idesc_qk, k != 0);
+          umma_ss(tmem + ATT_TMEM_S, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
         tc_commit(s_full);
-      };
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(p_full, (uint32_t)(j & 1));
-        tc_fence_after();
-        const int stage = j & 1;
-        const uint32_t v_addr = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      mbar_wait(p_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      const int stage = j & 1;
+      if (elect_one()) {
+        const uint32_t v_lo = (kv_lo0 + (uint32_t)((stage * 2 + 1) * (ATT_TILE_BYTES >> 4))) | ((1024u >> 4) << 16);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
-          umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, make_desc_sw128(v_addr + k * 2048, 1024, 1024),
-                  idesc_pv, (j | k) != 0);
+          umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, kDescHi | (v_lo + (2048u >> 4) * k), idesc_pv,
+                  (j | k) != 0);
         tc_commit(&kv_empty[stage]);
         tc_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ===================== softmax / correction / epilogue =====================

@@ -128,6 +128,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// One lane of a CONVERGED warp.  The TMA / MMA issuing warps stay warp-uniform and elect at the instruction: the
+// operands of UTMALDG / UTCHMMA then live in uniform registers; a `lane == 0` branch instead makes the compiler move
+// every operand vector->uniform (R2UR) inside a per-thread serialisation loop — ~80 cycles per MMA issue, measured.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- cluster / CTA-pair (cta_group::2) helpers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

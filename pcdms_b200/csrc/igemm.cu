@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp, converged; one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     const int hw = p.H * p.W;
@@ -139,49 +139,55 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        if (CG == 1) {
-          mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
-          if (p.mode == 0) {
-            if (kb < p.kb_split) tma_load_2d(sa, &p.tmA[0], &full[stage], kb * 64, m0);
-            else tma_load_2d(sa, &p.tmA[1], &full[stage], (kb - p.kb_split) * 64, m0);
-          } else {
-            const int r = tap / 3, s = tap - r * 3;
-            if (p.mode == 1) {
-              tma_load_4d(sa, &p.tmA[0], &full[stage], cb * 64, s - 1, y0 + r - 1, b0);
-            } else {
-              // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
-              const int py = (r != 1), px = (s != 1);
-              tma_load_4d(sa, &p.tmA[py * 2 + px], &full[stage], cb * 64, (s == 0) ? -1 : 0,
-                          y0 + ((r == 0) ? -1 : 0), b0);
-            }
-            if (++cb == p.cblocks) { cb = 0; ++tap; }
-          }
-          tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+        // box coordinates, computed by the whole warp (uniform registers)
+        const CUtensorMap* tma = &p.tmA[0];
+        int c0, c1, c2 = 0, c3 = 0;
+        if (p.mode == 0) {
+          if (kb < p.kb_split) { c0 = kb * 64; }
+          else { tma = &p.tmA[1]; c0 = (kb - p.kb_split) * 64; }
+          c1 = m0;
         } else {
-          // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
-          if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
-          const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
-          if (p.mode == 0) {
-            if (kb < p.kb_split) tma_load_2d_cg2(sa, &p.tmA[0], fbar, kb * 64, m0);
-            else tma_load_2d_cg2(sa, &p.tmA[1], fbar, (kb - p.kb_split) * 64, m0);
+          const int r = tap / 3, s = tap - r * 3;
+          c0 = cb * 64;
+          c3 = b0;
+          if (p.mode == 1) {
+            c1 = s - 1;
+            c2 = y0 + r - 1;
           } else {
-            const int r = tap / 3, s = tap - r * 3;
-            if (p.mode == 1) {
-              tma_load_4d_cg2(sa, &p.tmA[0], fbar, cb * 64, s - 1, y0 + r - 1, b0);
-            } else {
-              const int py = (r != 1), px = (s != 1);
-              tma_load_4d_cg2(sa, &p.tmA[py * 2 + px], fbar, cb * 64, (s == 0) ? -1 : 0, y0 + ((r == 0) ? -1 : 0), b0);
-            }
-            if (++cb == p.cblocks) { cb = 0; ++tap; }
+            // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
+            const int py = (r != 1), px = (s != 1);
+            tma = &p.tmA[py * 2 + px];
+            c1 = (s == 0) ? -1 : 0;
+            c2 = y0 + ((r == 0) ? -1 : 0);
           }
-          tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
+          if (++cb == p.cblocks) { cb = 0; ++tap; }
         }
+        if (elect_one()) {
+          if (CG == 1) {
+            mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+            if (p.mode == 0) tma_load_2d(sa, tma, &full[stage], c0, c1);
+            else tma_load_4d(sa, tma, &full[stage], c0, c1, c2, c3);
+            tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+          } else {
+            // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+            if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
+            const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
+            if (p.mode == 0) tma_load_2d_cg2(sa, tma, fbar, c0, c1);
+            else tma_load_4d_cg2(sa, tma, fbar, c0, c1, c2, c3);
+            tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
+          }
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ===================== MMA issuer (leader CTA of a pair) =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA of a pair; whole warp, one elected lane issues) =====================
     constexpr uint32_t idesc = make_idesc(DT, 128 * CG, BN, 0, 0);
+    // SW128 K-major descriptor: high word constant (SBO 1024 B, version 1, 128-byte swizzle); low word = addr >> 4 |
+    // LBO(16 B) << 16, advanced by plain adds (shared addresses < 256 KB never carry out of the 14-bit field)
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t desc_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -195,21 +201,27 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        if (elect_one()) {
+          const uint32_t a_lo = desc_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_desc_sw128(a_addr + k * 32, 1024, 16);
-          const uint64_t db = make_desc_sw128(b_addr + k * 32, 1024, 16);
-          if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-          else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = ((uint64_t)kDescHi << 32) | (a_lo + 2u * k);   // +32 B per k16 inside the swizzle atom
+            const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + 2u * k);
+            if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          // commits come from the SAME lane as the MMAs they track
+          if (CG == 2) tc_commit_cg2(&empty[stage]);   // frees the stage in both CTAs
+          else tc_commit(&empty[stage]);
+          if (kb == nkb - 1) {
+            if (CG == 2) tc_commit_cg2(&tfull[acc]);    // both CTAs' epilogues
+            else tc_commit(&tfull[acc]);
+          }
         }
-        if (CG == 2) tc_commit_cg2(&empty[stage]);   // frees the stage in both CTAs
-        else tc_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (CG == 2) tc_commit_cg2(&tfull[acc]);        // both CTAs' epilogues
-      else tc_commit(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
