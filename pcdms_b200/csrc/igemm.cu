@@ -8,7 +8,8 @@
 //   over the same NHWC buffer (element strides doubled), so they use the identical box loads.
 // * A 128 x BN fp32 accumulator lives in TMEM (double-buffered: the epilogue of tile i overlaps the MMAs of tile
 //   i+1); one elected thread issues tcgen05.mma (M=128, N=BN, K=16) from 128B-swizzled shared-memory operands.
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+// * Warp roles: warp 0 = TMA producer (activations), warp 3 = TMA producer (weights), warp 1 = MMA issuer, warp 2 = TMEM
+//   allocator, warps 4-11 = epilogue.  Producer and MMA warps stay converged and elect one lane per issue.
 //   (tcgen05.ld -> fp32 math -> 16-bit stores).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
 //
 // Replaces, on the reference path, torch.nn.Conv2d / torch.nn.Linear as called from diffusers' ResnetBlock2D,
@@ -19,7 +20,7 @@
 
 namespace pcdm {
 
-constexpr int IG_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
+constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
 constexpr int IG_EPI_WARPS = 8;
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
 constexpr int IG_MAX_STAGES = 8;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     if (!p.out_f32) tma_prefetch_desc(&p.tmOut);
     if (p.has_res) tma_prefetch_desc(&p.tmRes);
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 2);   // the activation producer's and the weight producer's expect_tx arrivals
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -118,10 +119,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp, converged; one elected lane issues) =====================
+    // ===================== TMA producer, activations (whole warp, converged; one elected lane issues) ==========
+    // (the weight tiles come from warp 3: two short issue chains in parallel instead of one long one per k-block)
     int stage = 0;
     uint32_t phase = 0;
     const int hw = p.H * p.W;
+    const int nstages = p.stages;
+    const uint32_t a_bytes = p.a_bytes;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int m_blk = mn / p.n_tiles, n_blk = mn % p.n_tiles;
@@ -133,22 +137,23 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       }
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-      int tap = 0, cb = kb_begin;
-      if (p.mode != 0) { tap = kb_begin / p.cblocks; cb = kb_begin - tap * p.cblocks; }
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
-        // box coordinates, computed by the whole warp (uniform registers)
+      // The K range is walked segment by segment — one filter tap of a conv, or one of the (up to two) concatenated
+      // A matrices of a GEMM — so that inside a segment only the channel coordinate moves and the per-k-block loop is
+      // a barrier wait, one elected lane's expect_tx + two TMA issues, and a few adds: this thread's latency per
+      // k-block has to stay below the MMA time of the k-block.
+      int kb = kb_begin;
+      while (kb < kb_end) {
         const CUtensorMap* tma = &p.tmA[0];
-        int c0, c1, c2 = 0, c3 = 0;
+        int seg_end, c0, c1, c2 = 0, c3 = 0;
         if (p.mode == 0) {
-          if (kb < p.kb_split) { c0 = kb * 64; }
-          else { tma = &p.tmA[1]; c0 = (kb - p.kb_split) * 64; }
+          if (kb < p.kb_split) { c0 = kb * 64; seg_end = min(kb_end, p.kb_split); }
+          else { tma = &p.tmA[1]; c0 = (kb - p.kb_split) * 64; seg_end = kb_end; }
           c1 = m0;
         } else {
+          const int tap = kb / p.cblocks;
           const int r = tap / 3, s = tap - r * 3;
-          c0 = cb * 64;
+          c0 = (kb - tap * p.cblocks) * 64;
+          seg_end = min(kb_end, (tap + 1) * p.cblocks);
           c3 = b0;
           if (p.mode == 1) {
             c1 = s - 1;
@@ -160,25 +165,55 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             c1 = (s == 0) ? -1 : 0;
             c2 = y0 + ((r == 0) ? -1 : 0);
           }
-          if (++cb == p.cblocks) { cb = 0; ++tap; }
         }
+        const bool is_gemm = p.mode == 0;
+        for (; kb < seg_end; ++kb, c0 += 64) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (CG == 1) {
+              mbar_expect_tx(&full[stage], a_bytes);
+              if (is_gemm) tma_load_2d(sa, tma, &full[stage], c0, c1);
+              else tma_load_4d(sa, tma, &full[stage], c0, c1, c2, c3);
+            } else {
+              // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+              if (rank == 0) mbar_expect_tx(&full[stage], 2u * a_bytes);
+              const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
+              if (is_gemm) tma_load_2d_cg2(sa, tma, fbar, c0, c1);
+              else tma_load_4d_cg2(sa, tma, fbar, c0, c1, c2, c3);
+            }
+          }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer, weights =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nstages = p.stages;
+    const uint32_t b_bytes = p.b_bytes;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int n_blk = mn % p.n_tiles;
+      const int n0 = n_blk * BN + ((CG == 2) ? (int)rank * (BN / 2) : 0);
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
+          uint8_t* sb = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
           if (CG == 1) {
-            mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
-            if (p.mode == 0) tma_load_2d(sa, tma, &full[stage], c0, c1);
-            else tma_load_4d(sa, tma, &full[stage], c0, c1, c2, c3);
-            tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n_blk * BN);
+            mbar_expect_tx(&full[stage], b_bytes);
+            tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n0);
           } else {
-            // pair: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
-            if (rank == 0) mbar_expect_tx(&full[stage], 2u * (p.a_bytes + p.b_bytes));
-            const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
-            if (p.mode == 0) tma_load_2d_cg2(sa, tma, fbar, c0, c1);
-            else tma_load_4d_cg2(sa, tma, fbar, c0, c1, c2, c3);
-            tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n_blk * BN + (int)rank * (BN / 2));
+            if (rank == 0) mbar_expect_tx(&full[stage], 2u * b_bytes);
+            tma_load_2d_cg2(sb, &p.tmB, mapa_u32(smem_u32(&full[stage]), 0), kb * 64, n0);
           }
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && rank == 0) {
