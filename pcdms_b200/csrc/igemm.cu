@@ -561,25 +561,38 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-static int pick_bn(int m_tiles, int N, int geglu) {
-  // Measured on B200 (tools/autotune.py): the time of one output tile is nearly independent of its width for
-  // BN in 64..256 (the mainloop is paced per k-block, not per MMA column), so the best BN is the one that needs the
-  // fewest waves of tiles; ties go to the wider tile (fewer A re-reads).  A narrow tile only wins when it avoids
-  // padding waste that costs a whole extra wave.
-  const int cand[4] = {256, 160, 128, 64};
-  int best = 128;
-  long long best_waves = 1LL << 60, best_pad = 1LL << 60;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cand[i];
-    if (geglu && (bn % 64)) continue;
-    if (bn == 160 && (N % 160)) continue;
-    const int n_tiles = (N + bn - 1) / bn;
-    const long long tiles = (long long)m_tiles * n_tiles;
-    const long long waves = (tiles + num_sms() - 1) / num_sms();
-    const long long pad = (long long)n_tiles * bn - N;   // wasted MMA columns
-    if (waves < best_waves || (waves == best_waves && pad < best_pad)) { best_waves = waves; best_pad = pad; best = bn; }
+// Tile-shape selection from a cost model fitted to B200 measurements (tools/autotune.py, profiles/r1_autotune2.json):
+// cycles per 64-deep k-block of one CTA in steady state.  Once the issue chains were shortened the loop is bound by
+// L2 -> shared-memory delivery (~70 B/clk/SM: (128 + BN / cta_group) x 128 B per k-block) or by the MMAs (2 BN
+// cycles), which makes 160-wide tiles on CTA pairs the best shape for this UNet (every N is a multiple of 160).
+static int kb_cycles(int bn, int cg) {
+  if (cg == 2) return bn == 128 ? 361 : (bn == 160 ? 398 : 629);
+  return bn == 64 ? 446 : (bn == 128 ? 479 : (bn == 160 ? 549 : 619));
+}
+
+static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int force_cg, int* bn_out, int* cg_out) {
+  const int cand[4] = {160, 256, 128, 64};
+  long long best = 1LL << 62;
+  *bn_out = 128;
+  *cg_out = 1;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (force_cg && cg != force_cg) continue;
+    if (cg == 2 && M <= 128) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (geglu && (bn % 64)) continue;
+      if (bn == 160 && (N % 160)) continue;
+      if (cg == 2 && bn < 128) continue;
+      const long long tiles = (long long)((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+      const long long slots = num_sms() / cg;
+      const long long waves = (tiles + slots - 1) / slots;
+      // per tile: the k loop, plus the part of the epilogue / pipeline turn-around that is not hidden
+      const long long tile_cycles = (long long)num_kb * kb_cycles(bn, cg) + 1500 + (geglu ? 1500 : 0) + (has_res ? 300 : 0) +
+                                    (cg == 2 ? 400 : 0);
+      const long long cost = waves * tile_cycles;
+      if (cost < best) { best = cost; *bn_out = bn; *cg_out = cg; }
+    }
   }
-  return best;
 }
 
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
@@ -606,7 +619,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   //      otherwise idle SMs into fp32 partials, then one small finishing kernel applies the epilogue ----
   EpiArgs epi = {p.bias, p.rowvec, p.ld_rowvec, p.hw, residual, ldr, p.out, p.ldo, p.silu};
   bool split = false;
-  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 16 && (p.N % 8) == 0) {
+  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0) {   // K >= 4096: below, one launch wins
     const int sbn = (p.N % 160 == 0) ? 160 : 128;
     const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
     if (tiles * 2 <= num_sms()) {
@@ -626,13 +639,16 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
       }
     }
   }
-  if (bn == 0) bn = pick_bn(p.m_tiles, p.N, p.geglu);
-  // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles and the N tile can be halved on 8-row groups
-  // (measured on B200: pairs win ~2-12% once the K loop is long enough to be operand-delivery bound, and lose on
-  //  short-K GEMMs whose time is epilogue + prologue: K >= 2048 is the crossover)
-  int cg = (p.M > 128 && bn >= 128 && (bn / 2) % 8 == 0 && p.num_kb >= 32) ? 2 : 1;
-  if (g_force_cg == 1 || split) cg = 1;
-  if (g_force_cg == 2 && bn >= 128 && !split) cg = 2;
+  int cg = 1;
+  if (bn == 0) {
+    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, &bn, &cg);
+  } else {
+    // explicit tile width (tests / tuning): CTA pairs (256-row tiles) when forced, or by the same model
+    int bn_model;
+    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, &bn_model, &cg);
+    if (g_force_cg == 0) cg = (p.M > 128 && bn >= 128 && !split && kb_cycles(bn, 2) < kb_cycles(bn, 1)) ? 2 : 1;
+    if (bn < 128 || p.M <= 128 || split) cg = 1;
+  }
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
   p.has_res = residual ? 1 : 0;
   if (p.has_res && (p.geglu || p.out_f32))

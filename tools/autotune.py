@@ -35,6 +35,7 @@ torch.cuda.synchronize()
 def timeit(fn, n=10):
     for _ in range(2): fn()
     torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True)
+    torch.cuda._sleep(2_000_000)   # ~1 ms of spin: the CPU queues all n launches behind it (GPU-bound timing)
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
