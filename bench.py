@@ -221,6 +221,9 @@ def roofline_probe(unet, pipe_state, peaks):
     try:
         for _ in range(2):
             pending.clear()
+            # ~30 ms of spin first: the CPU queues the whole evaluation behind it, so the event intervals hold kernel
+            # time, not launch latency (Python issues ~15 us per launch, the kernels average ~20 us)
+            torch.cuda._sleep(60_000_000)
             unet.forward_nhwc(pipe_state.x9, pipe_state.t_cur, pipe_state.kv, pipe_state.cls, pipe_state.pose)
         torch.cuda.synchronize()
     finally:

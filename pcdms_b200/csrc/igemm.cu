@@ -353,21 +353,23 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tc_wait_ld();
-          float v[32];
+          float2 v[16];   // column pairs, packed fp32 (FFMA2 path)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              v[j / 2] = __fadd2_rn(v[j / 2], make_float2(b.x, b.y));
+              v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
           }
           if (rv) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              v[j / 2] = __fadd2_rn(v[j / 2], make_float2(b.x, b.y));
+              v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
           }
           if (p.has_res) {
@@ -375,24 +377,23 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = *reinterpret_cast<const uint4*>(sl + sw64(lane, j));
-              float2 f;
-              f = unpack2<DT>(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
-              f = unpack2<DT>(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
-              f = unpack2<DT>(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
-              f = unpack2<DT>(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+              v[j * 4 + 0] = __fadd2_rn(v[j * 4 + 0], unpack2<DT>(u.x));
+              v[j * 4 + 1] = __fadd2_rn(v[j * 4 + 1], unpack2<DT>(u.y));
+              v[j * 4 + 2] = __fadd2_rn(v[j * 4 + 2], unpack2<DT>(u.z));
+              v[j * 4 + 3] = __fadd2_rn(v[j * 4 + 3], unpack2<DT>(u.w));
             }
           }
           if (p.silu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = silu2_exact(v[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
-            u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
-            u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
-            u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
+            u.x = pack2<DT>(v[j * 4 + 0].x, v[j * 4 + 0].y);
+            u.y = pack2<DT>(v[j * 4 + 1].x, v[j * 4 + 1].y);
+            u.z = pack2<DT>(v[j * 4 + 2].x, v[j * 4 + 2].y);
+            u.w = pack2<DT>(v[j * 4 + 3].x, v[j * 4 + 3].y);
             *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = u;
           }
           fence_proxy_async();
@@ -418,33 +419,27 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           tmem_ld32(t_row + c * 64, rh);
           tmem_ld32(t_row + c * 64 + 32, rg);
           tc_wait_ld();
-          float v[32];
-          if (p.bias) {
+          // packed fp32 (FFMA2) arithmetic: this epilogue is issue-bound at K = 320..1280
+          uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
-              rh[j] = __float_as_uint(__uint_as_float(rh[j]) + bh.x);
-              rh[j + 1] = __float_as_uint(__uint_as_float(rh[j + 1]) + bh.y);
-              rh[j + 2] = __float_as_uint(__uint_as_float(rh[j + 2]) + bh.z);
-              rh[j + 3] = __float_as_uint(__uint_as_float(rh[j + 3]) + bh.w);
-              rg[j] = __float_as_uint(__uint_as_float(rg[j]) + bg.x);
-              rg[j + 1] = __float_as_uint(__uint_as_float(rg[j + 1]) + bg.y);
-              rg[j + 2] = __float_as_uint(__uint_as_float(rg[j + 2]) + bg.z);
-              rg[j + 3] = __float_as_uint(__uint_as_float(rg[j + 3]) + bg.w);
+          for (int j = 0; j < 32; j += 4) {
+            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+            if (p.bias) {
+              bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
             }
+            const float2 h0 = __fadd2_rn(make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), make_float2(bh.x, bh.y));
+            const float2 h1 = __fadd2_rn(make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
+            const float2 g0 = __fadd2_rn(make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
+            const float2 g1 = __fadd2_rn(make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
+            const float2 v0 = __fmul2_rn(h0, gelu_erf2_f(g0));
+            const float2 v1 = __fmul2_rn(h1, gelu_erf2_f(g1));
+            o[j / 2] = pack2<DT>(v0.x, v0.y);
+            o[j / 2 + 1] = pack2<DT>(v1.x, v1.y);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) * gelu_erf_f(__uint_as_float(rg[j]));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack2<DT>(v[j * 8 + 0], v[j * 8 + 1]);
-            u.y = pack2<DT>(v[j * 8 + 2], v[j * 8 + 3]);
-            u.z = pack2<DT>(v[j * 8 + 4], v[j * 8 + 5]);
-            u.w = pack2<DT>(v[j * 8 + 6], v[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = u;
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {

@@ -11,12 +11,11 @@ x1280 = torch.randn(16, 8, 16, 1280, device=dev, dtype=dt); w1280 = (torch.randn
 a320 = torch.randn(32768, 320, device=dev, dtype=dt); wg = (torch.randn(2560, 320, device=dev) / 18).to(dt); bg = torch.randn(2560, device=dev)
 qkv = torch.randn(16 * 2048, 960, device=dev, dtype=dt)
 def run():
+    ops.conv3x3(x320, w320, bias=b320, residual=r320)                  # 0: conv 320->320 @32x64 (auto: BN160, CTA pairs)
+    ops.conv3x3(x1280, w1280)                                          # 1: conv 1280->1280 @8x16 (auto: BN160, CTA pairs)
+    ops.gemm(a320, wg, bias=bg, geglu=True)                            # 2: GEGLU GEMM (auto: BN256, single CTA)
     L.pcdm_set_gemm_cta_group(1)
-    ops.conv3x3(x320, w320, bias=b320, residual=r320, bn=160)          # 0: conv 320->320 @32x64, single-CTA tiles
-    ops.conv3x3(x1280, w1280, bn=256)                                  # 1: conv 1280->1280 @8x16
-    ops.gemm(a320, wg, bias=bg, geglu=True, bn=256)                    # 2: GEGLU GEMM
-    L.pcdm_set_gemm_cta_group(2)
-    ops.conv3x3(x320, w320, bias=b320, residual=r320, bn=160)          # 3: conv 320 CTA pairs
+    ops.conv3x3(x320, w320, bias=b320, residual=r320, bn=160)          # 3: conv 320->320, single-CTA BN160 tiles
     L.pcdm_set_gemm_cta_group(0)
     ops.attention(qkv[:, :320], qkv[:, 320:640], qkv[:, 640:], 16, 5)  # 4: self-attention 2048x2048, 5 heads
     torch.cuda.synchronize()
