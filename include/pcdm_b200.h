@@ -95,6 +95,7 @@ int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const f
  * F.scaled_dot_product_attention behind diffusers' attention processors (stage2_batchtest_inpaint_model.py:133;
  * SURVEY.md §8a a9).  q: element (b, s, h, d) at q[(b*Sq + s)*ldq + h*64 + d]; k, v likewise with Skv; out likewise
  * with ldo — so q/k/v may be column slices of one fused projection buffer. */
+int pcdm_set_attention_poly(int on); /* experiment hook: 1 = half of the softmax exp2 on the FMA pipe (default 0: measured slower) */
 int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);
 

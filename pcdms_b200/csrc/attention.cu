@@ -45,7 +45,7 @@ __device__ __forceinline__ void pair_barrier(int q) {   // the two softmax warps
   asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
 }
 
-template <int DT>
+template <int DT, int ATT_POLY_OF_4>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,32 +216,48 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
           m_ref = m_new;
         }
       }
-      // p = exp2(s * scale - m_ref), row sum, 16-bit pack into this warp's 32 P columns
-      float sum = 0.f;
+      // p = exp2(s * scale - m_ref), row sum, 16-bit pack into this warp's 32 P columns; packed fp32 (FFMA2) math.
+      // ATT_POLY_OF_4 of every 4 column pairs can take their exp2 on the FMA pipe (exp2_poly2) instead of the SFU — the
+      // FlashAttention-4 remedy for the 16 ex2/clk/SM limit.  Measured here (tools/dev_attn_perf.py, 2048x2048, d=64):
+      // 150 us with 0/4, 156 with 1/4, 182 with 2/4, 208 with 3/4 — these softmax warps are bound by their own
+      // instruction stream (4 warps per scheduler), not by the SFU, so the default is 0.
+      float2 sum2 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      auto exp_pair = [&](int c, int i) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
+                                    sc2, nm2);
+        float2 e;
+        if ((i & 3) < ATT_POLY_OF_4) {
+          e = exp2_poly2(x);
+        } else {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+        }
+        return e;
+      };
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
         if (kv_left >= 64) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
-            const float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
-            sum += a + bq;
-            pk[i] = pack2<DT>(a, bq);
+            const float2 e = exp_pair(c, i);
+            sum2 = __fadd2_rn(sum2, e);
+            pk[i] = pack2<DT>(e.x, e.y);
           }
-        } else {
+        } else {   // ragged last block: columns past the sequence contribute nothing
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = exp2f(__uint_as_float(s[c * 32 + 2 * i]) * p.scale_log2 - m_ref);
-            float bq = exp2f(__uint_as_float(s[c * 32 + 2 * i + 1]) * p.scale_log2 - m_ref);
-            if (c * 32 + 2 * i >= kv_left) a = 0.f;
-            if (c * 32 + 2 * i + 1 >= kv_left) bq = 0.f;
-            sum += a + bq;
-            pk[i] = pack2<DT>(a, bq);
+            float2 e = exp_pair(c, i);
+            if (c * 32 + 2 * i >= kv_left) e.x = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_left) e.y = 0.f;
+            sum2 = __fadd2_rn(sum2, e);
+            pk[i] = pack2<DT>(e.x, e.y);
           }
         }
         tmem_st16(tmem + lane_off + ATT_TMEM_P + half * 32 + c * 16, pk);
       }
+      const float sum = sum2.x + sum2.y;
       l += sum;
       tc_wait_st();
       tc_fence_before();
@@ -295,6 +311,12 @@ static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, i
   return make_tmap(m, base, 4, dims, strides, box);
 }
 
+static int g_att_poly = 0;   // 1: half of the exp2 on the FMA pipe (experiment hook; measured slower, see the kernel)
+extern "C" int pcdm_set_attention_poly(int on) {
+  g_att_poly = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                               void* out, long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype,
                               void* stream_) {
@@ -314,17 +336,25 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
-    PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    configured = true;
-  }
   const int grid = B * heads * p.q_tiles;
-  if (dtype == DT_F16)
-    PCDM_CUDA(launch_kernel(attention_kernel<DT_F16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
-  else
-    PCDM_CUDA(launch_kernel(attention_kernel<DT_BF16>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p));
+#define ATT_LAUNCH(DT_, P_)                                                                                         \
+  do {                                                                                                              \
+    static bool configured = false;                                                                                 \
+    if (!configured) {                                                                                              \
+      PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                     ATT_SMEM_BYTES));                                                              \
+      configured = true;                                                                                            \
+    }                                                                                                               \
+    PCDM_CUDA(launch_kernel(attention_kernel<DT_, P_>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p)); \
+  } while (0)
+  if (dtype == DT_F16) {
+    if (g_att_poly) ATT_LAUNCH(DT_F16, 2);
+    else ATT_LAUNCH(DT_F16, 0);
+  } else {
+    if (g_att_poly) ATT_LAUNCH(DT_BF16, 2);
+    else ATT_LAUNCH(DT_BF16, 0);
+  }
+#undef ATT_LAUNCH
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -359,6 +359,25 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// Two exp2 on the FMA pipe instead of the SFU (16 ex2/clk/SM is what bounds attention at head_dim 64).  Cody-Waite:
+// n = round(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-4 polynomial (relative error
+// 4e-5: a sixth of an fp16 ulp of the 16-bit P it feeds), exponent spliced in with one integer shift-add.
+// x <= ~8 by construction (lazy rescale threshold); very negative x is clamped so that n stays in the 9-bit field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -120.0f);
+  x.y = fmaxf(x.y, -120.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 r = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.0096181291f, 0.0096181291f), f, make_float2(0.0555041087f, 0.0555041087f));
+  p = __ffma2_rn(p, f, make_float2(0.2402265070f, 0.2402265070f));
+  p = __ffma2_rn(p, f, make_float2(0.6931471806f, 0.6931471806f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
+}
+
 // Two GELUs at once: the same A&S 7.1.26 form with the fp32 arithmetic on the packed FFMA2 path (the GEGLU epilogue
 // is issue-bound: ~10 issue slots + 2 SFU ops per element instead of ~22 + 2).
 __device__ __forceinline__ float2 gelu_erf2_f(float2 x) {

@@ -1,4 +1,5 @@
-"""Dev check (GPU): attention kernel variants — correctness vs an fp32 softmax reference and timing."""
+"""Dev check (GPU): attention kernel — share of exp2 on the FMA pipe (0..3 of 4 column pairs): correctness vs an fp32
+softmax reference and timing."""
 import sys; sys.path.insert(0, ".")
 import torch
 from pcdms_b200 import ops, lib
@@ -6,6 +7,7 @@ L = lib.load(); dev = "cuda"
 def timeit(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True)
+    torch.cuda._sleep(4_000_000)
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
@@ -22,20 +24,19 @@ for dt in (torch.float16, torch.bfloat16):
         C = heads * 64
         q = torch.randn(B * Sq, C, device=dev).to(dt); k = torch.randn(B * Skv, C, device=dev).to(dt); v = torch.randn(B * Skv, C, device=dev).to(dt)
         want = ref(q, k, v, B, heads)
-        for var in (1, 2):
-            if var == 2 and Sq < 256: continue
-            L.pcdm_set_attention_variant(var)
+        for var in (0, 1):
+            L.pcdm_set_attention_poly(var)
             got = ops.attention(q, k, v, B, heads).float()
             err = (got - want).abs().max().item()
-            print(f"{str(dt)[6:]:9s} B{B} h{heads} Sq{Sq} Skv{Skv} variant {var}: max abs err {err:.2e} nan {bool(torch.isnan(got).any())}", flush=True)
+            print(f"{str(dt)[6:]:9s} B{B} h{heads} Sq{Sq} Skv{Skv} fma-exp2 {var}: max abs err {err:.2e} nan {bool(torch.isnan(got).any())}", flush=True)
 dt = torch.bfloat16
 qkv = torch.randn(16 * 2048, 960, device=dev, dtype=dt)
 q = torch.randn(16 * 2048, 320, device=dev, dtype=dt); kv = torch.randn(16 * 258, 640, device=dev, dtype=dt)
 qkv2 = torch.randn(16 * 512, 1920, device=dev, dtype=dt)
-for var in (1, 2):
-    L.pcdm_set_attention_variant(var)
+for var in (0, 1):
+    L.pcdm_set_attention_poly(var)
     a = timeit(lambda: ops.attention(qkv[:, :320], qkv[:, 320:640], qkv[:, 640:], 16, 5))
     b = timeit(lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 5))
     c = timeit(lambda: ops.attention(qkv2[:, :640], qkv2[:, 640:1280], qkv2[:, 1280:], 16, 10))
-    print(f"variant {var}: self2048 {a:7.1f} us ({85.9e3/a:6.1f} TF)  cross258 {b:6.1f} us  self512 {c:6.1f} us", flush=True)
-L.pcdm_set_attention_variant(0)
+    print(f"fma-exp2 {var}: self2048 {a:7.1f} us ({85.9e3/a:6.1f} TF)  cross258 {b:6.1f} us  self512 {c:6.1f} us", flush=True)
+L.pcdm_set_attention_poly(0)
