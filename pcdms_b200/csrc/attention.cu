@@ -111,8 +111,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);  // S = Q K^T : both operands K-major
-    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);   // O += P V  : A from TMEM, B (V) MN-major
+    // S = Q K^T : both operands K-major, N = the block's kv rows rounded up to 16 (a ragged last block — 2 rows of the
+    // 258 cross-attention tokens — costs a 16-wide MMA, not a 128-wide one); O += P V : A from TMEM, B (V) MN-major,
+    // one K=16 MMA per 16 kv rows that exist
+    constexpr uint32_t idesc_qk0 = make_idesc(DT, 128, 0, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);
+    auto n16_of = [&](int j) { return (min(128, p.Skv - j * 128) + 15) >> 4; };
     // shared-memory descriptors: constant high word (SBO 1024 B, version 1, 128-byte swizzle), low word = addr >> 4
     // | LBO >> 4 << 16, advanced by plain adds
     constexpr uint64_t kDescHi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       tc_fence_after();
       if (elect_one()) {
         const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
+        const uint32_t idesc_qk = idesc_qk0 | ((uint32_t)(n16_of(j) * 2) << 17);   // N >> 3 at bits [17, 23)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tmem + ATT_TMEM_S, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
@@ -141,10 +146,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       const int stage = j & 1;
       if (elect_one()) {
         const uint32_t v_lo = (kv_lo0 + (uint32_t)((stage * 2 + 1) * (ATT_TILE_BYTES >> 4))) | ((1024u >> 4) << 16);
+        const int n16 = n16_of(j);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
-          umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, kDescHi | (v_lo + (2048u >> 4) * k), idesc_pv,
-                  (j | k) != 0);
+          if (k < n16)
+            umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, kDescHi | (v_lo + (2048u >> 4) * k), idesc_pv,
+                    (j | k) != 0);
         tc_commit(&kv_empty[stage]);
         tc_commit(pv_done);
       }
@@ -245,14 +252,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
             sum2 = __fadd2_rn(sum2, e);
             pk[i] = pack2<DT>(e.x, e.y);
           }
-        } else {   // ragged last block: columns past the sequence contribute nothing
+        } else {
+          // ragged last block: columns past the sequence contribute nothing and cost nothing (warp-uniform skips);
+          // the PV MMAs read only the P columns of 16-row groups that exist, so chunks beyond them are not written
+          if (c * 32 >= ((kv_left + 15) & ~15)) continue;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float2 e = exp_pair(c, i);
-            if (c * 32 + 2 * i >= kv_left) e.x = 0.f;
-            if (c * 32 + 2 * i + 1 >= kv_left) e.y = 0.f;
-            sum2 = __fadd2_rn(sum2, e);
-            pk[i] = pack2<DT>(e.x, e.y);
+            if (c * 32 + 2 * i < kv_left) {
+              float2 e = exp_pair(c, i);
+              if (c * 32 + 2 * i + 1 >= kv_left) e.y = 0.f;
+              sum2 = __fadd2_rn(sum2, e);
+              pk[i] = pack2<DT>(e.x, e.y);
+            } else {
+              pk[i] = 0u;
+            }
           }
         }
         tmem_st16(tmem + lane_off + ATT_TMEM_P + half * 32 + c * 16, pk);

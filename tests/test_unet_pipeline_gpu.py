@@ -96,6 +96,21 @@ def test_unet_full_size_stage2_fp16_and_bf16():
     _check(outb, ref, 2.4e-2, 4e-3, "full stage-2 UNet bf16")
 
 
+@pytest.mark.parametrize("which,h,w,s_kv", [("stage2", 64, 128, 258), ("stage3", 64, 64, 257)])
+def test_unet_full_size_other_baseline_shapes(which, h, w, s_kv):
+    """The latent shapes of BASELINE configs 3 (stage-2 at 512x512: 64x128 latents, self-attention over 8192 tokens)
+    and 5 (stage-3: in_channels 8, no class embedding / pose, 64x64 latents, 257 tokens) with the real-size nets, one
+    batch row (the CPU oracle needs ~2 TFLOP per row at these sizes)."""
+    from oracle.factory import make_unet_inputs
+    from oracle.unet import UNetConfig
+    cfg = UNetConfig.stage2() if which == "stage2" else UNetConfig.stage3()
+    o, m = _models(cfg, torch.float16)
+    i = make_unet_inputs(cfg, batch=1, h=h, w=w, s_kv=s_kv)
+    out, ref = _run_unet(o, m, i, 501)
+    assert out.shape == ref.shape
+    _check(out, ref, 3e-3, 5e-4, f"full {which} UNet fp16 at {h}x{w}")
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_pipeline_config1_shape_tiny_weights(use_graph):
     """10-step DDIM, guidance 2.0, through B200Stage2InpaintPipeline.__call__ vs the oracle loop (which is itself
