@@ -33,7 +33,9 @@ extern "C" {
 
 #define PCDM_FLAG_GEGLU 1   /* gemm: weight rows packed [32 value | 32 gate]; writes N/2 columns value*gelu(gate) */
 #define PCDM_FLAG_OUT_F32 2 /* gemm/conv: write fp32 instead of the 16-bit dtype */
-#define PCDM_FLAG_SILU 4    /* norm kernels: apply SiLU after the affine */
+#define PCDM_FLAG_SILU 4    /* gemm/conv epilogue and norm kernels: apply SiLU last */
+#define PCDM_FLAG_GELU 8    /* gemm/conv epilogue: apply GELU (erf form) last */
+#define PCDM_FLAG_PAD_BR 16 /* conv3x3 stride 2: zero padding on the bottom/right only (F.pad(x,(0,1,0,1)) + conv pad 0) */
 
 int pcdm_abi_version(void);
 /* 1 (default): every kernel is launched with programmatic dependent launch, so its prologue overlaps the tail of its
@@ -47,7 +49,7 @@ const char* pcdm_last_error(void);
  *   out[M, N] = act( A[M, K] . W[N, K]^T + bias[N] + rowvec[m / rows_per_image, :] + residual[M, N] )
  * A may be given as two K-segments (a: columns [0, k1), a2: columns [k1, K)) — the skip-concat of the up blocks
  * is consumed in place, never materialised.  lda/lda2/ldo/ldr/ld_rowvec are row strides in elements.
- * flags: PCDM_FLAG_GEGLU | PCDM_FLAG_OUT_F32 | PCDM_FLAG_SILU (act = SiLU, else identity).
+ * flags: PCDM_FLAG_GEGLU | PCDM_FLAG_OUT_F32 | PCDM_FLAG_SILU (act = SiLU) | PCDM_FLAG_GELU (act = GELU; else identity).
  * K % 64 == 0, N % 32 == 0.  bn = 0 picks the N tile automatically (64/128/160/256 to force one). */
 int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w, void* out,
               long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
@@ -68,7 +70,9 @@ int pcdm_set_workspace(void* ptr, long long bytes);
  * (SURVEY.md §8a a4-a6, a10).
  *   x: [B, stride*H, stride*W, Cin]; out: [B, H, W, Cout]; w_packed: [Cout][3][3][Cin] (tap-major K);
  *   rowvec: fp32, row b at rowvec + b*ld_rowvec, added per image (the resnet's time_emb_proj term);
- *   residual: [B, H, W, Cout].  Cin % 64 == 0, Cout % 32 == 0, W | 128, (H*W) % 128 == 0 or 128 % (H*W) == 0. */
+ *   residual: [B, H, W, Cout].  Cin % 64 == 0, Cout % 32 == 0; W | 128 with (H*W) % 128 == 0 or 128 % (H*W) == 0, or
+ *   W % 128 == 0 (the VAE / pose-encoder resolutions).  With stride 2, PCDM_FLAG_PAD_BR selects the asymmetric padding
+ *   of the VAE encoder's Downsample2D (diffusers: F.pad(x, (0, 1, 0, 1)) then Conv2d(stride 2, padding 0)). */
 int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                  long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride,
                  int dtype, int flags, int bn, void* stream);
@@ -132,6 +136,30 @@ int pcdm_ddim_step(const void* model_output, int eps_dtype, const void* sample, 
 /* DDPMScheduler.add_noise (stage2_train_inpaint_model.py:361): out = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise. */
 int pcdm_add_noise(const void* x0, const void* noise, void* out, int dtype, const float* alphas_cumprod,
                    const long long* timesteps, int B, long long per_sample, void* stream);
+
+/* UniPCMultistepScheduler.step (diffusers 0.24.0 — the scheduler stage2_batchtest_inpaint_model.py:132 installs):
+ * predict_x0, solver bh1/bh2, solver_order <= 2, epsilon prediction, corrector on.  A table row holds the 16
+ * schedule-only scalars of one step: {sigma_t, alpha_t (convert_model_output); use_corrector, sigma_t/sigma_s0,
+ * alpha_t*h_phi_1, alpha_t*B_h, rk, rho_0, rho_last, order (multistep_uni_c_bh_update); sigma_t/sigma_s0,
+ * alpha_t*h_phi_1, alpha_t*B_h, rk, rho, order (multistep_uni_p_bh_update)}.  fp32 state, IEEE round-to-nearest
+ * arithmetic in the reference's operation order (bit-identical to its fp32 CPU evaluation).
+ * pcdm_cfg_unipc_step: fused CFG combine + update + rewrite of the next UNet input, graph-replayable like
+ * pcdm_cfg_ddim_step; state = 4 planes [n,4,HW] fp32 {sample, last_sample, model_outputs[-1], model_outputs[-2]};
+ * coef_table: device, steps x 16 floats.
+ * pcdm_unipc_step: the scheduler protocol's step() on same-shape contiguous tensors (dtypes 0 f16, 1 bf16, 2 f32);
+ * last_sample / m0 / m1 are fp32 history buffers of numel entries owned by the caller; coef_row_host: 16 HOST floats. */
+int pcdm_cfg_unipc_step(const void* eps, int eps_dtype, long long ld_eps, float* state, void* x9, int x9_dtype,
+                        long long ld_x9, const float* coef_table, int* step_counter, float guidance_scale, int n,
+                        int HW, const float* t_table, float* t_cur, void* stream);
+int pcdm_unipc_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
+                    float* last_sample, float* m0, float* m1, const float* coef_row_host, long long numel,
+                    void* stream);
+
+/* y[m, :] = softmax(scale * x[m, :]): fp32 scores in, 16-bit probabilities out (row strides in elements).  The VAE
+ * mid-block attention (diffusers AutoencoderKL, one head of dim 512: stage2_inpaint_pipeline.py:443,528) runs as
+ * pcdm_gemm (Q K^T, fp32 out) -> pcdm_softmax_rows -> pcdm_gemm (P V).  N % 4 == 0, N <= 16384. */
+int pcdm_softmax_rows(const float* x, long long ldx, void* y, long long ldy, int M, int N, float scale, int dtype,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -185,6 +185,178 @@ __global__ void ddim_step_kernel(const void* __restrict__ eps, int eps_dt, const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// UniPCMultistepScheduler.step (diffusers 0.24.0; predict_x0, solver bh1/bh2, solver_order <= 2, epsilon prediction) —
+// the scheduler the reference's batch-test driver installs (stage2_batchtest_inpaint_model.py:132).  All step-dependent
+// scalars are functions of the noise schedule only and come from a 16-float host-built table row:
+//   [0] sigma_t  [1] alpha_t            convert_model_output: m_t = (x - sigma_t e) / alpha_t
+//   [2] use_corrector  [3] c_a = sigma_t/sigma_s0  [4] c_b = alpha_t h_phi_1  [5] c_c = alpha_t B_h  [6] c_rk
+//   [7] c_rho0  [8] c_rho_last  [9] corrector order                             multistep_uni_c_bh_update
+//   [10] p_a  [11] p_b  [12] p_c  [13] p_rk  [14] p_rho  [15] predictor order   multistep_uni_p_bh_update
+// Per element the arithmetic follows the reference's tensor expressions operation by operation with IEEE
+// round-to-nearest intrinsics (no FMA contraction), so fp32 results are bit-identical to the torch-CPU evaluation.
+// State (fp32): x = current sample, last = last_sample, ma = model_outputs[-1], mb = model_outputs[-2].
+// ---------------------------------------------------------------------------------------------------------------
+struct UniPCRow { float v[16]; };
+
+__device__ __forceinline__ void unipc_update(const UniPCRow& r, float e, float& x, float& last, float& ma, float& mb) {
+  const float mt = __fdiv_rn(__fsub_rn(x, __fmul_rn(r.v[0], e)), r.v[1]);
+  float xc = x;
+  if (r.v[2] != 0.f) {
+    const float xt_ = __fsub_rn(__fmul_rn(r.v[3], last), __fmul_rn(r.v[4], ma));
+    const float d1t = __fsub_rn(mt, ma);
+    float corr = __fmul_rn(r.v[8], d1t);
+    if (r.v[9] >= 2.f) corr = __fadd_rn(__fmul_rn(r.v[7], __fdiv_rn(__fsub_rn(mb, ma), r.v[6])), corr);
+    xc = __fsub_rn(xt_, __fmul_rn(r.v[5], corr));
+  }
+  // shift the history: model_outputs = [old ma, mt], last_sample = corrected sample
+  const float m_prev = ma;
+  mb = ma;
+  ma = mt;
+  last = xc;
+  float xn = __fsub_rn(__fmul_rn(r.v[10], xc), __fmul_rn(r.v[11], mt));
+  if (r.v[15] >= 2.f) {
+    const float pred = __fmul_rn(r.v[14], __fdiv_rn(__fsub_rn(m_prev, mt), r.v[13]));
+    xn = __fsub_rn(xn, __fmul_rn(r.v[12], pred));
+  }
+  x = xn;
+}
+
+// Fused per-step kernel of the B200 pipeline: CFG combine + UniPC update + rewrite of the next UNet input, replayable
+// from one CUDA graph (device step counter, as cfg_ddim_step_kernel).  state: 4 planes of [n, 4, HW] fp32.
+__global__ void cfg_unipc_step_kernel(const void* __restrict__ eps, int eps_dt, long long ld_eps,
+                                      float* __restrict__ state, void* __restrict__ x9, int x9_dt, long long ld_x9,
+                                      const UniPCRow* __restrict__ coef, int* __restrict__ step_counter, float guidance,
+                                      int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step = *step_counter;
+  const UniPCRow r = coef[step];
+  const long long total = (long long)n * HW;
+  const long long plane = total * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int b = (int)(i / HW);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float eu = load_any(eps, ((long long)b * HW + p) * ld_eps + c, eps_dt);
+      const float ec = load_any(eps, ((long long)(b + n) * HW + p) * ld_eps + c, eps_dt);
+      const float e = __fadd_rn(eu, __fmul_rn(guidance, __fsub_rn(ec, eu)));
+      const long long li = ((long long)b * 4 + c) * HW + p;
+      float x = state[li], last = state[plane + li], ma = state[2 * plane + li], mb = state[3 * plane + li];
+      unipc_update(r, e, x, last, ma, mb);
+      state[li] = x; state[plane + li] = last; state[2 * plane + li] = ma; state[3 * plane + li] = mb;
+      store_any(x9, ((long long)b * HW + p) * ld_x9 + c, x9_dt, x);
+      store_any(x9, ((long long)(b + n) * HW + p) * ld_x9 + c, x9_dt, x);
+    }
+  }
+  __syncthreads();
+  __shared__ bool last_block;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(step_counter + 1), 1u);
+    last_block = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_block && threadIdx.x == 0) {
+    step_counter[1] = 0;
+    step_counter[0] = step + 1;
+    if (t_table && t_cur) *t_cur = t_table[step + 1];
+  }
+}
+
+// stand-alone scheduler.step for callers that drive the scheduler protocol tensor by tensor: model_output / sample /
+// prev_sample are same-shape contiguous tensors, the three history planes are fp32 buffers the scheduler object owns.
+__global__ void unipc_step_kernel(const void* __restrict__ eps, int eps_dt, const void* __restrict__ sample,
+                                  void* __restrict__ prev, int dt, float* __restrict__ last, float* __restrict__ ma,
+                                  float* __restrict__ mb, UniPCRow r, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float x = load_any(sample, i, dt), l = last[i], a = ma[i], b = mb[i];
+    unipc_update(r, load_any(eps, i, eps_dt), x, l, a, b);
+    last[i] = l; ma[i] = a; mb[i] = b;
+    store_any(prev, i, dt, x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row softmax of fp32 scores -> 16-bit probabilities: y[m, :] = softmax(scale * x[m, :]).  Used by the VAE mid-block
+// attention (one head of dim 512, diffusers AutoencoderKL: stage2_inpaint_pipeline.py:443,528), whose QK^T and PV
+// products run on the GEMM kernel.  One CTA per row, the row lives in registers (N <= 16384): one read, one write.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 256;
+constexpr int SM_MAXV = 16;   // float4 per thread
+
+template <int DT>
+__global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ x, long long ldx,
+                                                                  void* __restrict__ y, long long ldy, int M, int N,
+                                                                  float scale_log2e) {
+  using T = typename TypeOf<DT>::T;
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[SM_THREADS / 32];
+  __shared__ float bcast;
+  const int nv = N / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)m * ldx);
+    float4 v[SM_MAXV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SM_MAXV; ++k) {
+      const int i = threadIdx.x + k * SM_THREADS;
+      if (i < nv) {
+        v[k] = __ldg(xr + i);
+        mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = red[0];
+      for (int w = 1; w < SM_THREADS / 32; ++w) t = fmaxf(t, red[w]);
+      bcast = t;
+    }
+    __syncthreads();
+    mx = bcast;
+    const float off = mx * scale_log2e;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < SM_MAXV; ++k) {
+      const int i = threadIdx.x + k * SM_THREADS;
+      if (i < nv) {
+        v[k].x = exp2f(fmaf(v[k].x, scale_log2e, -off));
+        v[k].y = exp2f(fmaf(v[k].y, scale_log2e, -off));
+        v[k].z = exp2f(fmaf(v[k].z, scale_log2e, -off));
+        v[k].w = exp2f(fmaf(v[k].w, scale_log2e, -off));
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+    sum = warp_sum(sum);
+    __syncthreads();   // red / bcast reuse
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < SM_THREADS / 32; ++w) t += red[w];   // fixed order: bit-reproducible
+      bcast = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = bcast;
+    uint2* yr = reinterpret_cast<uint2*>(reinterpret_cast<T*>(y) + (long long)m * ldy);
+#pragma unroll
+    for (int k = 0; k < SM_MAXV; ++k) {
+      const int i = threadIdx.x + k * SM_THREADS;
+      if (i < nv) yr[i] = make_uint2(pack2<DT>(v[k].x * inv, v[k].y * inv), pack2<DT>(v[k].z * inv, v[k].w * inv));
+    }
+    __syncthreads();
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -271,6 +443,50 @@ extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const voi
   if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "ddim_step: bad dtype");
   if (numel <= 0) return set_error(PCDM_ERR_INVALID, "ddim_step: empty problem");
   PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, numel));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_cfg_unipc_step(const void* eps, int eps_dtype, long long ld_eps, float* state, void* x9,
+                                   int x9_dtype, long long ld_x9, const float* coef_table, int* step_counter,
+                                   float guidance_scale, int n, int HW, const float* t_table, float* t_cur,
+                                   void* stream_) {
+  if (!eps || !state || !x9 || !coef_table || !step_counter) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || x9_dtype < 0 || x9_dtype > 1) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: bad dtype");
+  if (n <= 0 || HW <= 0 || ld_eps < 4 || ld_x9 < 4) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: bad shape");
+  const long long total = (long long)n * HW;
+  PCDM_CUDA(launch_kernel(cfg_unipc_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, state, x9, x9_dtype, ld_x9, reinterpret_cast<const UniPCRow*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_unipc_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
+                               float* last_sample, float* m0, float* m1, const float* coef_row_host, long long numel,
+                               void* stream_) {
+  if (!model_output || !sample || !prev_sample || !last_sample || !m0 || !m1 || !coef_row_host)
+    return set_error(PCDM_ERR_INVALID, "unipc_step: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "unipc_step: bad dtype");
+  if (numel <= 0) return set_error(PCDM_ERR_INVALID, "unipc_step: empty problem");
+  UniPCRow r;
+  memcpy(r.v, coef_row_host, sizeof(r.v));
+  PCDM_CUDA(launch_kernel(unipc_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, last_sample, m0, m1, r, numel));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_softmax_rows(const float* x, long long ldx, void* y, long long ldy, int M, int N, float scale,
+                                 int dtype, void* stream_) {
+  if (!x || !y) return set_error(PCDM_ERR_INVALID, "softmax_rows: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "softmax_rows: bad dtype");
+  if (M <= 0 || N <= 0) return set_error(PCDM_ERR_INVALID, "softmax_rows: empty problem");
+  if (N % 4 || N > 4 * SM_THREADS * SM_MAXV || (ldx % 4) || (ldy % 4))
+    return set_error(PCDM_ERR_UNSUPPORTED, "softmax_rows: N % 4 == 0, N <= 16384, strides % 4 == 0");
+  int grid = M < 8 * num_sms() ? M : 8 * num_sms();
+  const float sl2 = scale * 1.4426950408889634f;
+  if (dtype == DT_F16)
+    PCDM_CUDA(launch_kernel(softmax_rows_kernel<DT_F16>, dim3(grid), dim3(SM_THREADS), 0, (cudaStream_t)stream_, 1, x, ldx, y, ldy, M, N, sl2));
+  else
+    PCDM_CUDA(launch_kernel(softmax_rows_kernel<DT_BF16>, dim3(grid), dim3(SM_THREADS), 0, (cudaStream_t)stream_, 1, x, ldx, y, ldy, M, N, sl2));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

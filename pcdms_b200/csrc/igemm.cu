@@ -33,7 +33,8 @@ struct IGemmParams {
   int M, N;
   int num_kb;      // K / 64
   int m_tiles, n_tiles;
-  int mode;        // 0 = plain GEMM (A row-major [M, K], up to two K-segments), 1 = conv3x3 s1, 2 = conv3x3 s2
+  int mode;        // 0 = plain GEMM (A row-major [M, K], up to two K-segments), 1 = conv3x3 s1, 2 = conv3x3 s2 (pad 1),
+                   // 3 = conv3x3 s2 with bottom/right padding only
   int H, W;        // conv: output height / width
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
@@ -51,7 +52,7 @@ struct IGemmParams {
   long long ldo;
   int geglu;
   int out_f32;
-  int silu;
+  int silu;        // activation: 0 none, 1 SiLU, 2 GELU (erf)
 };
 
 template <int BN, int CG>
@@ -130,10 +131,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int m_blk = mn / p.n_tiles, n_blk = mn % p.n_tiles;
       const int m0 = (m_blk * CG + (int)rank) * 128;
-      int b0 = 0, y0 = 0;
+      int b0 = 0, y0 = 0, x0 = 0;   // x0 != 0 only for rows wider than a tile (W > 128: 128-pixel row segments)
       if (p.mode != 0) {
         b0 = m0 / hw;
-        y0 = (m0 - b0 * hw) / p.W;
+        const int rem = m0 - b0 * hw;
+        y0 = rem / p.W;
+        x0 = rem - y0 * p.W;
       }
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
@@ -156,14 +159,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           seg_end = min(kb_end, (tap + 1) * p.cblocks);
           c3 = b0;
           if (p.mode == 1) {
-            c1 = s - 1;
+            c1 = x0 + s - 1;
             c2 = y0 + r - 1;
-          } else {
+          } else if (p.mode == 2) {
             // input row 2y + r - 1: r=0 -> odd plane, row y-1; r=1 -> even plane, row y; r=2 -> odd plane, row y
             const int py = (r != 1), px = (s != 1);
             tma = &p.tmA[py * 2 + px];
-            c1 = (s == 0) ? -1 : 0;
+            c1 = x0 + ((s == 0) ? -1 : 0);
             c2 = y0 + ((r == 0) ? -1 : 0);
+          } else {
+            // mode 3, padding on the bottom/right only: input row 2y + r: r=0 -> even plane, row y; r=1 -> odd plane,
+            // row y; r=2 -> even plane, row y+1 (row H of the plane is out of bounds = the zero padding)
+            const int py = (r == 1), px = (s == 1);
+            tma = &p.tmA[py * 2 + px];
+            c1 = x0 + ((s == 2) ? 1 : 0);
+            c2 = y0 + ((r == 2) ? 1 : 0);
           }
         }
         const bool is_gemm = p.mode == 0;
@@ -313,9 +323,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
                 v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
               }
             }
-            if (p.silu) {
+            if (p.silu == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if (p.silu == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
             }
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
                                                    ((long long)split * p.M + m) * p.ldo + n0);
@@ -383,9 +396,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               v[j * 4 + 3] = __fadd2_rn(v[j * 4 + 3], unpack2<DT>(u.w));
             }
           }
-          if (p.silu) {
+          if (p.silu == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = silu2_exact(v[j]);
+          } else if (p.silu == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf2_f(v[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -511,9 +527,12 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
       f = unpack2<DT>(u.z); v[4] += f.x; v[5] += f.y;
       f = unpack2<DT>(u.w); v[6] += f.x; v[7] += f.y;
     }
-    if (silu) {
+    if (silu == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    } else if (silu == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
     }
     uint4 o;
     o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
@@ -737,7 +756,7 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
   }
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
   p.out = out; p.ldo = ldo;
-  p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
+  p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: rowvec stride must be a multiple of 4");
   if (p.geglu && p.out_f32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU with fp32 output");
   return dispatch_igemm(p, dtype, bn, w, K, residual, ldr, stream);
@@ -752,11 +771,17 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
   if (stride != 1 && stride != 2) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: stride must be 1 or 2");
   if (B <= 0 || H <= 0 || W <= 0) return set_error(PCDM_ERR_INVALID, "conv3x3: empty problem");
   if (Cin % 64 || Cout % 32) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: Cin must be a multiple of 64 and Cout of 32");
-  // output tile = 128 consecutive NHWC pixels = tile_b images x tile_h rows x W columns
-  if (W > 128 || (128 % W)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: output width must divide 128");
+  // output tile = 128 consecutive NHWC pixels = tile_b images x tile_h rows x W columns, or (rows wider than a tile,
+  // W % 128 == 0: the VAE / pose-encoder resolutions) one 128-pixel segment of a row
+  const bool wide = W > 128;
+  if (wide ? (W % 128) : (128 % W)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: output width must divide 128 or be a multiple of it");
+  const bool pad_br = (flags & PCDM_FLAG_PAD_BR) != 0;
+  if (pad_br && stride != 2) return set_error(PCDM_ERR_INVALID, "conv3x3: PCDM_FLAG_PAD_BR goes with stride 2");
   const int hw = H * W;
-  int tile_h, tile_b;
-  if (hw >= 128) {
+  int tile_h, tile_b, tile_w = wide ? 128 : W;
+  if (wide) {
+    tile_h = 1; tile_b = 1;
+  } else if (hw >= 128) {
     if (hw % 128) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: H*W must be a multiple of 128 (or divide it)");
     tile_h = 128 / W; tile_b = 1;
   } else {
@@ -764,13 +789,14 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
     tile_h = H; tile_b = 128 / hw;
   }
   if (tile_b > B) tile_b = B;
+  if ((long long)B * hw > 0x7fffffffLL - 256) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: B*H*W exceeds 2^31");
   IGemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = B * hw; p.N = Cout; p.num_kb = 9 * (Cin / 64);
   p.m_tiles = (p.M + 127) / 128;
-  p.mode = stride; p.H = H; p.W = W; p.cblocks = Cin / 64; p.kb_split = p.num_kb;
-  p.a_bytes = 128u * (uint32_t)(W * tile_h * tile_b);
-  const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)tile_h, (uint32_t)tile_b};
+  p.mode = stride == 1 ? 1 : (pad_br ? 3 : 2); p.H = H; p.W = W; p.cblocks = Cin / 64; p.kb_split = p.num_kb;
+  p.a_bytes = 128u * (uint32_t)(tile_w * tile_h * tile_b);
+  const uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_b};
   if (stride == 1) {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)hw * Cin * 2};
@@ -787,7 +813,7 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
   }
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = hw;
   p.out = out; p.ldo = Cout;
-  p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
+  p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: rowvec stride must be a multiple of 4");
   return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, residual, Cout, stream);
 }

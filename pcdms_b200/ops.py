@@ -70,7 +70,7 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # K1/K2
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, bn=0):
+         out_f32=False, silu=False, gelu=False, bn=0):
     """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual)."""
     lib = _l.load()
     M, k1 = a.shape
@@ -85,7 +85,8 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     assert out.shape == (M, n_out) and out.stride(1) == 1
-    flags = (_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0)
+    flags = ((_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) |
+             (_l.FLAG_GELU if gelu else 0))
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
@@ -95,8 +96,10 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     return out
 
 
-def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, bn=0):
-    """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout]."""
+def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
+            pad_br=False, bn=0):
+    """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout].
+    pad_br (stride 2 only): zero padding on the bottom/right instead of all round (the VAE encoder's downsampler)."""
     lib = _l.load()
     B, Hin, Win, Cin = x.shape
     Cout = w_packed.shape[0]
@@ -107,7 +110,7 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
     assert out.is_contiguous() and tuple(out.shape) == (B, H, W, Cout)
     if residual is not None:
         assert residual.is_contiguous() and residual.shape == out.shape
-    flags = _l.FLAG_OUT_F32 if out_f32 else 0
+    flags = (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_PAD_BR if pad_br else 0)
     rc = lib.pcdm_conv3x3(_l.ptr(x), _l.ptr(w_packed), _l.ptr(out), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
                           C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
                           C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), _stream(x))
@@ -277,5 +280,55 @@ def ddim_step(model_output, sample, coefs, out=None):
     rc = lib.pcdm_ddim_step(_l.ptr(model_output), C.c_int(_any_dt(model_output)), _l.ptr(sample), _l.ptr(out),
                             C.c_int(_any_dt(sample)), C.c_float(coefs[0]), C.c_float(coefs[1]), C.c_float(coefs[2]),
                             C.c_float(coefs[3]), C.c_longlong(sample.numel()), _stream(sample))
+    _l.check(rc)
+    return out
+
+
+UNIPC_ROW = 16  # floats per step in the UniPC coefficient table (include/pcdm_b200.h)
+
+
+def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+    """eps_rows: [2n, H, W, ld] UNet output rows; state: [4, n, 4, H, W] fp32 {sample, last_sample, m0, m1} (in
+    place); x9: [2n, H, W, ld9]; coef_table: [steps, 16] fp32 device."""
+    lib = _l.load()
+    n = state.shape[1]
+    HW = state.shape[3] * state.shape[4]
+    assert state.dtype == torch.float32 and state.is_contiguous() and state.shape[0] == 4 and eps_rows.is_contiguous()
+    assert coef_table.dtype == torch.float32 and coef_table.shape[-1] == UNIPC_ROW and coef_table.is_contiguous()
+    assert step_counter.dtype == torch.int32 and step_counter.numel() == 2
+    rc = lib.pcdm_cfg_unipc_step(_l.ptr(eps_rows), C.c_int(_any_dt(eps_rows)), C.c_longlong(eps_rows.shape[-1]),
+                                 _l.ptr(state), _l.ptr(x9), C.c_int(_any_dt(x9)), C.c_longlong(x9.shape[-1]),
+                                 _l.ptr(coef_table), _l.ptr(step_counter), C.c_float(guidance_scale), C.c_int(n),
+                                 C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _stream(state))
+    _l.check(rc)
+
+
+def unipc_step(model_output, sample, last_sample, m0, m1, coef_row, out=None):
+    """One UniPCMultistepScheduler.step on same-shape tensors; last_sample/m0/m1: fp32 history (updated in place);
+    coef_row: 16 python floats."""
+    lib = _l.load()
+    assert model_output.is_contiguous() and sample.is_contiguous() and model_output.shape == sample.shape
+    for t in (last_sample, m0, m1):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == sample.numel()
+    if out is None:
+        out = torch.empty_like(sample)
+    row = (C.c_float * UNIPC_ROW)(*[float(v) for v in coef_row])
+    rc = lib.pcdm_unipc_step(_l.ptr(model_output), C.c_int(_any_dt(model_output)), _l.ptr(sample), _l.ptr(out),
+                             C.c_int(_any_dt(sample)), _l.ptr(last_sample), _l.ptr(m0), _l.ptr(m1), row,
+                             C.c_longlong(sample.numel()), _stream(sample))
+    _l.check(rc)
+    return out
+
+
+def softmax_rows(x, scale, dtype, out=None):
+    """x: [M, N] fp32 scores (unit column stride) -> softmax(scale * x) rows as `dtype` (fp16 / bf16)."""
+    lib = _l.load()
+    M, N = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=dtype)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    rc = lib.pcdm_softmax_rows(_l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(out), C.c_longlong(out.stride(0)),
+                               C.c_int(M), C.c_int(N), C.c_float(scale), C.c_int(_dt(out)), _stream(x))
     _l.check(rc)
     return out

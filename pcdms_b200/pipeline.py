@@ -21,7 +21,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .scheduler import B200DDIMScheduler
+from .scheduler import B200DDIMScheduler, B200UniPCMultistepScheduler
 from .unet import B200AttnProcessor, B200UNet2DConditionModel
 
 
@@ -142,7 +142,8 @@ class B200Stage2InpaintPipeline:
                                   device=generator.device if generator is not None else dev, dtype=torch.float32)
         latents = latents.to(device=dev, dtype=torch.float32) * self.scheduler.init_noise_sigma
 
-        fast = (isinstance(self.unet, B200UNet2DConditionModel) and isinstance(self.scheduler, B200DDIMScheduler)
+        fast = (isinstance(self.unet, B200UNet2DConditionModel)
+                and isinstance(self.scheduler, (B200DDIMScheduler, B200UniPCMultistepScheduler))
                 and eta == 0.0 and callback is None
                 and all(isinstance(a.processor, B200AttnProcessor) for a in self.unet._attn.values()))
         if fast:
@@ -187,13 +188,17 @@ class B200Stage2InpaintPipeline:
         dev, dt = unet.device, unet.dtype
         n, _, h, w = latents.shape
         B = 2 * n
-        key = (n, h, w, feature_f.shape[1], dt)
+        unipc = isinstance(sch, B200UniPCMultistepScheduler)
+        key = (n, h, w, feature_f.shape[1], dt, unipc)
         st = self._graphs.get(key)
         if st is None:
+            # UniPC keeps {sample, last_sample, model_outputs[-1], model_outputs[-2]} as four fp32 planes
+            state = torch.zeros((4 if unipc else 1, n, 4, h, w), device=dev, dtype=torch.float32)
             st = SimpleNamespace(
                 x9=torch.zeros((B, h, w, 64), device=dev, dtype=dt),
                 x9_init=torch.zeros((B, h, w, 64), device=dev, dtype=dt),
-                latents=torch.empty((n, 4, h, w), device=dev, dtype=torch.float32),
+                state=state, unipc=unipc,
+                latents=state[0],
                 latents_init=torch.empty((n, 4, h, w), device=dev, dtype=torch.float32),
                 pose=torch.empty((B, h, w, pose_cond.shape[1]), device=dev, dtype=dt),
                 cls=torch.empty((B, prior_embed.shape[-1]), device=dev, dtype=dt),
@@ -239,10 +244,15 @@ class B200Stage2InpaintPipeline:
 
     def _one_step(self, st):
         eps_rows = self.unet.forward_nhwc(st.x9, st.t_cur, st.kv, st.cls, st.pose)
-        ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
+        if st.unipc:
+            ops.cfg_unipc_step(eps_rows, st.state, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
+        else:
+            ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
 
     def _reset_state(self, st):
         st.x9.copy_(st.x9_init)
+        if st.unipc:
+            st.state[1:].zero_()
         st.latents.copy_(st.latents_init)
         st.counter.zero_()
         st.t_cur.copy_(st.t_table[:1])

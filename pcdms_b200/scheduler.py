@@ -126,6 +126,198 @@ class B200DDPMScheduler:
         return _add_noise(self.alphas_cumprod, original_samples, noise, timesteps)
 
 
+class B200UniPCMultistepScheduler:
+    """diffusers `UniPCMultistepScheduler` surface (the scheduler the reference's batch-test drivers install:
+    /root/reference/stage2_batchtest_inpaint_model.py:132; protocol use at
+    /root/reference/src/pipelines/stage2_inpaint_pipeline.py:472,500,519): predict_x0, bh1/bh2, solver_order <= 2,
+    epsilon prediction, corrector on every step but the first.
+
+    The host only derives the per-step scalars of the multistep update from the noise schedule (fp32 torch scalar
+    arithmetic in the published order: sigma -> (alpha_t, sigma_t) -> lambda -> h, rk, h_phi_1, B_h, rho);
+    `coefficient_table` lays them out as 16 floats per step for `pcdm_cfg_unipc_step` (fused, graph-replayable) and
+    `step` feeds one row to `pcdm_unipc_step`.  Sample history (last_sample, two converted model outputs) lives in
+    fp32 device buffers."""
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 trained_betas=None, solver_order=2, prediction_type="epsilon", thresholding=False,
+                 dynamic_thresholding_ratio=0.995, sample_max_value=1.0, predict_x0=True, solver_type="bh2",
+                 lower_order_final=True, disable_corrector=(), solver_p=None, use_karras_sigmas=False,
+                 timestep_spacing="linspace", steps_offset=0):
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"B200UniPCMultistepScheduler: {what}")
+        need(trained_betas is None and solver_p is None and not use_karras_sigmas and not thresholding,
+             "trained_betas / solver_p / karras sigmas / thresholding are not on the reference path")
+        need(prediction_type == "epsilon" and predict_x0, "epsilon prediction with predict_x0 only")
+        need(solver_type in ("bh1", "bh2") and solver_order in (1, 2), "solver bh1/bh2 with solver_order <= 2")
+        need(timestep_spacing in ("linspace", "leading", "trailing"), f"timestep_spacing {timestep_spacing}")
+        self.config = _AttrDict(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                                beta_schedule=beta_schedule, solver_order=solver_order,
+                                prediction_type=prediction_type, thresholding=thresholding, predict_x0=predict_x0,
+                                solver_type=solver_type, lower_order_final=lower_order_final,
+                                disable_corrector=list(disable_corrector), use_karras_sigmas=use_karras_sigmas,
+                                timestep_spacing=timestep_spacing, steps_offset=steps_offset)
+        self.alphas_cumprod = _alphas_cumprod(num_train_timesteps, beta_start, beta_end, beta_schedule)
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps,
+                                                      dtype=np.float32)[::-1].copy())
+        self.sigmas = None
+        self._step_index = None
+        self._hist = None
+        self._rows = None
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        """`UniPCMultistepScheduler.from_config(pipe.scheduler.config)`: keys of another scheduler's config that this
+        one does not know (skip_prk_steps, set_alpha_to_one, clip_sample, ...) are ignored, as diffusers does."""
+        import inspect
+        known = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        d = {k: v for k, v in dict(config).items() if k in known}
+        d.update(kw)
+        return cls(**d)
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        c = self.config
+        T = c.num_train_timesteps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            ratio = T // (num_inference_steps + 1)
+            ts = (np.arange(0, num_inference_steps + 1) * ratio).round()[::-1][:-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        else:
+            ts = np.arange(T, 0, -T / num_inference_steps).round().copy().astype(np.int64) - 1
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        sig_last = ((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [sig_last]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts).to(device=device, dtype=torch.int64)
+        self.num_inference_steps = len(ts)
+        self._step_index = None
+        self._hist = None
+        self._rows = None
+
+    def scale_model_input(self, sample, *a, **k):
+        return sample
+
+    # -- schedule-only scalars ------------------------------------------------------------------------------------
+    @staticmethod
+    def _alpha_sigma(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def _lambda(self, i):
+        a, s = self._alpha_sigma(self.sigmas[i])
+        return torch.log(a) - torch.log(s)
+
+    def _update_scalars(self, i_t, i_s0, i_s1, order, corrector):
+        """(sigma_t/sigma_s0, alpha_t h_phi_1, alpha_t B_h, rk, rho_0, rho_last) of one bh update from sigma index
+        i_s0 to i_t; i_s1 is the index of the older model output (order 2)."""
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i_t])
+        _, sigma_s0 = self._alpha_sigma(self.sigmas[i_s0])
+        lam_s0 = self._lambda(i_s0)
+        h = self._lambda(i_t) - lam_s0
+        rks = []
+        if order == 2:
+            rks.append((self._lambda(i_s1) - lam_s0) / h)
+        rks.append(1.0)
+        rks_t = torch.tensor(rks)
+        hh = -h
+        h_phi_1 = torch.expm1(hh)
+        h_phi_k = h_phi_1 / hh - 1
+        fact = 1
+        B_h = hh if self.config.solver_type == "bh1" else torch.expm1(hh)
+        R, b = [], []
+        for k in range(1, order + 1):
+            R.append(torch.pow(rks_t, k - 1))
+            b.append(h_phi_k * fact / B_h)
+            fact *= k + 1
+            h_phi_k = h_phi_k / hh - 1 / fact
+        if corrector:
+            rhos = torch.tensor([0.5]) if order == 1 else torch.linalg.solve(torch.stack(R), torch.tensor(b))
+        else:
+            rhos = torch.tensor([0.5])   # order-2 predictor: the simplified rho = 1/2; unused at order 1
+        rk = float(rks[0]) if order == 2 else 1.0
+        rho0 = float(rhos[0]) if (order == 2) else 0.0
+        return (float(sigma_t / sigma_s0), float(alpha_t * h_phi_1), float(alpha_t * B_h), rk, rho0, float(rhos[-1]))
+
+    def _orders(self):
+        N, so = self.num_inference_steps, self.config.solver_order
+        out = []
+        for i in range(N):
+            o = min(so, N - i) if self.config.lower_order_final else so
+            out.append(min(o, min(i, so) + 1))
+        return out
+
+    def coefficient_rows(self):
+        """[steps][16] python floats (layout: include/pcdm_b200.h, pcdm_cfg_unipc_step)."""
+        if self._rows is not None:
+            return self._rows
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps() first")
+        orders = self._orders()
+        rows = []
+        for i in range(self.num_inference_steps):
+            alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i])
+            row = [float(sigma_t), float(alpha_t)]
+            use_c = i > 0 and (i - 1) not in self.config.disable_corrector
+            if use_c:
+                oc = orders[i - 1]
+                a, bq, cq, rk, rho0, rho_last = self._update_scalars(i, i - 1, i - 2, oc, corrector=True)
+                row += [1.0, a, bq, cq, rk, rho0, rho_last, float(oc)]
+            else:
+                row += [0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0]
+            op = orders[i]
+            a, bq, cq, rk, _, rho = self._update_scalars(i + 1, i, i - 1, op, corrector=False)
+            row += [a, bq, cq, rk, rho, float(op)]
+            rows.append(row)
+        self._rows = rows
+        return rows
+
+    def coefficient_table(self, device):
+        return torch.tensor(self.coefficient_rows(), dtype=torch.float32, device=device).contiguous()
+
+    # -- scheduler protocol ---------------------------------------------------------------------------------------
+    def _init_step_index(self, timestep):
+        t = int(timestep)
+        idx = (self.timesteps.cpu() == t).nonzero()
+        if len(idx) == 0:
+            self._step_index = len(self.timesteps) - 1
+        elif len(idx) > 1:
+            self._step_index = int(idx[1])
+        else:
+            self._step_index = int(idx[0])
+
+    def step(self, model_output, timestep, sample, return_dict: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' first")
+        if not sample.is_cuda:
+            raise RuntimeError("B200UniPCMultistepScheduler.step runs on CUDA tensors only (no CPU fallback)")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        if self._hist is None or self._hist.shape[1] != sample.numel() or self._hist.device != sample.device:
+            self._hist = torch.zeros((3, sample.numel()), dtype=torch.float32, device=sample.device)
+        row = self.coefficient_rows()[self._step_index]
+        prev = ops.unipc_step(model_output.contiguous(), sample.contiguous(), self._hist[0], self._hist[1],
+                              self._hist[2], row)
+        self._step_index += 1
+        if not return_dict:
+            return (prev,)
+        return SimpleNamespace(prev_sample=prev)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        return _add_noise(self.alphas_cumprod, original_samples, noise, timesteps)
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
 _ac_cache = {}
 
 

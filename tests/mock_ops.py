@@ -18,7 +18,7 @@ def _rt(x, dtype):
 
 
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, bn=0):
+         out_f32=False, silu=False, gelu=False, bn=0):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
     if geglu:
@@ -34,6 +34,8 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
             y = y + residual.float()
         if silu:
             y = F.silu(y)
+        if gelu:
+            y = F.gelu(y)
     y = y if out_f32 else _rt(y, a.dtype)
     if out is not None:
         out.copy_(y)
@@ -41,15 +43,23 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     return y
 
 
-def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, bn=0):
+def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
+            pad_br=False, bn=0):
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     w = w_packed.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad_br:
+        assert stride == 2
+        y = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w, bias, stride=2, padding=0).permute(0, 2, 3, 1)
+    else:
+        y = F.conv2d(xin, w, bias, stride=stride, padding=1).permute(0, 2, 3, 1)
     if rowvec is not None:
         y = y + rowvec[:, None, None, :]
     if residual is not None:
         y = y + residual.float()
+    if silu:
+        y = F.silu(y)
     y = y.contiguous()
     return y if out_f32 else _rt(y, x.dtype)
 
@@ -125,12 +135,60 @@ def ddim_step(model_output, sample, coefs, out=None):
     return (coefs[2] * x0 + coefs[3] * model_output.float()).to(sample.dtype)
 
 
+def _unipc_update(r, e, x, last, ma, mb):
+    """include/pcdm_b200.h, pcdm_cfg_unipc_step: one UniPC step on fp32 tensors, the reference's operation order."""
+    r = [torch.tensor(v, dtype=torch.float32) for v in r]
+    mt = (x - r[0] * e) / r[1]
+    xc = x
+    if float(r[2]) != 0.0:
+        xt_ = r[3] * last - r[4] * ma
+        corr = r[8] * (mt - ma)
+        if float(r[9]) >= 2:
+            corr = r[7] * ((mb - ma) / r[6]) + corr
+        xc = xt_ - r[5] * corr
+    xn = r[10] * xc - r[11] * mt
+    if float(r[15]) >= 2:
+        xn = xn - r[12] * (r[14] * ((ma - mt) / r[13]))
+    return xn, xc, mt, ma
+
+
+def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+    n = state.shape[1]
+    step = int(step_counter[0])
+    e = eps_rows[..., :4].float().permute(0, 3, 1, 2)
+    e = e[:n] + guidance_scale * (e[n:] - e[:n])
+    xn, xc, mt, ma_old = _unipc_update(coef_table[step].tolist(), e, state[0], state[1], state[2], state[3])
+    state[3].copy_(ma_old)
+    state[2].copy_(mt)
+    state[1].copy_(xc)
+    state[0].copy_(xn)
+    x9[..., :4] = torch.cat([state[0], state[0]]).permute(0, 2, 3, 1).to(x9.dtype)
+    step_counter[0] = step + 1
+    if t_table is not None and t_cur is not None:
+        t_cur[0] = t_table[step + 1]
+
+
+def unipc_step(model_output, sample, last_sample, m0, m1, coef_row, out=None):
+    shp = sample.shape
+    xn, xc, mt, ma_old = _unipc_update(coef_row, model_output.float().reshape(-1), sample.float().reshape(-1),
+                                       last_sample, m0, m1)
+    m1.copy_(ma_old)
+    m0.copy_(mt)
+    last_sample.copy_(xc)
+    return xn.reshape(shp).to(sample.dtype)
+
+
+def softmax_rows(x, scale, dtype, out=None):
+    return torch.softmax(x.float() * scale, dim=-1).to(dtype)
+
+
 def ensure_workspace(device, nbytes=0):
     return None
 
 
 _NAMES = ["ensure_workspace", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
-          "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step"]
+          "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step", "cfg_unipc_step",
+          "unipc_step", "softmax_rows"]
 
 
 @contextlib.contextmanager

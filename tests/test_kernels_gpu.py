@@ -241,3 +241,51 @@ def test_fused_step_and_schedulers_match_oracle(ops):
     ts = torch.tensor([0, 500])
     out = B200DDPMScheduler().add_noise(s.cuda(), e.cuda(), ts.cuda())
     torch.testing.assert_close(out.cpu(), ddpm_add_noise(s, e, ts), rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VAE / conditioning front-end shapes: rows wider than a tile, bottom/right-padded stride 2,
+# SiLU / GELU epilogues, fp32 score softmax
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,pad_br", [
+    (1, 8, 256, 64, 64, 1, False), (2, 6, 512, 128, 128, 1, False), (1, 3, 384, 64, 32, 1, False),
+    (2, 4, 256, 64, 128, 2, False), (2, 16, 32, 128, 128, 2, True), (1, 4, 128, 64, 64, 2, True),
+    (2, 5, 256, 64, 64, 2, True),
+])
+def test_conv3x3_wide_and_asymmetric(ops, dt, B, H, W, Cin, Cout, stride, pad_br):
+    g = torch.Generator().manual_seed(B * H + W + Cin)
+    x = torch.randn(B, Cin, H * stride, W * stride, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dt)
+    b = torch.randn(Cout, generator=g)
+    if pad_br:
+        ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), b, stride=2, padding=0)
+    else:
+        ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1)
+    r = torch.randn(B, Cout, H, W, generator=g).to(dt)
+    ref = F.silu(ref + r.float())
+    out = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_conv3x3_weight(w, dt).cuda(), bias=b.cuda(),
+                      residual=r.permute(0, 2, 3, 1).contiguous().cuda(), stride=stride, pad_br=pad_br, silu=True)
+    close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_gemm_gelu_epilogue(ops, dt):
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(514, 1536, generator=g).to(dt)
+    w = (torch.randn(768, 1536, generator=g) / 1536 ** 0.5).to(dt)
+    b = torch.randn(768, generator=g)
+    ref = F.gelu(a.float() @ w.float().t() + b)
+    close(ops.gemm(a.cuda(), w.cuda(), bias=b.cuda(), gelu=True), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N", [(64, 2048), (300, 8192), (5, 36), (17, 16384)])
+def test_softmax_rows(ops, dt, M, N):
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, N, generator=g) * 30.0
+    scale = 512 ** -0.5
+    got = ops.softmax_rows(x.cuda(), scale, dt)
+    want = torch.softmax(x * scale, dim=-1)
+    torch.testing.assert_close(got.float().cpu(), want, rtol=(2 ** -7 if dt == torch.bfloat16 else 2 ** -10), atol=1e-6)
+    assert torch.equal(got, ops.softmax_rows(x.cuda(), scale, dt))
