@@ -161,6 +161,13 @@ int pcdm_unipc_step(const void* model_output, int eps_dtype, const void* sample,
 int pcdm_softmax_rows(const float* x, long long ldx, void* y, long long ldy, int M, int N, float scale, int dtype,
                       void* stream);
 
+/* DiagonalGaussianDistribution.sample() / .mode() of diffusers AutoencoderKL.encode (stage2_inpaint_pipeline.py:443,
+ * stage3_refined_pipeline.py:479): z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale.
+ * moments: [B, HW, ld] fp32 rows (channels [0, C) mean, [C, 2C) logvar); noise: [B, C, HW] fp32 or NULL (mode);
+ * out: [B, C, HW] fp32. */
+int pcdm_gaussian_sample(const float* moments, long long ld, const float* noise, float* out, int B, int C, int HW,
+                         float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -357,6 +357,30 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
   }
 }
 
+// DiagonalGaussianDistribution.sample() of diffusers AutoencoderKL (stage2_inpaint_pipeline.py:443):
+//   z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale
+// moments: [B, HW, ld] fp32 rows out of the quant_conv GEMM (channels [0, C) mean, [C, 2C) logvar);
+// noise: [B, C, HW] fp32 or NULL (= mode()); out: [B, C, HW] fp32.
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, long long ld, const float* __restrict__ noise,
+                                       float* __restrict__ out, int B, int C, int HW, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long bc = i / HW;
+    const int c = (int)(bc % C);
+    const int b = (int)(bc / C);
+    const float* row = moments + ((long long)b * HW + p) * ld;
+    float v = row[c];
+    if (noise) {
+      const float lv = fminf(fmaxf(row[C + c], -30.f), 20.f);
+      v = __fadd_rn(v, __fmul_rn(expf(0.5f * lv), noise[i]));
+    }
+    out[i] = v * scale;
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -487,6 +511,16 @@ extern "C" int pcdm_softmax_rows(const float* x, long long ldx, void* y, long lo
     PCDM_CUDA(launch_kernel(softmax_rows_kernel<DT_F16>, dim3(grid), dim3(SM_THREADS), 0, (cudaStream_t)stream_, 1, x, ldx, y, ldy, M, N, sl2));
   else
     PCDM_CUDA(launch_kernel(softmax_rows_kernel<DT_BF16>, dim3(grid), dim3(SM_THREADS), 0, (cudaStream_t)stream_, 1, x, ldx, y, ldy, M, N, sl2));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_gaussian_sample(const float* moments, long long ld, const float* noise, float* out, int B, int C,
+                                    int HW, float scale, void* stream_) {
+  if (!moments || !out) return set_error(PCDM_ERR_INVALID, "gaussian_sample: null pointer");
+  if (B <= 0 || C <= 0 || HW <= 0 || ld < 2 * C) return set_error(PCDM_ERR_INVALID, "gaussian_sample: bad shape");
+  const long long total = (long long)B * C * HW;
+  PCDM_CUDA(launch_kernel(gaussian_sample_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, moments, ld, noise, out, B, C, HW, scale));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -332,3 +332,18 @@ def softmax_rows(x, scale, dtype, out=None):
                                C.c_int(M), C.c_int(N), C.c_float(scale), C.c_int(_dt(out)), _stream(x))
     _l.check(rc)
     return out
+
+
+def gaussian_sample(moments, B, channels, HW, noise=None, scale=1.0, out=None):
+    """moments: [B*HW, ld] fp32 rows (mean | logvar); noise: [B, channels, HW] fp32 or None (mode) -> [B, channels, HW]
+    fp32."""
+    lib = _l.load()
+    assert moments.dtype == torch.float32 and moments.stride(1) == 1 and moments.shape[0] == B * HW
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == B * channels * HW
+    if out is None:
+        out = torch.empty((B, channels, HW), device=moments.device, dtype=torch.float32)
+    rc = lib.pcdm_gaussian_sample(_l.ptr(moments), C.c_longlong(moments.stride(0)), _l.ptr(noise), _l.ptr(out),
+                                  C.c_int(B), C.c_int(channels), C.c_int(HW), C.c_float(scale), _stream(moments))
+    _l.check(rc)
+    return out

@@ -179,7 +179,19 @@ def unipc_step(model_output, sample, last_sample, m0, m1, coef_row, out=None):
 
 
 def softmax_rows(x, scale, dtype, out=None):
-    return torch.softmax(x.float() * scale, dim=-1).to(dtype)
+    y = torch.softmax(x.float() * scale, dim=-1).to(dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def gaussian_sample(moments, B, channels, HW, noise=None, scale=1.0, out=None):
+    m = moments.view(B, HW, -1).permute(0, 2, 1)
+    v = m[:, :channels]
+    if noise is not None:
+        v = v + torch.exp(0.5 * m[:, channels:2 * channels].clamp(-30.0, 20.0)) * noise.view(B, channels, HW)
+    return (v * scale).contiguous()
 
 
 def ensure_workspace(device, nbytes=0):
@@ -188,7 +200,7 @@ def ensure_workspace(device, nbytes=0):
 
 _NAMES = ["ensure_workspace", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
           "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step", "cfg_unipc_step",
-          "unipc_step", "softmax_rows"]
+          "unipc_step", "softmax_rows", "gaussian_sample"]
 
 
 @contextlib.contextmanager
