@@ -70,3 +70,43 @@ def denoise_loop(unet, scheduler, *, latents, cond, num_inference_steps, guidanc
         if return_trajectory:
             traj.append((eps.clone(), latents.clone()))
     return (latents, traj) if return_trajectory else latents
+
+
+@torch.no_grad()
+def denoise_loop_pcdms(unet, scheduler, *, latents, mask, simg_mask_latents, cond_pose, prompt_embeds,
+                       negative_prompt_embeds, num_inference_steps, guidance_scale=2.0, dtype=torch.float32):
+    """Demo driver loop, /root/reference/src/pipelines/PCDMs_pipeline.py:1062-1063 (CFG token batch = [negative ;
+    positive]) and :1107-1150: the 9-channel input is assembled BEFORE the CFG duplication (:1115-1117), there is no
+    class embedding, `cond_pose` ([1, C0, h, w]) broadcasts over the batch of 2 inside UNet.forward (:742)."""
+    scheduler.set_timesteps(num_inference_steps)
+    latents = latents.to(dtype)
+    feature_f = torch.cat([negative_prompt_embeds, prompt_embeds]).to(dtype)
+    for t in scheduler.timesteps:
+        x = torch.cat([latents, mask, simg_mask_latents], dim=1).to(dtype)                # :1115
+        x = torch.cat([x] * 2)                                                            # :1117
+        x = scheduler.scale_model_input(x, t)                                             # :1118
+        eps = unet(x, t, encoder_hidden_states=feature_f, my_pose_cond=cond_pose.to(dtype), return_dict=False)[0]
+        eps = cfg_combine(eps, guidance_scale)                                            # :1133-1135
+        latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :1142
+    return latents
+
+
+@torch.no_grad()
+def denoise_loop_stage3(unet, scheduler, *, latents, gen_t_img_latents, s_img_proj_f, num_inference_steps,
+                        guidance_scale=2.0, dtype=torch.float32):
+    """/root/reference/src/pipelines/stage3_refined_pipeline.py:484-491 (CFG halves: zero tokens AND zero image
+    latents for the unconditional one) and :530-556 (loop; 8-channel input `cat([latents x2, gen_t_img_f])`, :538).
+    Only defined for bs * num_images_per_prompt == 1, like the reference."""
+    assert latents.shape[0] == 1 and s_img_proj_f.shape[0] == 1
+    scheduler.set_timesteps(num_inference_steps)
+    feature_f = torch.cat([torch.zeros_like(s_img_proj_f), s_img_proj_f], dim=0).to(dtype)
+    g = torch.cat([torch.zeros_like(gen_t_img_latents), gen_t_img_latents], dim=0).to(dtype)
+    latents = latents.to(dtype)
+    for t in scheduler.timesteps:
+        x = torch.cat([latents] * 2)
+        x = scheduler.scale_model_input(x, t)
+        x8 = torch.cat([x, g], dim=1).to(dtype)                                           # :538
+        eps = unet(x8, t, encoder_hidden_states=feature_f, return_dict=False)[0]          # :541-543
+        eps = cfg_combine(eps, guidance_scale)
+        latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :556
+    return latents

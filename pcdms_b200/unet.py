@@ -583,10 +583,13 @@ class B200UNet2DConditionModel:
         x_in = ops.nchw_to_nhwc_pad(sample.contiguous(), 64, self._dtype)
         t_dev = self._timestep_tensor(timestep, B)
         pose = None
-        if self.use_pose_cond:
-            if my_pose_cond is None:
-                raise ValueError("my_pose_cond is required by the stage-2 UNet (reference :742)")
-            pose = self._pose_nhwc(my_pose_cond)
+        if my_pose_cond is not None:      # reference :742 adds it whenever it is passed; [1, ...] broadcasts over B
+            if my_pose_cond.shape[0] not in (1, B):
+                raise ValueError(f"my_pose_cond batch {my_pose_cond.shape[0]} does not match sample batch {B}")
+            pose = self._pose_nhwc(my_pose_cond.expand(B, *my_pose_cond.shape[1:]) if my_pose_cond.shape[0] != B
+                                   else my_pose_cond)
+        elif self.use_pose_cond:
+            raise ValueError("my_pose_cond is required by the stage-2 UNet (reference :742)")
         kv = self.context_kv(encoder_hidden_states)
         out_rows = self.forward_nhwc(x_in, t_dev, kv, class_labels, pose)
         out = ops.nhwc_to_nchw(out_rows, cfg.out_channels, sample.dtype)
