@@ -332,6 +332,38 @@ def run_b200(args):
     res_ms, _ = timed(lambda: pipe.replay_fused(state), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- extra (not the headline): image in -> image out, i.e. the same call with the B200 VAE on both ends ---------
+    # (vae.encode of the source|black canvas before the loop, vae.decode of the 8 results after it)
+    img_extra = None
+    if not args.no_image_extra:
+        from pcdms_b200.vae import B200AutoencoderKL
+        vae = B200AutoencoderKL(dtype=dt, device=dev)
+        vae.load_state_dict(vae.synthetic_state_dict(seed=1))
+        pipe_img = B200Stage2InpaintPipeline(vae=vae, unet=unet, scheduler=pipe.scheduler)
+        pipe_img._graphs = pipe._graphs          # same shapes: reuse the captured graph
+        canvas = (torch.rand((1, 3, LAT_H * 8, LAT_W * 8), generator=torch.Generator().manual_seed(7 + rank)) * 2 - 1
+                  ).pin_memory()
+        img_host = torch.empty((N_IMAGES, 3, LAT_H * 8, LAT_W * 8), dtype=dt).pin_memory()
+
+        def img_call():
+            out = pipe_img(height=LAT_H * 8, width=LAT_W * 8, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE,
+                           num_images_per_prompt=N_IMAGES, latents=hin["latents"], output_type="pt", vae_image=canvas,
+                           s_img_proj_f=hin["s_img_proj_f"], st_pose_f=hin["st_pose_f"],
+                           pred_t_img_embed=hin["pred_t_img_embed"]).images
+            img_host.copy_(out, non_blocking=True)
+
+        for _ in range(2):
+            img_call()
+        k = max(1, min(args.steps, 3))
+        img_ms, img_wall = timed(img_call, k)
+        img_extra = {"value": N_IMAGES * world * k / (max(img_ms, img_wall) * 1e-3), "unit": "images/s",
+                     "ms_per_step": max(img_ms, img_wall) / k, "steps": k,
+                     "h2d_bytes_per_step": h2d - hin["masked_latents"].numel() * 4 + canvas.numel() * 4,
+                     "d2h_bytes_per_step": img_host.numel() * img_host.element_size(),
+                     "what": "pinned host canvas image -> B200AutoencoderKL.encode -> 50 graph replays -> "
+                             "B200AutoencoderKL.decode of 8 images -> D2H of [8,3,256,512] (random-init SD VAE, "
+                             "83.65 M params)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -399,7 +431,7 @@ def run_b200(args):
         "gpu_launches_detail": {"kernels_per_unet_step_graph": launches_per_unet_step,
                                 "graph_replays_per_step": DDIM_STEPS, "setup_kernels_per_call": setup_launches,
                                 "timed_regions": 2},
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "image_in_image_out": img_extra,
         "weights_broadcast_ms": bcast_ms, "model_build_s": load_s,
     }
     print(json.dumps(line), flush=True)
@@ -414,6 +446,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-image-extra", action="store_true", help="skip the extra image-in/image-out (VAE) timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,3 +9,6 @@ class VaeImageProcessor:
         if output_type in ("latent", "pt"):
             return image
         raise NotImplementedError("shim: use output_type='pt' (PIL conversion is outside the hot path)")
+
+
+PipelineImageInput = object

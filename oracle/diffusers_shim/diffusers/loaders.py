@@ -7,3 +7,15 @@ class UNet2DConditionLoadersMixin:
 
 class LoraLoaderMixin:
     pass
+
+
+class TextualInversionLoaderMixin:
+    pass
+
+
+class IPAdapterMixin:
+    pass
+
+
+class FromSingleFileMixin:
+    pass

@@ -14,6 +14,20 @@ class DiffusionPipeline:
         for k, v in kwargs.items():
             setattr(self, k, v)
 
+    def register_to_config(self, **kwargs):
+        from types import SimpleNamespace
+        cfg = dict(getattr(self, "_config", {}))
+        cfg.update(kwargs)
+        self._config = cfg
+        self.config = SimpleNamespace(**cfg)
+
+    @property
+    def _execution_device(self):
+        return self.device
+
+    def maybe_free_model_hooks(self):
+        return None
+
     @property
     def device(self):
         unet = getattr(self, "unet", None)

@@ -1,5 +1,6 @@
 """Shim of diffusers.schedulers: DDIM from the oracle; the other names exist only so the imports resolve."""
 from oracle.schedulers import OracleDDIMScheduler as DDIMScheduler  # noqa: F401
+from oracle.unipc import UniPCMultistepScheduler  # noqa: F401
 
 
 class KarrasDiffusionSchedulers:

@@ -37,3 +37,18 @@ def is_accelerate_available():
 
 def is_accelerate_version(*args, **kwargs):
     return False
+
+
+USE_PEFT_BACKEND = False
+
+
+def replace_example_docstring(doc):
+    return lambda fn: fn
+
+
+def scale_lora_layers(*args, **kwargs):
+    return None
+
+
+def unscale_lora_layers(*args, **kwargs):
+    return None

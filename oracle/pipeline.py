@@ -93,20 +93,24 @@ def denoise_loop_pcdms(unet, scheduler, *, latents, mask, simg_mask_latents, con
 
 @torch.no_grad()
 def denoise_loop_stage3(unet, scheduler, *, latents, gen_t_img_latents, s_img_proj_f, num_inference_steps,
-                        guidance_scale=2.0, dtype=torch.float32):
+                        guidance_scale=2.0, dtype=torch.float32, unet_dtype=torch.float32):
     """/root/reference/src/pipelines/stage3_refined_pipeline.py:484-491 (CFG halves: zero tokens AND zero image
     latents for the unconditional one) and :530-556 (loop; 8-channel input `cat([latents x2, gen_t_img_f])`, :538).
-    Only defined for bs * num_images_per_prompt == 1, like the reference."""
+    Only defined for bs * num_images_per_prompt == 1, like the reference.  `dtype` is the type of the conditioning and
+    of the initial latents (fp16 in the reference, :487-491,:519); the UNet input and tokens are cast to `unet_dtype`
+    (fp32 in the reference, :538,:542), so after the first scheduler step the latents live in the promoted type."""
     assert latents.shape[0] == 1 and s_img_proj_f.shape[0] == 1
     scheduler.set_timesteps(num_inference_steps)
-    feature_f = torch.cat([torch.zeros_like(s_img_proj_f), s_img_proj_f], dim=0).to(dtype)
-    g = torch.cat([torch.zeros_like(gen_t_img_latents), gen_t_img_latents], dim=0).to(dtype)
+    # :487-488 — the tokens keep the caller's dtype (the fp16 zeros are promoted by the cat)
+    feature_f = torch.cat([torch.zeros(s_img_proj_f.shape, dtype=dtype), s_img_proj_f], dim=0)
+    g = gen_t_img_latents.to(dtype)                                                       # vae.encode(x.half()), :479
+    g = torch.cat([torch.zeros(g.shape, dtype=dtype), g], dim=0)                          # :490-491
     latents = latents.to(dtype)
     for t in scheduler.timesteps:
         x = torch.cat([latents] * 2)
         x = scheduler.scale_model_input(x, t)
-        x8 = torch.cat([x, g], dim=1).to(dtype)                                           # :538
-        eps = unet(x8, t, encoder_hidden_states=feature_f, return_dict=False)[0]          # :541-543
+        x8 = torch.cat([x, g], dim=1).to(unet_dtype)                                      # :538
+        eps = unet(x8, t, encoder_hidden_states=feature_f.to(unet_dtype), return_dict=False)[0]   # :541-543
         eps = cfg_combine(eps, guidance_scale)
         latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :556
     return latents

@@ -80,3 +80,97 @@ def run_reference_pipeline(cfg, state_dict, pin, *, num_inference_steps, guidanc
                s_img_proj_f=pin["s_img_proj_f"], st_pose_f=pin["st_pose_f"],
                pred_t_img_embed=pin["pred_t_img_embed"])
     return out.images  # = final latents through the identity decoder (scaling_factor 1.0)
+
+
+class _EncodeVAE:
+    """Identity-scaled stand-in whose encode() returns given latents (sample ignores the generator) and whose decode()
+    is the identity: exposes the loop of a pipeline without the VAE."""
+
+    def __init__(self, latents):
+        self.config = SimpleNamespace(block_out_channels=(1, 2, 3, 4), scaling_factor=1.0)
+        self._lat = latents
+
+    def encode(self, x):
+        lat = self._lat.to(x.dtype)
+        return SimpleNamespace(latent_dist=SimpleNamespace(sample=lambda generator=None: lat))
+
+    def decode(self, z, return_dict=False, generator=None):
+        return (z,)
+
+
+class _Stage3UNetAdapter(torch.nn.Module):
+    """The stock diffusers UNet2DConditionModel call surface the stage-3 pipeline uses
+    (stage3_refined_pipeline.py:541-543) over the oracle UNet with the stage-3 config."""
+
+    def __init__(self, unet, cfg):
+        super().__init__()
+        self.unet = unet
+        self.config = SimpleNamespace(**asdict(cfg))
+
+    @property
+    def device(self):
+        return torch.device("cpu")
+
+    def forward(self, sample, timestep, encoder_hidden_states=None, cross_attention_kwargs=None, return_dict=True):
+        assert cross_attention_kwargs is None and not return_dict
+        return self.unet(sample, timestep, encoder_hidden_states)
+
+
+def run_reference_stage3_pipeline(cfg, oracle_unet, *, latents, gen_t_img_latents, s_img_proj_f, num_inference_steps,
+                                  guidance_scale, scheduler):
+    """Run Stage3_RefinedPipeline.__call__ (stage3_refined_pipeline.py:443-578) unmodified on CPU: fp16 latents and
+    conditioning, fp32 UNet evaluation (:538-542), identity VAE.  Returns the final latents."""
+    _enable()
+    from src.pipelines.stage3_refined_pipeline import Stage3_RefinedPipeline
+
+    pipe = Stage3_RefinedPipeline(vae=_EncodeVAE(gen_t_img_latents), unet=_Stage3UNetAdapter(oracle_unet, cfg),
+                                  scheduler=scheduler)
+    h, w = latents.shape[-2:]
+    out = pipe(height=h * 8, width=w * 8, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+               num_images_per_prompt=1, latents=latents.half(), output_type="pt",
+               vae_gen_t_image=torch.zeros(1, 3, h * 8, w * 8), s_img_proj_f=s_img_proj_f)
+    return out.images
+
+
+class _DemoUNetAdapter(torch.nn.Module):
+    """The call surface PCDMsPipeline uses on its UNet (PCDMs_pipeline.py:1121-1130; `config.time_cond_proj_dim`
+    :1100, `encoder_hid_proj` :1067) over the oracle UNet (9 input channels, no class embedding, pose add)."""
+
+    def __init__(self, unet, cfg):
+        super().__init__()
+        self.unet = unet
+        self.config = SimpleNamespace(**asdict(cfg))
+        self.encoder_hid_proj = None
+
+    @property
+    def device(self):
+        return torch.device("cpu")
+
+    @property
+    def dtype(self):
+        return next(self.unet.parameters()).dtype
+
+    def forward(self, sample, timestep, encoder_hidden_states=None, my_pose_cond=None, timestep_cond=None,
+                cross_attention_kwargs=None, added_cond_kwargs=None, return_dict=True):
+        assert timestep_cond is None and cross_attention_kwargs is None and added_cond_kwargs is None
+        return self.unet(sample, timestep, encoder_hidden_states, my_pose_cond=my_pose_cond)
+
+
+def run_reference_demo_pipeline(cfg, oracle_unet_half, *, latents, mask, simg_mask_latents, cond_pose, prompt_embeds,
+                                negative_prompt_embeds, num_inference_steps, guidance_scale):
+    """Run PCDMsPipeline.__call__ (PCDMs_pipeline.py:889-1180, the pcdms_demo.ipynb driver) unmodified on CPU.  The
+    reference hard-codes fp16 for the UNet input (:1115), so the UNet and the conditioning are fp16 here.  Returns the
+    final latents (identity VAE)."""
+    _enable()
+    from diffusers.schedulers import DDIMScheduler
+    from src.pipelines.PCDMs_pipeline import PCDMsPipeline
+
+    pipe = PCDMsPipeline(vae=_EncodeVAE(latents), text_encoder=None, tokenizer=None,
+                         unet=_DemoUNetAdapter(oracle_unet_half, cfg), scheduler=DDIMScheduler(), safety_checker=None,
+                         feature_extractor=None, requires_safety_checker=False)
+    h, w = latents.shape[-2:]
+    out = pipe(simg_mask_latents=simg_mask_latents, mask=mask, cond_pose=cond_pose.half(),
+               prompt_embeds=prompt_embeds.half(), negative_prompt_embeds=negative_prompt_embeds.half(),
+               height=h * 8, width=w * 8, num_images_per_prompt=1, guidance_scale=guidance_scale,
+               latents=latents.half(), num_inference_steps=num_inference_steps, output_type="pt")
+    return out.images

@@ -86,3 +86,15 @@ def test_frontend_gpu_real_sizes(dt, tol):
     for got, want in ((got1, want1), (got2, want2)):
         err = (got.float().cpu() - want).abs().max() / want.abs().max()
         assert float(err) < tol, float(err)
+
+
+@pytest.mark.gpu
+def test_image_proj_against_reference_golden_gpu():
+    """tests/golden/ref_image_proj.pt holds the output of the reference's own ImageProjModel_p class."""
+    from pathlib import Path
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "ref_image_proj.pt")
+    p = B200ImageProjModel_p(128, 64, 96, dtype=torch.float16)
+    p.load_state_dict(g["state_dict"])
+    got = p(g["x"].cuda())
+    err = (got.float().cpu() - g["y"]).abs().max() / g["y"].abs().max()
+    assert float(err) < 4e-3

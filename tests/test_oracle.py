@@ -174,3 +174,28 @@ def test_oracle_matches_reference_pipeline_golden():
                        guidance_scale=g["guidance_scale"], dtype=torch.float16)
     assert lat.dtype == torch.float16
     assert torch.equal(lat, g["latents"])
+
+
+def test_oracle_matches_reference_stage3_and_demo_goldens():
+    """tests/golden/ref_stage3_tiny.pt / ref_demo_tiny.pt were produced by the reference's own Stage3_RefinedPipeline
+    and PCDMsPipeline `__call__` (tools/make_golden.py); the oracle loops must reproduce them bit for bit."""
+    from dataclasses import replace
+    from oracle.pipeline import denoise_loop_pcdms, denoise_loop_stage3
+    g = torch.load(GOLD / "ref_stage3_tiny.pt")
+    u3 = make_unet(UNetConfig.tiny(in_channels=8, stage2=False), seed=g["seed"])
+    got = denoise_loop_stage3(u3, OracleDDIMScheduler(), dtype=torch.float16, unet_dtype=torch.float32, **g["inputs"])
+    assert torch.equal(got.float(), g["latents"].float())
+    g = torch.load(GOLD / "ref_demo_tiny.pt")
+    ud = make_unet(replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True), seed=g["seed"]).half()
+    got = denoise_loop_pcdms(ud, OracleDDIMScheduler(), dtype=torch.float16, **g["inputs"])
+    assert torch.equal(got, g["latents"])
+
+
+def test_oracle_image_proj_matches_reference_golden():
+    """tests/golden/ref_image_proj.pt: state dict, input and output of the reference's own ImageProjModel_p."""
+    from oracle.frontend import ImageProjModel_p
+    g = torch.load(GOLD / "ref_image_proj.pt")
+    m = ImageProjModel_p(128, 64, 96).eval()
+    m.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        assert torch.equal(m(g["x"]), g["y"])

@@ -48,3 +48,46 @@ def test_reference_pipeline_equals_oracle_loop():
     got = denoise_loop(oracle.half(), OracleDDIMScheduler(), latents=pin["latents"], cond=cond,
                        num_inference_steps=3, guidance_scale=2.0, dtype=torch.float16)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("sched", ["ddim", "unipc"])
+def test_reference_stage3_pipeline_equals_oracle_loop(sched):
+    """The reference's own Stage3_RefinedPipeline.__call__ (fp16 loop tensors, fp32 UNet evaluation) against
+    oracle.pipeline.denoise_loop_stage3 run with the same casts: bit-equal, under both schedulers."""
+    from oracle.pipeline import denoise_loop_stage3
+    from oracle.unipc import UniPCMultistepScheduler
+    cfg = UNetConfig.tiny(in_channels=8, stage2=False)
+    oracle = make_unet(cfg, seed=7)
+    g = torch.Generator().manual_seed(31)
+    lat, gl = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    f = torch.randn(1, 5, cfg.cross_attention_dim, generator=g)
+    mk = (lambda: OracleDDIMScheduler()) if sched == "ddim" else (lambda: UniPCMultistepScheduler(
+        beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1, timestep_spacing="leading"))
+    want = rs.run_reference_stage3_pipeline(cfg, oracle, latents=lat, gen_t_img_latents=gl, s_img_proj_f=f,
+                                            num_inference_steps=4, guidance_scale=2.0, scheduler=mk())
+
+    got = denoise_loop_stage3(oracle, mk(), latents=lat.half(), gen_t_img_latents=gl, s_img_proj_f=f,
+                              num_inference_steps=4, guidance_scale=2.0, dtype=torch.float16,
+                              unet_dtype=torch.float32)
+    assert torch.equal(got.float(), want.float())
+
+
+def test_reference_demo_pipeline_equals_oracle_loop():
+    """The reference's own PCDMsPipeline.__call__ (the pcdms_demo.ipynb driver; fp16 as it hard-codes) against
+    oracle.pipeline.denoise_loop_pcdms: bit-equal."""
+    from dataclasses import replace
+    from oracle.pipeline import denoise_loop_pcdms
+    cfg = replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True)
+    oracle = make_unet(cfg, seed=9).half()
+    h, w = 8, 16
+    g = torch.Generator().manual_seed(41)
+    lat, msk_l = torch.randn(1, 4, h, w, generator=g), torch.randn(1, 4, h, w, generator=g)
+    mask = torch.cat([torch.ones(1, 1, h, w // 2), torch.zeros(1, 1, h, w // 2)], dim=3)
+    pose = 0.1 * torch.randn(1, cfg.block_out_channels[0], h, w, generator=g)
+    pe = torch.randn(1, 7, cfg.cross_attention_dim, generator=g)
+    ne = 0.3 * torch.randn(1, 7, cfg.cross_attention_dim, generator=g)
+    kw = dict(latents=lat, mask=mask, simg_mask_latents=msk_l, cond_pose=pose, prompt_embeds=pe,
+              negative_prompt_embeds=ne, num_inference_steps=3, guidance_scale=2.0)
+    want = rs.run_reference_demo_pipeline(cfg, oracle, **kw)
+    got = denoise_loop_pcdms(oracle, OracleDDIMScheduler(), dtype=torch.float16, **kw)
+    assert torch.equal(got, want)

@@ -185,3 +185,30 @@ def test_image_in_image_out_gpu():
     assert _rel(got, want) < 1e-2
     pil = pipe(output_type="pil", generator=_g(11), **kw).images
     assert len(pil) == 2 and pil[0].size == (256, 128)
+
+
+@pytest.mark.gpu
+def test_drivers_against_reference_goldens_gpu():
+    """Product pipelines against tensors produced by the REFERENCE's own pipeline classes (tests/golden/*.pt, made by
+    tools/make_golden.py in the build container): stage-3 refiner and the demo driver."""
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden"
+    g = torch.load(gold / "ref_stage3_tiny.pt")
+    cfg = UNetConfig.tiny(in_channels=8, stage2=False)
+    _, m = _unet(cfg, torch.float16, "cuda", seed=g["seed"])
+    i = g["inputs"]
+    pipe = B200Stage3RefinedPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    got = pipe(height=64, width=64, num_inference_steps=i["num_inference_steps"], guidance_scale=i["guidance_scale"],
+               latents=i["latents"], s_img_proj_f=i["s_img_proj_f"], gen_t_img_latents=i["gen_t_img_latents"],
+               output_type="latent").images
+    assert _rel(got, g["latents"].float()) < 4e-3
+    g = torch.load(gold / "ref_demo_tiny.pt")
+    cfg = replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True)
+    _, m = _unet(cfg, torch.float16, "cuda", seed=g["seed"])
+    i = g["inputs"]
+    pipe = B200PCDMsPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    got = pipe(simg_mask_latents=i["simg_mask_latents"], mask=i["mask"], cond_pose=i["cond_pose"],
+               prompt_embeds=i["prompt_embeds"], negative_prompt_embeds=i["negative_prompt_embeds"], height=64,
+               width=128, num_images_per_prompt=1, guidance_scale=i["guidance_scale"], latents=i["latents"],
+               num_inference_steps=i["num_inference_steps"], output_type="latent").images
+    assert _rel(got, g["latents"].float()) < 4e-3

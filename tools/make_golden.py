@@ -7,6 +7,10 @@ Fixtures (tiny topology-preserving config so the files stay small):
   ref_unet_tiny.pt      inputs + output of Stage2_InapintUNet2DConditionModel.forward (fp32)
   ref_pipeline_tiny.pt  inputs + final latents of Stage2_InpaintDiffusionPipeline.__call__ (fp16 loop tensors, as
                         the reference hard-codes them; DDIM, 4 steps, guidance 2.0, 2 images per prompt)
+  ref_stage3_tiny.pt    inputs + final latents of Stage3_RefinedPipeline.__call__ (fp16 loop tensors, fp32 UNet; DDIM)
+  ref_demo_tiny.pt      inputs + final latents of PCDMsPipeline.__call__ (the pcdms_demo.ipynb driver; fp16; DDIM)
+  ref_image_proj.pt     state dict + input + output of the reference's ImageProjModel_p class
+                        (stage2_batchtest_inpaint_model.py:48-66), at a reduced width
 """
 import sys
 from pathlib import Path
@@ -46,6 +50,45 @@ def main():
     torch.save({"cfg": "tiny", "seed": 0, "inputs": pin, "steps": 4, "guidance_scale": 2.0, "n": 2,
                 "latents": latents}, GOLD / "ref_pipeline_tiny.pt")
     print("ref_pipeline_tiny", latents.shape, latents.dtype, float(latents.float().std()))
+
+    from dataclasses import replace
+    from oracle.schedulers import OracleDDIMScheduler
+    g = torch.Generator().manual_seed(31)
+    cfg3 = UNetConfig.tiny(in_channels=8, stage2=False)
+    u3 = make_unet(cfg3, seed=7)
+    kw3 = dict(latents=torch.randn(1, 4, 8, 8, generator=g), gen_t_img_latents=torch.randn(1, 4, 8, 8, generator=g),
+               s_img_proj_f=torch.randn(1, 5, cfg3.cross_attention_dim, generator=g), num_inference_steps=4,
+               guidance_scale=2.0)
+    out3 = rs.run_reference_stage3_pipeline(cfg3, u3, scheduler=OracleDDIMScheduler(), **kw3)
+    torch.save({"seed": 7, "inputs": kw3, "latents": out3}, GOLD / "ref_stage3_tiny.pt")
+    print("ref_stage3_tiny", out3.shape, out3.dtype)
+
+    cfgd = replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True)
+    ud = make_unet(cfgd, seed=9).half()
+    h, w = 8, 16
+    kwd = dict(latents=torch.randn(1, 4, h, w, generator=g), simg_mask_latents=torch.randn(1, 4, h, w, generator=g),
+               mask=torch.cat([torch.ones(1, 1, h, w // 2), torch.zeros(1, 1, h, w // 2)], dim=3),
+               cond_pose=0.1 * torch.randn(1, cfgd.block_out_channels[0], h, w, generator=g),
+               prompt_embeds=torch.randn(1, 7, cfgd.cross_attention_dim, generator=g),
+               negative_prompt_embeds=0.3 * torch.randn(1, 7, cfgd.cross_attention_dim, generator=g),
+               num_inference_steps=3, guidance_scale=2.0)
+    outd = rs.run_reference_demo_pipeline(cfgd, ud, **kwd)
+    torch.save({"seed": 9, "inputs": kwd, "latents": outd}, GOLD / "ref_demo_tiny.pt")
+    print("ref_demo_tiny", outd.shape, outd.dtype)
+
+    import ast
+    path = "/root/reference/stage2_batchtest_inpaint_model.py"
+    node = next(n for n in ast.parse(open(path).read()).body
+                if isinstance(n, ast.ClassDef) and n.name == "ImageProjModel_p")
+    ns = {"torch": torch, "nn": torch.nn}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    torch.manual_seed(3)
+    proj = ns["ImageProjModel_p"](in_dim=128, hidden_dim=64, out_dim=96).eval()
+    x = torch.randn(1, 9, 128, generator=g)
+    with torch.no_grad():
+        y = proj(x)
+    torch.save({"state_dict": proj.state_dict(), "x": x, "y": y}, GOLD / "ref_image_proj.pt")
+    print("ref_image_proj", y.shape)
 
 
 if __name__ == "__main__":
