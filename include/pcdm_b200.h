@@ -31,7 +31,8 @@ extern "C" {
 #define PCDM_DT_F16 0
 #define PCDM_DT_BF16 1
 
-#define PCDM_FLAG_GEGLU 1   /* gemm: weight rows packed [32 value | 32 gate]; writes N/2 columns value*gelu(gate) */
+#define PCDM_FLAG_GEGLU 1   /* gemm: weight rows packed [32 value | 32 gate]; writes N/2 columns value*gelu(gate);
+                             * together with PCDM_FLAG_SILU the gate activation is SiLU (SwiGLU) */
 #define PCDM_FLAG_OUT_F32 2 /* gemm/conv: write fp32 instead of the 16-bit dtype */
 #define PCDM_FLAG_SILU 4    /* gemm/conv epilogue and norm kernels: apply SiLU last */
 #define PCDM_FLAG_GELU 8    /* gemm/conv epilogue: apply GELU (erf form) last */

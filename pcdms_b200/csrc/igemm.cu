@@ -448,8 +448,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             const float2 h1 = __fadd2_rn(make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
             const float2 g0 = __fadd2_rn(make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
             const float2 g1 = __fadd2_rn(make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
-            const float2 v0 = __fmul2_rn(h0, gelu_erf2_f(g0));
-            const float2 v1 = __fmul2_rn(h1, gelu_erf2_f(g1));
+            // gate activation: GELU (GEGLU, diffusers FeedForward) or SiLU (SwiGLU, DINOv2's FFN) — warp-uniform
+            const float2 v0 = __fmul2_rn(h0, p.silu == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
+            const float2 v1 = __fmul2_rn(h1, p.silu == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
             o[j / 2] = pack2<DT>(v0.x, v0.y);
             o[j / 2 + 1] = pack2<DT>(v1.x, v1.y);
           }

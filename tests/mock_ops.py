@@ -24,7 +24,7 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     if geglu:
         y = y + (bias if bias is not None else 0)
         g = y.view(y.shape[0], -1, 64)
-        y = (g[..., :32] * F.gelu(g[..., 32:])).reshape(y.shape[0], -1)
+        y = (g[..., :32] * (F.silu(g[..., 32:]) if silu else F.gelu(g[..., 32:]))).reshape(y.shape[0], -1)
     else:
         if bias is not None:
             y = y + bias
