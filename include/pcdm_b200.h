@@ -103,6 +103,14 @@ int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const f
 int pcdm_set_attention_poly(int on); /* experiment hook: 1 = half of the softmax exp2 on the FMA pipe (default 0: measured slower) */
 int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);
+/* The same with an explicit head width: head_dim = 64 or 128; head h of a token row lives at columns
+ * [h*head_dim, (h+1)*head_dim) of q / k / v / out.  Other widths are served by zero-padding the projection weights to
+ * the next supported width at load time: the CLIP ViT-H/14 image encoder (transformers CLIPVisionModelWithProjection,
+ * head_dim 80: stage1_batchtest_prior_model.py:61,100-101; stage2_batchtest_inpaint_model.py:97,181-183) runs with
+ * head_dim = 128 and scale = 80^-1/2 — zero q/k columns add nothing to the scores, zero v columns give zero outputs. */
+int pcdm_attention_hd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                      void* out, long long ldo, int B, int heads, int Sq, int Skv, int head_dim, float scale, int dtype,
+                      void* stream);
 
 /* Boundary layout conversion (the reference's tensors are NCHW).  *_dtype: 0 f16, 1 bf16, 2 f32 (destination of
  * nchw_to_nhwc_pad must be 16-bit).  Replaces nothing arithmetic: forward() entry/exit at reference :579-595,:822-825. */

@@ -37,21 +37,27 @@ constexpr int ATT_THREADS = 320;   // warp 0: TMA + TMEM alloc, warp 1: MMA, war
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
 constexpr int ATT_XCH_BYTES = 2 * 2 * 128 * 4 + 2 * 128 * 4;   // row-max exchange [parity][half][row] + row-sum [half][row]
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + ATT_XCH_BYTES + 1024 + 256;
-constexpr int ATT_TMEM_COLS = 256;
+// head_dim HD = 64 (the UNet / DINOv2 / prior transformer) or 128 (CLIP ViT-H: 80 real columns per head, zero-padded by
+// the caller's weight packing).  HD = 128 keeps every operand as 64-column 128B-swizzled tiles (two per Q / K / V),
+// needs 128 + 64 + 128 TMEM columns (allocation 512) and 160 KB of shared memory: one CTA per SM.
+__host__ __device__ constexpr int att_smem_bytes(int HD) { return ATT_TILE_BYTES * (HD / 64) * (1 + 2 * ATT_KV_STAGES) + ATT_XCH_BYTES + 1024 + 256; }
+__host__ __device__ constexpr int att_tmem_cols(int HD) { return HD == 64 ? 256 : 512; }
 constexpr int ATT_TMEM_S = 0, ATT_TMEM_P = 128, ATT_TMEM_O = 192;
 
 __device__ __forceinline__ void pair_barrier(int q) {   // the two softmax warps that share TMEM quadrant q
   asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
 }
 
-template <int DT, int ATT_POLY_OF_4>
-__global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+template <int DT, int ATT_POLY_OF_4, int HD>
+__global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int NCH = HD / 64;                       // 64-column operand tiles per Q / K / V block
+  constexpr int ATT_STAGE_BYTES = 2 * NCH * ATT_TILE_BYTES;
+  constexpr int ATT_TMEM_COLS = att_tmem_cols(HD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + ATT_TILE_BYTES;  // stage s: K at s*2*TILE, V at s*2*TILE + TILE
-  float* xmax = reinterpret_cast<float*>(smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));   // [2][2][128]
+  uint8_t* sKV = smem + NCH * ATT_TILE_BYTES;  // stage s: K tiles at s*STAGE, V tiles at s*STAGE + NCH*TILE
+  float* xmax = reinterpret_cast<float*>(smem + NCH * ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES));   // [2][2][128]
   float* xsum = xmax + 2 * 2 * 128;                                                          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + ATT_XCH_BYTES);
   uint64_t* q_full = bars;
@@ -94,18 +100,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_4d(sQ, &p.tmQ, q_full, 0, qt * 128, h, b);
+      mbar_expect_tx(q_full, NCH * ATT_TILE_BYTES);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tma_load_4d(sQ + c * ATT_TILE_BYTES, &p.tmQ, q_full, c * 64, qt * 128, h, b);
     }
     __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
       const int stage = j & 1;
       mbar_wait(&kv_empty[stage], (uint32_t)(((j >> 1) & 1) ^ 1));
-      uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+      uint8_t* sk = sKV + stage * ATT_STAGE_BYTES;
       if (elect_one()) {
-        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, h, b);
-        tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, h, b);
+        mbar_expect_tx(&kv_full[stage], ATT_STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_4d(sk + c * ATT_TILE_BYTES, &p.tmK, &kv_full[stage], c * 64, j * 128, h, b);
+          tma_load_4d(sk + (NCH + c) * ATT_TILE_BYTES, &p.tmV, &kv_full[stage], c * 64, j * 128, h, b);
+        }
       }
       __syncwarp();
     }
@@ -129,11 +139,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       if (j > 0) mbar_wait(s_free, (uint32_t)((j - 1) & 1));   // softmax holds S_{j-1} in registers
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
+        const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (ATT_STAGE_BYTES >> 4)) | ((16u >> 4) << 16);
         const uint32_t idesc_qk = idesc_qk0 | ((uint32_t)(n16_of(j) * 2) << 17);   // N >> 3 at bits [17, 23)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + ATT_TMEM_S, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem + ATT_TMEM_S, kDescHi | (q_lo + (uint32_t)c * (ATT_TILE_BYTES >> 4) + 2u * k),
+                    kDescHi | (k_lo + (uint32_t)c * (ATT_TILE_BYTES >> 4) + 2u * k), idesc_qk, (c | k) != 0);
         tc_commit(s_full);
       }
       __syncwarp();
@@ -145,13 +158,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
       tc_fence_after();
       const int stage = j & 1;
       if (elect_one()) {
-        const uint32_t v_lo = (kv_lo0 + (uint32_t)((stage * 2 + 1) * (ATT_TILE_BYTES >> 4))) | ((1024u >> 4) << 16);
+        const uint32_t v_lo = (kv_lo0 + (uint32_t)(stage * (ATT_STAGE_BYTES >> 4) + NCH * (ATT_TILE_BYTES >> 4))) |
+                              ((1024u >> 4) << 16);
         const int n16 = n16_of(j);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
-          if (k < n16)
-            umma_ts(tmem + ATT_TMEM_O, tmem + ATT_TMEM_P + k * 8, kDescHi | (v_lo + (2048u >> 4) * k), idesc_pv,
-                    (j | k) != 0);
+        for (int c = 0; c < NCH; ++c)   // one N = 64 MMA chain per 64-column tile of V -> output columns [64c, 64c+64)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // K = 16 kv rows per MMA: 8 packed P columns, 16 V rows (2048 B)
+            if (k < n16)
+              umma_ts(tmem + ATT_TMEM_O + c * 64, tmem + ATT_TMEM_P + k * 8,
+                      kDescHi | (v_lo + (uint32_t)c * (ATT_TILE_BYTES >> 4) + (2048u >> 4) * k), idesc_pv, (j | k) != 0);
         tc_commit(&kv_empty[stage]);
         tc_commit(pv_done);
       }
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   } else {
     // ===================== softmax / correction / epilogue =====================
     // warps 2..9: TMEM quadrant q = warp & 3 (rows 32q..32q+31); `half` selects which 64 of the 128 score columns
-    // (and which 32 of the 64 output columns) this warp owns.  The two warps of a quadrant exchange row maxima and,
+    // (and which HD/2 of the HD output columns) this warp owns.  The two warps of a quadrant exchange row maxima and,
     // at the end, row sums through shared memory.
     using T = typename TypeOf<DT>::T;
     const int q = warp & 3;
@@ -211,13 +227,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
           const float m_new = grow ? mx : m_ref;
           const float alpha = exp2f(m_ref - m_new);
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < HD / 32; ++c) {
             uint32_t o[16];
-            tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
+            tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
+            tmem_st16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
           }
           l *= alpha;
           m_ref = m_new;
@@ -284,11 +300,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     mbar_wait(pv_done, (uint32_t)((n_kv - 1) & 1));
     tc_fence_after();
     const long long qrow = (long long)qt * 128 + row;
-    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * 64 + half * 32;
+    T* op = reinterpret_cast<T*>(p.out) + ((long long)b * p.Sq + qrow) * p.ldo + h * HD + half * (HD / 2);
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t o[16];
-      tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * 32 + c * 16, o);
+      tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
       tc_wait_ld();
       if (qrow < p.Sq) {
 #pragma unroll
@@ -316,10 +332,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
 using namespace pcdm;
 
-static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, int heads, int B, int box_rows) {
-  // element (b, s, h, d) at ((b*S + s) * ld + h*64 + d)
-  const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)heads, (uint64_t)B};
-  const uint64_t strides[3] = {(uint64_t)ld * 2, 128, (uint64_t)S * ld * 2};
+static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, int heads, int B, int box_rows, int hd) {
+  // element (b, s, h, d) at ((b*S + s) * ld + h*hd + d); boxes are 64 columns wide (one 128B-swizzled operand tile)
+  const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)S, (uint64_t)heads, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)hd * 2, (uint64_t)S * ld * 2};
   const uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
   return make_tmap(m, base, 4, dims, strides, box);
 }
@@ -333,7 +349,15 @@ extern "C" int pcdm_set_attention_poly(int on) {
 extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                               void* out, long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype,
                               void* stream_) {
+  return pcdm_attention_hd(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Sq, Skv, 64, scale, dtype, stream_);
+}
+
+extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                 long long ldv, void* out, long long ldo, int B, int heads, int Sq, int Skv,
+                                 int head_dim, float scale, int dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (head_dim != 64 && head_dim != 128)
+    return set_error(PCDM_ERR_UNSUPPORTED, "attention: head_dim must be 64 or 128 (pad other widths with zero columns)");
   if (!q || !k || !v || !out) return set_error(PCDM_ERR_INVALID, "attention: null pointer");
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "attention: bad dtype");
   if (B <= 0 || heads <= 0 || Sq <= 0 || Skv <= 0) return set_error(PCDM_ERR_INVALID, "attention: empty problem");
@@ -342,30 +366,34 @@ extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long 
   memset(&p, 0, sizeof(p));
   // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and
   // are zero-filled, so short sequences need no special casing (zero K rows are masked, zero V rows add nothing).
-  PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128), "Q map");
-  PCDM_CHECK(make_qkv_map(&p.tmK, k, ldk, Skv, heads, B, 128), "K map");
-  PCDM_CHECK(make_qkv_map(&p.tmV, v, ldv, Skv, heads, B, 128), "V map");
+  PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128, head_dim), "Q map");
+  PCDM_CHECK(make_qkv_map(&p.tmK, k, ldk, Skv, heads, B, 128, head_dim), "K map");
+  PCDM_CHECK(make_qkv_map(&p.tmV, v, ldv, Skv, heads, B, 128, head_dim), "V map");
   p.B = B; p.heads = heads; p.Sq = Sq; p.Skv = Skv;
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int grid = B * heads * p.q_tiles;
-#define ATT_LAUNCH(DT_, P_)                                                                                         \
+#define ATT_LAUNCH(DT_, P_, HD_)                                                                                    \
   do {                                                                                                              \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
-      PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                     ATT_SMEM_BYTES));                                                              \
+      PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_, P_, HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     att_smem_bytes(HD_)));                                                         \
       configured = true;                                                                                            \
     }                                                                                                               \
-    PCDM_CUDA(launch_kernel(attention_kernel<DT_, P_>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, p)); \
+    PCDM_CUDA(launch_kernel(attention_kernel<DT_, P_, HD_>, dim3(grid), dim3(ATT_THREADS), att_smem_bytes(HD_),     \
+                            stream, 1, p));                                                                         \
   } while (0)
-  if (dtype == DT_F16) {
-    if (g_att_poly) ATT_LAUNCH(DT_F16, 2);
-    else ATT_LAUNCH(DT_F16, 0);
+  if (head_dim == 128) {
+    if (dtype == DT_F16) ATT_LAUNCH(DT_F16, 0, 128);
+    else ATT_LAUNCH(DT_BF16, 0, 128);
+  } else if (dtype == DT_F16) {
+    if (g_att_poly) ATT_LAUNCH(DT_F16, 2, 64);
+    else ATT_LAUNCH(DT_F16, 0, 64);
   } else {
-    if (g_att_poly) ATT_LAUNCH(DT_BF16, 2);
-    else ATT_LAUNCH(DT_BF16, 0);
+    if (g_att_poly) ATT_LAUNCH(DT_BF16, 2, 64);
+    else ATT_LAUNCH(DT_BF16, 0, 64);
   }
 #undef ATT_LAUNCH
   PCDM_CUDA(cudaGetLastError());

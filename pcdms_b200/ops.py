@@ -173,18 +173,20 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 # ---------------------------------------------------------------------------------------------------------------
 # K3 attention
 # ---------------------------------------------------------------------------------------------------------------
-def attention(q, k, v, B, heads, out=None, scale=0.125):
-    """q: [B*Sq, >=heads*64] view, k/v: [B*Skv, ...] views (unit column stride; may be slices of a fused buffer).
-    Head h of token row r lives at columns [h*64, h*64+64).  Returns [B*Sq, heads*64]."""
+def attention(q, k, v, B, heads, out=None, scale=0.125, head_dim=64):
+    """q: [B*Sq, >=heads*head_dim] view, k/v: [B*Skv, ...] views (unit column stride; may be slices of a fused buffer).
+    Head h of token row r lives at columns [h*head_dim, (h+1)*head_dim); head_dim is 64 or 128.
+    Returns [B*Sq, heads*head_dim]."""
     lib = _l.load()
     assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
     Sq = q.shape[0] // B
     Skv = k.shape[0] // B
     if out is None:
-        out = torch.empty((B * Sq, heads * 64), device=q.device, dtype=q.dtype)
-    rc = lib.pcdm_attention(_l.ptr(q), C.c_longlong(q.stride(0)), _l.ptr(k), C.c_longlong(k.stride(0)), _l.ptr(v),
-                            C.c_longlong(v.stride(0)), _l.ptr(out), C.c_longlong(out.stride(0)), C.c_int(B),
-                            C.c_int(heads), C.c_int(Sq), C.c_int(Skv), C.c_float(scale), C.c_int(_dt(q)), _stream(q))
+        out = torch.empty((B * Sq, heads * head_dim), device=q.device, dtype=q.dtype)
+    rc = lib.pcdm_attention_hd(_l.ptr(q), C.c_longlong(q.stride(0)), _l.ptr(k), C.c_longlong(k.stride(0)), _l.ptr(v),
+                               C.c_longlong(v.stride(0)), _l.ptr(out), C.c_longlong(out.stride(0)), C.c_int(B),
+                               C.c_int(heads), C.c_int(Sq), C.c_int(Skv), C.c_int(head_dim), C.c_float(scale),
+                               C.c_int(_dt(q)), _stream(q))
     _l.check(rc)
     return out
 

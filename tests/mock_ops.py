@@ -77,12 +77,12 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return _rt(F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps), x.dtype)
 
 
-def attention(q, k, v, B, heads, out=None, scale=0.125):
+def attention(q, k, v, B, heads, out=None, scale=0.125, head_dim=64):
     Sq, Skv = q.shape[0] // B, k.shape[0] // B
-    C = heads * 64
-    qh = q[:, :C].float().reshape(B, Sq, heads, 64).transpose(1, 2)
-    kh = k[:, :C].float().reshape(B, Skv, heads, 64).transpose(1, 2)
-    vh = v[:, :C].float().reshape(B, Skv, heads, 64).transpose(1, 2)
+    C = heads * head_dim
+    qh = q[:, :C].float().reshape(B, Sq, heads, head_dim).transpose(1, 2)
+    kh = k[:, :C].float().reshape(B, Skv, heads, head_dim).transpose(1, 2)
+    vh = v[:, :C].float().reshape(B, Skv, heads, head_dim).transpose(1, 2)
     p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
     return _rt((p @ vh).transpose(1, 2).reshape(B * Sq, C), q.dtype)
 
