@@ -164,6 +164,23 @@ int pcdm_unipc_step(const void* model_output, int eps_dtype, const void* sample,
                     float* last_sample, float* m0, float* m1, const float* coef_row_host, long long numel,
                     void* stream);
 
+/* UnCLIPScheduler.step (diffusers 0.24.0 — the scheduler Stage1_PriorPipeline samples the stage-1 prior with,
+ * src/pipelines/stage1_prior_pipeline.py:445-446,478-483): x_prev = (c_x0 * clamp(x0, -clip, clip) + c_xt * x_t) + std *
+ * noise, x0 = model_output ("sample" prediction) or (x_t - sqrt_b * model_output) / sqrt_a ("epsilon").  A table row
+ * holds 8 floats {c_x0, c_xt, std, clip, sqrt_a, sqrt_b, pred_is_epsilon, 0}; IEEE round-to-nearest arithmetic in the
+ * reference's operation order (fp32 results bit-identical to its CPU evaluation).
+ * pcdm_cfg_unclip_step: fused CFG combine (pred rows [0, n) unconditional, [n, 2n) conditional when use_cfg) + update of
+ * the fp32 latents [n, E] + rewrite of the next step's 16-bit / fp32 model-input rows (both halves); coef_table
+ * [steps, 8] and noise_table [steps, n, E] on the device, step_counter / t_table / t_cur as pcdm_cfg_ddim_step.
+ * pcdm_unclip_step: the scheduler protocol's step() on same-shape contiguous tensors (dtypes 0 f16, 1 bf16, 2 f32);
+ * noise has the sample's dtype (NULL allowed when the row's std is 0: the last step); coef_row_host: 8 HOST floats. */
+int pcdm_cfg_unclip_step(const float* pred, long long ld_pred, float* latents, void* xin, int xin_dtype,
+                         long long ld_xin, const float* coef_table, const float* noise_table, int* step_counter,
+                         float guidance_scale, int use_cfg, int n, int E, const float* t_table, float* t_cur,
+                         void* stream);
+int pcdm_unclip_step(const void* model_output, int mo_dtype, const void* sample, const void* noise, void* prev_sample,
+                     int dtype, const float* coef_row_host, long long numel, void* stream);
+
 /* y[m, :] = softmax(scale * x[m, :]): fp32 scores in, 16-bit probabilities out (row strides in elements).  The VAE
  * mid-block attention (diffusers AutoencoderKL, one head of dim 512: stage2_inpaint_pipeline.py:443,528) runs as
  * pcdm_gemm (Q K^T, fp32 out) -> pcdm_softmax_rows -> pcdm_gemm (P V).  N % 4 == 0, N <= 16384. */

@@ -286,15 +286,28 @@ class GEGLU(nn.Module):
         return hidden_states * F.gelu(gate)  # exact (erf) GELU
 
 
+class GELU(nn.Module):
+    """diffusers.models.activations.GELU (approximate="none"): Linear then exact (erf) GELU — the `activation_fn="gelu"`
+    feed-forward of the stage-1 prior's blocks (/root/reference/src/models/stage1_prior_transformer.py:112-120)."""
+
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+
+    def forward(self, hidden_states, scale: float = 1.0):
+        return F.gelu(self.proj(hidden_states))
+
+
 class FeedForward(nn.Module):
     def __init__(self, dim: int, dim_out: Optional[int] = None, mult: int = 4, dropout: float = 0.0,
                  activation_fn: str = "geglu", final_dropout: bool = False):
         super().__init__()
-        if activation_fn != "geglu":
+        if activation_fn not in ("geglu", "gelu"):
             raise NotImplementedError
         inner_dim = int(dim * mult)
         dim_out = dim_out if dim_out is not None else dim
-        self.net = nn.ModuleList([GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out)])
+        act = GEGLU(dim, inner_dim) if activation_fn == "geglu" else GELU(dim, inner_dim)
+        self.net = nn.ModuleList([act, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out)])
 
     def forward(self, hidden_states, scale: float = 1.0):
         for module in self.net:
@@ -314,10 +327,14 @@ class BasicTransformerBlock(nn.Module):
         self.norm1 = nn.LayerNorm(dim, elementwise_affine=norm_elementwise_affine)
         self.attn1 = Attention(query_dim=dim, heads=num_attention_heads, dim_head=attention_head_dim, dropout=dropout,
                                bias=attention_bias, upcast_attention=upcast_attention)
-        self.norm2 = nn.LayerNorm(dim, elementwise_affine=norm_elementwise_affine)
-        self.attn2 = Attention(query_dim=dim, cross_attention_dim=cross_attention_dim, heads=num_attention_heads,
-                               dim_head=attention_head_dim, dropout=dropout, bias=attention_bias,
-                               upcast_attention=upcast_attention)
+        if cross_attention_dim is not None:
+            self.norm2 = nn.LayerNorm(dim, elementwise_affine=norm_elementwise_affine)
+            self.attn2 = Attention(query_dim=dim, cross_attention_dim=cross_attention_dim, heads=num_attention_heads,
+                                   dim_head=attention_head_dim, dropout=dropout, bias=attention_bias,
+                                   upcast_attention=upcast_attention)
+        else:   # diffusers 0.24.0: no second attention without a cross_attention_dim (the stage-1 prior's blocks)
+            self.norm2 = None
+            self.attn2 = None
         self.norm3 = nn.LayerNorm(dim, elementwise_affine=norm_elementwise_affine)
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
 
@@ -326,9 +343,10 @@ class BasicTransformerBlock(nn.Module):
         kw = cross_attention_kwargs if cross_attention_kwargs is not None else {}
         n = self.norm1(hidden_states)
         hidden_states = self.attn1(n, encoder_hidden_states=None, attention_mask=attention_mask, **kw) + hidden_states
-        n = self.norm2(hidden_states)
-        hidden_states = self.attn2(n, encoder_hidden_states=encoder_hidden_states,
-                                   attention_mask=encoder_attention_mask, **kw) + hidden_states
+        if self.attn2 is not None:
+            n = self.norm2(hidden_states)
+            hidden_states = self.attn2(n, encoder_hidden_states=encoder_hidden_states,
+                                       attention_mask=encoder_attention_mask, **kw) + hidden_states
         n = self.norm3(hidden_states)
         hidden_states = self.ff(n) + hidden_states
         return hidden_states

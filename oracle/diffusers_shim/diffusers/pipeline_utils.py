@@ -30,9 +30,13 @@ class DiffusionPipeline:
 
     @property
     def device(self):
-        unet = getattr(self, "unet", None)
-        return unet.device if unet is not None else torch.device("cpu")
+        for name in ("unet", "prior"):
+            m = getattr(self, name, None)
+            if m is not None:
+                return m.device
+        return torch.device("cpu")
 
-    @contextlib.contextmanager
     def progress_bar(self, iterable=None, total=None):
-        yield _Bar()
+        if iterable is not None:   # `for t in self.progress_bar(timesteps)` (stage1_prior_pipeline.py:456)
+            return iterable
+        return contextlib.nullcontext(_Bar())

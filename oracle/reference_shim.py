@@ -174,3 +174,39 @@ def run_reference_demo_pipeline(cfg, oracle_unet_half, *, latents, mask, simg_ma
                height=h * 8, width=w * 8, num_images_per_prompt=1, guidance_scale=guidance_scale,
                latents=latents.half(), num_inference_steps=num_inference_steps, output_type="pt")
     return out.images
+
+
+def build_reference_prior(**cfg):
+    """Instantiate the reference's Stage1_PriorTransformer (src/models/stage1_prior_transformer.py:50) on the shim."""
+    _enable()
+    from src.models.stage1_prior_transformer import Stage1_PriorTransformer
+
+    model = Stage1_PriorTransformer(**cfg)
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
+def run_reference_prior_pipeline(ref_prior, *, s_embed, s_pose, t_pose, latents, num_inference_steps, guidance_scale,
+                                 zero_embed):
+    """Run Stage1_PriorPipeline.__call__ (src/pipelines/stage1_prior_pipeline.py:357-505) unmodified on CPU.  The
+    variance noise of each step comes from torch's global generator (the reference passes none to scheduler.step,
+    :478-483): seed it before calling.  `zero_embed` stands in for the CLIP embedding of a black image
+    (get_zero_embed, :282-289) — the image encoder is outside the loop.  Returns (image_embeds, negative_image_embeds)."""
+    _enable()
+    from diffusers.schedulers import UnCLIPScheduler
+    from src.pipelines.stage1_prior_pipeline import Stage1_PriorPipeline
+
+    class _Encoder:
+        config = SimpleNamespace(image_size=8)
+        dtype = torch.float32
+
+        def __call__(self, x):
+            return {"image_embeds": zero_embed}
+
+    pipe = Stage1_PriorPipeline(prior=ref_prior, image_encoder=_Encoder(), scheduler=UnCLIPScheduler(),
+                                image_processor=None)
+    out = pipe(s_embed=s_embed, s_pose=s_pose, t_pose=t_pose, num_images_per_prompt=1,
+               num_inference_steps=num_inference_steps, latents=latents, guidance_scale=guidance_scale)
+    return out[0] if isinstance(out, tuple) else (out["image_embeds"], out["negative_image_embeds"])

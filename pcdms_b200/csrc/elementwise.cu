@@ -282,6 +282,77 @@ __global__ void unipc_step_kernel(const void* __restrict__ eps, int eps_dt, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// UnCLIPScheduler.step (diffusers 0.24.0 scheduling_unclip.py; the scheduler of the stage-1 prior pipeline,
+// /root/reference/src/pipelines/stage1_prior_pipeline.py:478-483):
+//     x_prev = (c_x0 * clamp(x0, -clip, clip) + c_xt * x_t) + std * noise
+// with x0 = model_output ("sample" prediction, the reference's configuration) or (x_t - sqrt(1-abar) eps) / sqrt(abar)
+// ("epsilon").  A row holds the 8 schedule-only scalars of one step, computed by the host with the reference's fp32
+// tensor arithmetic; the products / sums below are IEEE round-to-nearest in the reference's order, so fp32 results are
+// bit-identical to its CPU evaluation.
+struct UnCLIPRow { float c_x0, c_xt, std, clip, sqrt_a, sqrt_b, pred_eps, pad; };
+
+__device__ __forceinline__ float unclip_update(const UnCLIPRow& r, float mo, float x, float noise) {
+  float x0 = mo;
+  if (r.pred_eps != 0.f) x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(r.sqrt_b, mo)), r.sqrt_a);
+  x0 = fminf(fmaxf(x0, -r.clip), r.clip);
+  float xp = __fadd_rn(__fmul_rn(r.c_x0, x0), __fmul_rn(r.c_xt, x));
+  if (r.std != 0.f) xp = __fadd_rn(xp, __fmul_rn(r.std, noise));
+  return xp;
+}
+
+// Fused per-step kernel of the stage-1 engine: CFG combine (rows [0, n) unconditional, [n, 2n) conditional when
+// use_cfg) + UnCLIP update of the fp32 latents [n, E] + rewrite of the 16-bit model-input rows of the next step (both
+// CFG halves); step-indexed device tables (coef [steps], noise [steps, n, E]) and the device step counter make one CUDA
+// graph serve every step, as cfg_ddim_step_kernel.
+__global__ void cfg_unclip_step_kernel(const float* __restrict__ pred, long long ld_pred, float* __restrict__ latents,
+                                       void* __restrict__ xin, int xin_dt, long long ld_xin,
+                                       const UnCLIPRow* __restrict__ coef, const float* __restrict__ noise,
+                                       int* __restrict__ step_counter, float guidance, int use_cfg, int n, int E,
+                                       const float* __restrict__ t_table, float* __restrict__ t_cur) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step = *step_counter;
+  const UnCLIPRow r = coef[step];
+  const long long total = (long long)n * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int b = (int)(i / E);
+    float mo = pred[(long long)b * ld_pred + e];
+    if (use_cfg) {
+      const float c = pred[(long long)(b + n) * ld_pred + e];
+      mo = __fadd_rn(mo, __fmul_rn(guidance, __fsub_rn(c, mo)));
+    }
+    const float xp = unclip_update(r, mo, latents[i], r.std != 0.f ? noise[(long long)step * total + i] : 0.f);
+    latents[i] = xp;
+    store_any(xin, (long long)b * ld_xin + e, xin_dt, xp);
+    if (use_cfg) store_any(xin, (long long)(b + n) * ld_xin + e, xin_dt, xp);
+  }
+  __syncthreads();
+  __shared__ bool last_block;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(step_counter + 1), 1u);
+    last_block = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_block && threadIdx.x == 0) {
+    step_counter[1] = 0;
+    step_counter[0] = step + 1;
+    if (t_table && t_cur) *t_cur = t_table[step + 1];
+  }
+}
+
+__global__ void unclip_step_kernel(const void* __restrict__ mo, int mo_dt, const void* __restrict__ sample,
+                                   const void* __restrict__ noise, void* __restrict__ prev, int dt, UnCLIPRow r,
+                                   long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    store_any(prev, i, dt, unclip_update(r, load_any(mo, i, mo_dt), load_any(sample, i, dt),
+                                         (noise && r.std != 0.f) ? load_any(noise, i, dt) : 0.f));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Row softmax of fp32 scores -> 16-bit probabilities: y[m, :] = softmax(scale * x[m, :]).  Used by the VAE mid-block
 // attention (one head of dim 512, diffusers AutoencoderKL: stage2_inpaint_pipeline.py:443,528), whose QK^T and PV
 // products run on the GEMM kernel.  One CTA per row, the row lives in registers (N <= 16384): one read, one write.
@@ -494,6 +565,35 @@ extern "C" int pcdm_unipc_step(const void* model_output, int eps_dtype, const vo
   UniPCRow r;
   memcpy(r.v, coef_row_host, sizeof(r.v));
   PCDM_CUDA(launch_kernel(unipc_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, last_sample, m0, m1, r, numel));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_cfg_unclip_step(const float* pred, long long ld_pred, float* latents, void* xin, int xin_dtype,
+                                    long long ld_xin, const float* coef_table, const float* noise_table,
+                                    int* step_counter, float guidance_scale, int use_cfg, int n, int E,
+                                    const float* t_table, float* t_cur, void* stream_) {
+  if (!pred || !latents || !xin || !coef_table || !noise_table || !step_counter)
+    return set_error(PCDM_ERR_INVALID, "cfg_unclip_step: null pointer");
+  if (xin_dtype < 0 || xin_dtype > 2) return set_error(PCDM_ERR_INVALID, "cfg_unclip_step: bad dtype");
+  if (n <= 0 || E <= 0 || ld_pred < E || ld_xin < E) return set_error(PCDM_ERR_INVALID, "cfg_unclip_step: bad shape");
+  if (reinterpret_cast<uintptr_t>(coef_table) & 15) return set_error(PCDM_ERR_INVALID, "cfg_unclip_step: coef table must be 16-byte aligned");
+  const long long total = (long long)n * E;
+  PCDM_CUDA(launch_kernel(cfg_unclip_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, pred, ld_pred, latents, xin, xin_dtype, ld_xin, reinterpret_cast<const UnCLIPRow*>(coef_table), noise_table, step_counter, guidance_scale, use_cfg, n, E, t_table, t_cur));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_unclip_step(const void* model_output, int mo_dtype, const void* sample, const void* noise,
+                                void* prev_sample, int dtype, const float* coef_row_host, long long numel,
+                                void* stream_) {
+  if (!model_output || !sample || !prev_sample || !coef_row_host) return set_error(PCDM_ERR_INVALID, "unclip_step: null pointer");
+  if (mo_dtype < 0 || mo_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "unclip_step: bad dtype");
+  if (numel <= 0) return set_error(PCDM_ERR_INVALID, "unclip_step: empty problem");
+  UnCLIPRow r;
+  memcpy(&r, coef_row_host, sizeof(r));
+  if (r.std != 0.f && !noise) return set_error(PCDM_ERR_INVALID, "unclip_step: this step adds noise (std != 0) but noise is NULL");
+  PCDM_CUDA(launch_kernel(unclip_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, mo_dtype, sample, noise, prev_sample, dtype, r, numel));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

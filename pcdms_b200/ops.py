@@ -322,6 +322,42 @@ def unipc_step(model_output, sample, last_sample, m0, m1, coef_row, out=None):
     return out
 
 
+UNCLIP_ROW = 8  # floats per step in the UnCLIP coefficient table (include/pcdm_b200.h)
+
+
+def cfg_unclip_step(pred, latents, xin, coef_table, noise_table, step_counter, guidance_scale, use_cfg, t_table=None,
+                    t_cur=None):
+    """pred: [n or 2n, E] fp32 prior outputs (rows [0, n) unconditional when use_cfg); latents: [n, E] fp32 (in place);
+    xin: [n or 2n, E] model-input rows of the next step; coef_table: [steps, 8] fp32; noise_table: [steps, n, E] fp32."""
+    lib = _l.load()
+    n, E = latents.shape
+    assert pred.dtype == torch.float32 and pred.stride(1) == 1 and pred.shape == ((2 if use_cfg else 1) * n, E)
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and xin.stride(1) == 1 and xin.shape == pred.shape
+    assert coef_table.dtype == torch.float32 and coef_table.shape[-1] == UNCLIP_ROW and coef_table.is_contiguous()
+    assert noise_table.dtype == torch.float32 and noise_table.is_contiguous() and noise_table.shape[1:] == (n, E)
+    assert noise_table.shape[0] == coef_table.shape[0] and step_counter.dtype == torch.int32 and step_counter.numel() == 2
+    rc = lib.pcdm_cfg_unclip_step(_l.ptr(pred), C.c_longlong(pred.stride(0)), _l.ptr(latents), _l.ptr(xin),
+                                  C.c_int(_any_dt(xin)), C.c_longlong(xin.stride(0)), _l.ptr(coef_table),
+                                  _l.ptr(noise_table), _l.ptr(step_counter), C.c_float(guidance_scale),
+                                  C.c_int(1 if use_cfg else 0), C.c_int(n), C.c_int(E), _l.ptr(t_table), _l.ptr(t_cur),
+                                  _stream(latents))
+    _l.check(rc)
+
+
+def unclip_step(model_output, sample, noise, coef_row, out=None):
+    """One UnCLIPScheduler.step on same-shape tensors; noise: like sample, or None when the row's std is 0."""
+    lib = _l.load()
+    assert model_output.is_contiguous() and sample.is_contiguous() and model_output.shape == sample.shape
+    assert noise is None or (noise.is_contiguous() and noise.shape == sample.shape and noise.dtype == sample.dtype)
+    if out is None:
+        out = torch.empty_like(sample)
+    row = (C.c_float * UNCLIP_ROW)(*[float(v) for v in coef_row])
+    rc = lib.pcdm_unclip_step(_l.ptr(model_output), C.c_int(_any_dt(model_output)), _l.ptr(sample), _l.ptr(noise),
+                              _l.ptr(out), C.c_int(_any_dt(sample)), row, C.c_longlong(sample.numel()), _stream(sample))
+    _l.check(rc)
+    return out
+
+
 def softmax_rows(x, scale, dtype, out=None):
     """x: [M, N] fp32 scores (unit column stride) -> softmax(scale * x) rows as `dtype` (fp16 / bf16)."""
     lib = _l.load()

@@ -330,3 +330,103 @@ def _add_noise(alphas_cumprod, x0, noise, timesteps):
         ac = alphas_cumprod.to(device=x0.device, dtype=torch.float32).contiguous()
         _ac_cache[key] = ac
     return ops.add_noise(x0.contiguous(), noise.contiguous(), ac, timesteps.to(device=x0.device, dtype=torch.int64))
+
+
+class B200UnCLIPScheduler:
+    """diffusers `UnCLIPScheduler` surface — the scheduler `Stage1_PriorPipeline` samples the stage-1 prior with
+    (/root/reference/src/pipelines/stage1_prior_pipeline.py:23,445-446,478-483; kandinsky-2-2-prior's
+    scheduler_config.json: squaredcos_cap_v2 betas, prediction_type "sample", variance_type "fixed_small_log",
+    clip_sample True with range 10).  Timesteps are spread evenly over [0, T-1] including both ends;
+    `step(model_output, timestep, sample, prev_timestep=None, generator=None, return_dict=True)` is the DDPM
+    posterior mean on the clipped x0 prediction plus "fixed_small_log" noise for t > 0.
+
+    The host derives the schedule-only scalars of each step with the published fp32 tensor arithmetic
+    (`step_coefficients`); the per-element update runs in `pcdm_unclip_step` / `pcdm_cfg_unclip_step`."""
+    order = 1
+    ROW = 8
+
+    def __init__(self, num_train_timesteps=1000, variance_type="fixed_small_log", clip_sample=True,
+                 clip_sample_range=1.0, prediction_type="epsilon", beta_schedule="squaredcos_cap_v2"):
+        if beta_schedule != "squaredcos_cap_v2":
+            raise ValueError("UnCLIPScheduler only supports `beta_schedule`: 'squaredcos_cap_v2'")
+        if variance_type != "fixed_small_log":
+            raise NotImplementedError("B200UnCLIPScheduler: variance_type 'fixed_small_log' only (no learned variance "
+                                      "on the reference path)")
+        if prediction_type not in ("sample", "epsilon"):
+            raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon` or `sample`")
+        self.config = _AttrDict(num_train_timesteps=num_train_timesteps, variance_type=variance_type,
+                                clip_sample=clip_sample, clip_sample_range=clip_sample_range,
+                                prediction_type=prediction_type, beta_schedule=beta_schedule)
+
+        def abar(x):
+            return math.cos((x + 0.008) / 1.008 * math.pi / 2) ** 2
+        n = num_train_timesteps
+        self.betas = torch.tensor([min(1 - abar((i + 1) / n) / abar(i / n), 0.999) for i in range(n)],
+                                  dtype=torch.float32)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, n)[::-1].copy())
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        keys = ("num_train_timesteps", "variance_type", "clip_sample", "clip_sample_range", "prediction_type",
+                "beta_schedule")
+        d = {k: config[k] for k in keys if k in config}
+        d.update(kw)
+        return cls(**d)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = (self.config.num_train_timesteps - 1) / (num_inference_steps - 1)
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts).to(device) if device is not None else torch.from_numpy(ts)
+
+    def step_coefficients(self, timestep, prev_timestep=None):
+        """The 8 floats of one `pcdm_unclip_step` row: {c_x0, c_xt, std, clip, sqrt(abar_t), sqrt(1 - abar_t),
+        prediction is epsilon, 0}."""
+        t = int(timestep)
+        prev_t = t - 1 if prev_timestep is None else int(prev_timestep)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        if prev_t == t - 1:
+            beta, alpha = self.betas[t], self.alphas[t]
+        else:
+            beta = 1 - a_t / a_prev
+            alpha = 1 - beta
+        c_x0 = (a_prev ** 0.5 * beta) / b_t
+        c_xt = alpha ** 0.5 * b_prev / b_t
+        std = 0.0
+        if t > 0:
+            std = float(torch.exp(0.5 * torch.log(torch.clamp(b_prev / b_t * beta, min=1e-20))))
+        clip = float(self.config.clip_sample_range) if self.config.clip_sample else float("inf")
+        return (float(c_x0), float(c_xt), std, clip, float(a_t ** 0.5), float(b_t ** 0.5),
+                1.0 if self.config.prediction_type == "epsilon" else 0.0, 0.0)
+
+    def coefficient_table(self, device):
+        """[num_inference_steps, 8] fp32 device table for the fused per-step kernel (prev_timestep = the next entry of
+        `timesteps`, None on the last step: stage1_prior_pipeline.py:473-476)."""
+        ts = self.timesteps.tolist()
+        rows = [self.step_coefficients(t, ts[i + 1] if i + 1 < len(ts) else None) for i, t in enumerate(ts)]
+        return torch.tensor(rows, dtype=torch.float32, device=device).contiguous()
+
+    def step(self, model_output, timestep, sample, prev_timestep=None, generator=None, return_dict: bool = True):
+        if not sample.is_cuda:
+            raise RuntimeError("B200UnCLIPScheduler.step runs on CUDA tensors only (no CPU fallback)")
+        row = self.step_coefficients(timestep, prev_timestep)
+        noise = None
+        if row[2] != 0.0:
+            noise = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        prev = ops.unclip_step(model_output.contiguous(), sample.contiguous(), noise, row)
+        if not return_dict:
+            return (prev,)
+        return SimpleNamespace(prev_sample=prev)
+
+    def __len__(self):
+        return self.config.num_train_timesteps

@@ -178,6 +178,38 @@ def unipc_step(model_output, sample, last_sample, m0, m1, coef_row, out=None):
     return xn.reshape(shp).to(sample.dtype)
 
 
+def _unclip_update(r, mo, x, noise):
+    """include/pcdm_b200.h, pcdm_unclip_step: fp32, the reference's operation order."""
+    r = [torch.tensor(v, dtype=torch.float32) for v in r]
+    x0 = mo
+    if float(r[6]) != 0.0:
+        x0 = (x - r[5] * mo) / r[4]
+    x0 = torch.clamp(x0, -r[3], r[3])
+    xp = r[0] * x0 + r[1] * x
+    if float(r[2]) != 0.0:
+        xp = xp + r[2] * noise
+    return xp
+
+
+def cfg_unclip_step(pred, latents, xin, coef_table, noise_table, step_counter, guidance_scale, use_cfg, t_table=None,
+                    t_cur=None):
+    n = latents.shape[0]
+    step = int(step_counter[0])
+    mo = pred[:n]
+    if use_cfg:
+        mo = mo + guidance_scale * (pred[n:] - mo)
+    latents.copy_(_unclip_update(coef_table[step].tolist(), mo, latents, noise_table[step]))
+    xin.copy_(torch.cat([latents, latents]) if use_cfg else latents)
+    step_counter[0] = step + 1
+    if t_table is not None and t_cur is not None:
+        t_cur[0] = t_table[step + 1]
+
+
+def unclip_step(model_output, sample, noise, coef_row, out=None):
+    return _unclip_update(coef_row, model_output.float(), sample.float(),
+                          None if noise is None else noise.float()).to(sample.dtype)
+
+
 def softmax_rows(x, scale, dtype, out=None):
     y = torch.softmax(x.float() * scale, dim=-1).to(dtype)
     if out is not None:
@@ -200,7 +232,7 @@ def ensure_workspace(device, nbytes=0):
 
 _NAMES = ["ensure_workspace", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
           "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step", "cfg_unipc_step",
-          "unipc_step", "softmax_rows", "gaussian_sample"]
+          "unipc_step", "softmax_rows", "gaussian_sample", "cfg_unclip_step", "unclip_step"]
 
 
 @contextlib.contextmanager

@@ -9,6 +9,9 @@ Fixtures (tiny topology-preserving config so the files stay small):
                         the reference hard-codes them; DDIM, 4 steps, guidance 2.0, 2 images per prompt)
   ref_stage3_tiny.pt    inputs + final latents of Stage3_RefinedPipeline.__call__ (fp16 loop tensors, fp32 UNet; DDIM)
   ref_demo_tiny.pt      inputs + final latents of PCDMsPipeline.__call__ (the pcdms_demo.ipynb driver; fp16; DDIM)
+  ref_prior_tiny.pt     inputs + outputs of Stage1_PriorTransformer.forward (plain and test_flag) and of
+                        Stage1_PriorPipeline.__call__ (fp32, 4 UnCLIP steps, guidance 0 as the batch-test driver) with
+                        the variance noise the global generator produced
   ref_image_proj.pt     state dict + input + output of the reference's ImageProjModel_p class
                         (stage2_batchtest_inpaint_model.py:48-66), at a reduced width
 """
@@ -75,6 +78,28 @@ def main():
     outd = rs.run_reference_demo_pipeline(cfgd, ud, **kwd)
     torch.save({"seed": 9, "inputs": kwd, "latents": outd}, GOLD / "ref_demo_tiny.pt")
     print("ref_demo_tiny", outd.shape, outd.dtype)
+
+    from oracle.prior import TINY, make_prior, make_prior_inputs
+    op = make_prior(seed=13, **TINY)
+    rp = rs.build_reference_prior(**TINY)
+    rp.load_state_dict(op.state_dict(), strict=True)
+    pi = make_prior_inputs(n=1, seed=17, steps=4)
+    x, x2 = pi["latents"][:, None], torch.cat([pi["latents"], pi["latents"]])[:, None]
+    e2 = torch.cat([torch.zeros_like(pi["s_embed"]), pi["s_embed"]])
+    with torch.no_grad():
+        fwd = rp(x, 500, pi["s_embed"], pi["s_pose"], pi["t_pose"]).predicted_image_embedding
+        fwd_flag = rp(x2, torch.tensor(37), e2, pi["s_pose"], pi["t_pose"], test_flag=True).predicted_image_embedding
+    # the reference draws each step's variance noise from the global generator: record what it drew (same seed, same
+    # shapes, same order) so that the fixture carries it
+    torch.manual_seed(23)
+    drawn = torch.stack([torch.randn(1, 1024) for _ in range(3)] + [torch.zeros(1, 1024)])   # last step adds none
+    torch.manual_seed(23)
+    emb, zero = rs.run_reference_prior_pipeline(rp, s_embed=pi["s_embed"], s_pose=pi["s_pose"], t_pose=pi["t_pose"],
+                                                latents=pi["latents"], num_inference_steps=4, guidance_scale=0,
+                                                zero_embed=torch.zeros(1, 1024))
+    torch.save({"seed": 13, "input_seed": 17, "forward": fwd, "forward_test_flag": fwd_flag, "steps": 4,
+                "variance_noise": drawn, "image_embeds": emb}, GOLD / "ref_prior_tiny.pt")
+    print("ref_prior_tiny", emb.shape, float(emb.std()))
 
     import ast
     path = "/root/reference/stage2_batchtest_inpaint_model.py"
