@@ -60,6 +60,9 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
  * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
 int pcdm_set_gemm_cta_group(int mode);
 int pcdm_set_gemm_max_stages(int n); /* experiment hook: cap the smem ring depth (2..8, default 8 = as deep as fits) */
+int pcdm_set_gemm_debug(int mask);   /* experiment hook: switch parts of the kernel off for timing (results WRONG while
+                                      * non-zero): 1 no TMA stores, 2 no residual, 4 no bias/rowvec, 8 no epilogue body,
+                                      * 16 no MMAs */
 
 /* Caller-owned fp32 scratch for pcdm_gemm / pcdm_conv3x3 split-K (used for tile-starved shapes: few output tiles, long
  * K — the 4x8 and 8x16 UNet levels): process-wide, single-stream use; must outlive every launch (and every captured

@@ -158,7 +158,10 @@ __device__ __forceinline__ double2 ld_dsmem_f64x2(uint32_t cluster_addr) {
   return make_double2(a, b);
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): what this arrive hands over
+  // lives in TMEM and is ordered by the tcgen05 fences either side; `.release.cluster` cost a MEMBAR.ALL.GPU + ERRBAR
+  // per epilogue warp per tile (11 % of the samples of a short-K GEMM, profiles/r1_s3_shortk_gemm.md)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair whose completion bytes are credited to a barrier in the LEADER CTA
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

@@ -23,6 +23,7 @@ namespace pcdm {
 constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
 constexpr int IG_EPI_WARPS = 8;
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
+constexpr int IG_RES_SLOTS = 4;        // residual slots per epilogue warp: the chunks one warp owns in a <= 256-wide tile
 constexpr int IG_MAX_STAGES = 8;
 
 struct IGemmParams {
@@ -42,12 +43,15 @@ struct IGemmParams {
   int splits;      // split-K factor (1 = off): tile index also enumerates the K slice; partials go to fp32 scratch
   int kb_per_split;
   int stages;      // smem ring depth (runtime: depends on BN and on whether residual staging is needed)
-  int nbuf;        // staging slots per epilogue warp (2, or 3 with a residual: one slot is being prefetched)
+  int nbuf;        // staging slots per epilogue warp (2; 4 with a residual: one per 32-column chunk a warp owns in a
+                   // tile, so the whole residual tile is in flight while the tile's MMAs run)
   const float* bias;
   const float* rowvec;
   long long ld_rowvec;
   int hw;          // rows per image for rowvec indexing
   int has_res;
+  int dbg;         // experiment mask (pcdm_set_gemm_debug; results are WRONG when non-zero): 1 no TMA stores, 2 no
+                   // residual, 4 no bias / rowvec, 8 epilogue body skipped, 16 no MMAs
   void* out;       // only dereferenced for fp32 output
   long long ldo;
   int geglu;
@@ -66,6 +70,16 @@ struct IGemmCfg {
 
 // byte offset of 16-byte chunk j of row r inside a [rows x 64 B] tile written with the TMA 64-byte swizzle
 __device__ __forceinline__ uint32_t sw64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+// staging-slot accesses in the shared state space proper (a generic ST/LD to shared memory made the compiler put a
+// MEMBAR.ALL.CTA in front of every fence.proxy.async, and 64-bit address arithmetic around every access)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 u) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA loads its own 128 activation rows and HALF of the weight tile, the leader CTA issues the M = 256 MMAs, each
@@ -80,8 +94,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   uint64_t* empty = full + IG_MAX_STAGES;
   uint64_t* tfull = empty + IG_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* res_bar = tempty + 2;                 // [IG_EPI_WARPS][3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + IG_EPI_WARPS * 3);
+  uint64_t* res_bar = tempty + 2;                 // [IG_EPI_WARPS][IG_RES_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + IG_EPI_WARPS * IG_RES_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], IG_EPI_WARPS * CG);
     }
-    for (int i = 0; i < IG_EPI_WARPS * 3; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < IG_EPI_WARPS * IG_RES_SLOTS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           const uint32_t a_lo = desc_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
           const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 4 && !(p.dbg & 16); ++k) {
             const uint64_t da = ((uint64_t)kDescHi << 32) | (a_lo + 2u * k);   // +32 B per k16 inside the swizzle atom
             const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + 2u * k);
             if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
@@ -278,8 +292,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     const int half = e >> 2;
     const int row = q * 32 + lane;
     uint8_t* slots = epi_smem + e * p.nbuf * IG_SLOT_BYTES;
-    uint64_t* rbar = res_bar + e * 3;
-    uint32_t cnt = 0;         // chunks staged by this warp so far (slot rotation + residual barrier parity)
+    const uint32_t slots_s = smem_u32(slots);
+    uint64_t* rbar = res_bar + e * IG_RES_SLOTS;
+    uint32_t cnt = 0;         // chunks staged by this warp so far (slot rotation when there is no residual)
+    uint32_t rphase = 0;      // bit i: parity of the next completion of residual barrier i
     int acc = 0;
     uint32_t acc_phase = 0;
     const int nbuf = p.nbuf;
@@ -338,38 +354,40 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         }
       } else if (!p.geglu) {
         // ---- 16-bit output: TMEM -> registers -> (+bias, +rowvec, +residual, act) -> swizzled smem slot -> TMA store.
-        //      The residual chunk is TMA-prefetched into the slot one chunk ahead. ----
-        if (p.has_res && half * 32 < cols_here) {
+        //      ALL residual chunks this warp owns in the tile are TMA-prefetched (one slot each) before the wait for the
+        //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
+        //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
+        const bool use_res = p.has_res && !(p.dbg & 2);
+        if (use_res) {
           if (lane == 0) {
-            bulk_wait_read<1>();
-            const uint32_t slot = cnt % nbuf;
-            mbar_expect_tx(&rbar[slot], IG_SLOT_BYTES);
-            tma_load_2d(slots + slot * IG_SLOT_BYTES, &p.tmRes, &rbar[slot], n_tile0 + half * 32, m_warp0);
+            bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
+            int i = 0;
+            for (int c = half; c * 32 < cols_here; c += 2, ++i) {
+              mbar_expect_tx(&rbar[i], IG_SLOT_BYTES);
+              tma_load_2d(slots + i * IG_SLOT_BYTES, &p.tmRes, &rbar[i], n_tile0 + c * 32, m_warp0);
+            }
           }
         }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        int ci = 0;
 #pragma unroll 1
-        for (int c = half; c * 32 < cols_here; c += 2) {
+        for (int c = half; c * 32 < cols_here && !(p.dbg & 8); c += 2, ++ci) {
           const int n0 = n_tile0 + c * 32;
-          const uint32_t slot = cnt % nbuf;
+          const uint32_t slot = use_res ? (uint32_t)ci : (cnt & (uint32_t)(nbuf - 1));   // nbuf is 2 or 4
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
-          if (lane == 0) {
-            bulk_wait_read<1>();   // every store but the most recent has finished reading its slot
-            if (p.has_res && (c + 2) * 32 < cols_here) {
-              const uint32_t ns = (cnt + 1) % nbuf;
-              mbar_expect_tx(&rbar[ns], IG_SLOT_BYTES);
-              tma_load_2d(slots + ns * IG_SLOT_BYTES, &p.tmRes, &rbar[ns], n0 + 64, m_warp0);
-            }
+          const uint32_t sl_s = slots_s + slot * IG_SLOT_BYTES;
+          if (!use_res) {
+            if (lane == 0) bulk_wait_read<1>();   // every store but the most recent has finished reading its slot
+            __syncwarp();
           }
-          __syncwarp();
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tc_wait_ld();
           float2 v[16];   // column pairs, packed fp32 (FFMA2 path)
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          if (p.bias) {
+          if (p.bias && !(p.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
           }
-          if (rv) {
+          if (rv && !(p.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
@@ -385,11 +403,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
           }
-          if (p.has_res) {
-            mbar_wait(&rbar[slot], (cnt / nbuf) & 1);
+          if (use_res) {
+            mbar_wait(&rbar[slot], (rphase >> slot) & 1u);
+            rphase ^= 1u << slot;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(sl + sw64(lane, j));
+              const uint4 u = lds128(sl_s + sw64(lane, j));
               v[j * 4 + 0] = __fadd2_rn(v[j * 4 + 0], unpack2<DT>(u.x));
               v[j * 4 + 1] = __fadd2_rn(v[j * 4 + 1], unpack2<DT>(u.y));
               v[j * 4 + 2] = __fadd2_rn(v[j * 4 + 2], unpack2<DT>(u.z));
@@ -410,11 +429,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             u.y = pack2<DT>(v[j * 4 + 1].x, v[j * 4 + 1].y);
             u.z = pack2<DT>(v[j * 4 + 2].x, v[j * 4 + 2].y);
             u.w = pack2<DT>(v[j * 4 + 3].x, v[j * 4 + 3].y);
-            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = u;
+            sts128(sl_s + sw64(lane, j), u);
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 1)) {
             tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
             bulk_commit();
           }
@@ -427,8 +446,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll 1
         for (int c = half; c * 64 < cols_here; c += 2) {
           const int n0 = n_tile0 + c * 64;
-          const uint32_t slot = cnt % nbuf;
+          const uint32_t slot = cnt & (uint32_t)(nbuf - 1);
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
+          const uint32_t sl_s = slots_s + slot * IG_SLOT_BYTES;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
           uint32_t rh[32], rg[32];
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(sl + sw64(lane, j)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+            sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -545,7 +565,8 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
 // host side
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_SMEM_LIMIT = 227 * 1024;
-static int g_max_stages = IG_MAX_STAGES;  // tuning hook: cap on the smem ring depth (pcdm_set_gemm_max_stages)
+static int g_max_stages = IG_MAX_STAGES;
+static int g_gemm_dbg = 0;                // experiment mask (pcdm_set_gemm_debug)  // tuning hook: cap on the smem ring depth (pcdm_set_gemm_max_stages)
 
 template <int BN, int DT, int CG>
 static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
@@ -555,7 +576,8 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
     PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
     configured = true;
   }
-  p.nbuf = p.has_res ? 3 : 2;
+  p.nbuf = p.has_res ? IG_RES_SLOTS : 2;
+  p.dbg = g_gemm_dbg;
   const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
   if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
@@ -839,5 +861,12 @@ extern "C" int pcdm_set_workspace(void* ptr, long long bytes) {
 extern "C" int pcdm_set_gemm_max_stages(int n) {
   if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
   g_max_stages = n;
+  return 0;
+}
+
+/* experiment hook (tools/dev_epilogue.py): switch parts of the GEMM/conv kernel off to see what paces it.  Results are
+ * wrong while the mask is non-zero.  1 no TMA stores, 2 no residual, 4 no bias / rowvec, 8 no epilogue body, 16 no MMAs */
+extern "C" int pcdm_set_gemm_debug(int mask) {
+  g_gemm_dbg = mask;
   return 0;
 }

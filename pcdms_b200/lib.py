@@ -46,13 +46,16 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = LIB_PATH
+    if os.environ.get("PCDM_B200_LIB"):   # A/B hook for tools/: another build of the same library (never a fallback)
+        path = Path(os.environ["PCDM_B200_LIB"])
+    elif not LIB_PATH.exists():
         if not build_if_missing:
             raise FileNotFoundError(f"{LIB_PATH} not built; run python -m pcdms_b200.build")
         from . import build as _build
 
         _build.build()
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     lib.pcdm_last_error.restype = C.c_char_p
     lib.pcdm_abi_version.restype = C.c_int
     lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong

@@ -1,5 +1,6 @@
 """Enumerate every distinct conv / GEMM problem of one UNet evaluation (BASELINE config 2: B=16, 32x64, 258 tokens, bf16)
-and time it under each (bn, cta_group) variant plus the automatic choice.  Output: gpurun_out/autotune.json."""
+and time it under each (bn, cta_group) variant plus the automatic choice.  Output: gpurun_out/autotune.json.
+`python tools/autotune.py auto [out.json]` times only the automatic choice (A/B runs of a kernel change)."""
 import json
 import sys
 sys.path.insert(0, ".")
@@ -41,6 +42,8 @@ def timeit(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3  # us
 
+AUTO_ONLY = len(sys.argv) > 1 and sys.argv[1] == "auto"
+OUT = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/autotune.json"
 res = []
 tot_auto = tot_best = 0.0
 for key, (count, (a, wt, k)) in sorted(shapes.items(), key=lambda kv_: str(kv_[0])):
@@ -50,7 +53,7 @@ for key, (count, (a, wt, k)) in sorted(shapes.items(), key=lambda kv_: str(kv_[0
     row = {"key": str(key), "count": count, "auto_us": timeit(lambda: fn0(0))}
     best = ("auto", row["auto_us"])
     N = wt.shape[0]
-    for cg in (1, 2):
+    for cg in (() if AUTO_ONLY else (1, 2)):
         L.pcdm_set_gemm_cta_group(cg)
         for bn in (64, 128, 160, 256):
             if cg == 2 and bn < 128: continue
@@ -69,4 +72,4 @@ for key, (count, (a, wt, k)) in sorted(shapes.items(), key=lambda kv_: str(kv_[0
     res.append(row)
     print(json.dumps(row), flush=True)
 print("TOTAL auto us", tot_auto, "best us", tot_best)
-json.dump(res, open("gpurun_out/autotune.json", "w"), indent=1)
+json.dump(res, open(OUT, "w"), indent=1)
