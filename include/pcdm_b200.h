@@ -56,10 +56,24 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
               long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
               const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn, void* stream);
 
+/* torch.nn.LayerNorm(K, eps) followed by torch.nn.Linear, as one call:
+ *   out = act( LN(x[M, K]; gamma, beta, eps) . W[N, K]^T + bias + rowvec + residual )
+ * (norm1 -> to_q/to_k/to_v and norm3 -> ff.net.0 of the stage-1 prior's BasicTransformerBlocks,
+ * src/models/stage1_prior_transformer.py:112-120,283-289; norm_out -> proj_to_clip_embeddings, :286-290).  With M <= 32
+ * rows (K <= 2048, M * (K + 8) * 2 <= 100 KB) it is ONE launch: the skinny kernel normalises the rows itself, rounding them to the
+ * 16-bit dtype exactly as pcdm_layernorm stores them.  Otherwise pcdm_layernorm -> scratch ([M, K] 16-bit, caller-owned,
+ * may be NULL only when the fused path applies) -> pcdm_gemm.  flags as pcdm_gemm without PCDM_FLAG_GEGLU. */
+int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
+                 const void* w, void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
+                 int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags,
+                 void* stream);
+
 /* Tuning / test hook for the two calls above: 0 = automatic, 1 = single-CTA 128-row tiles only, 2 = CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
 int pcdm_set_gemm_cta_group(int mode);
 int pcdm_set_gemm_max_stages(int n); /* experiment hook: cap the smem ring depth (2..8, default 8 = as deep as fits) */
+int pcdm_set_skinny_gemm(int enabled); /* 1 (default): pcdm_gemm with M <= 32 rows (no GEGLU, one K segment, bn = 0) runs
+                                        * the weight-streaming skinny kernel (skinny.cu); 0: always the tcgen05 tiles */
 int pcdm_set_gemm_debug(int mask);   /* experiment hook: switch parts of the kernel off for timing (results WRONG while
                                       * non-zero): 1 no TMA stores, 2 no residual, 4 no bias/rowvec, 8 no epilogue body,
                                       * 16 no MMAs */
@@ -103,6 +117,7 @@ int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const f
  * F.scaled_dot_product_attention behind diffusers' attention processors (stage2_batchtest_inpaint_model.py:133;
  * SURVEY.md §8a a9).  q: element (b, s, h, d) at q[(b*Sq + s)*ldq + h*64 + d]; k, v likewise with Skv; out likewise
  * with ldo — so q/k/v may be column slices of one fused projection buffer. */
+int pcdm_set_attention_small(int on); /* 1 (default): Sq, Skv <= 32 at head_dim 64 run the one-warp-per-head kernel; 0: tcgen05 */
 int pcdm_set_attention_poly(int on); /* experiment hook: 1 = half of the softmax exp2 on the FMA pipe (default 0: measured slower) */
 int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);

@@ -328,6 +328,76 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short sequences (Sq, Skv <= 32; head_dim 64): the six-token sequence of the stage-1 prior
+// (/root/reference/src/models/stage1_prior_transformer.py:262-285).  A 128-row tcgen05 tile would be > 95 % padding and
+// its set-up (TMEM allocation, tensor maps, barrier ring) is pure latency in a chain of launch-bound kernels, so this is
+// plain CUDA-core code: one warp per (batch, head).  Lane s owns key row s (its 64 channels in registers) and computes
+// the score of every query against it; softmax statistics are warp reductions (fixed xor order); then lane j owns
+// output channels 2j, 2j+1 and accumulates sum_s p_s V[s] with p_s broadcast by shuffle.  fp32 throughout; P is NOT
+// rounded to 16 bits here (closer to the fp32 reference than the tensor-core kernel).
+template <int DT>
+__global__ void __launch_bounds__(128) attention_small_kernel(const void* __restrict__ q, long long ldq,
+                                                             const void* __restrict__ k, long long ldk,
+                                                             const void* __restrict__ v, long long ldv,
+                                                             void* __restrict__ out, long long ldo, int B, int heads,
+                                                             int Sq, int Skv, float scale_log2) {
+  using T = typename TypeOf<DT>::T;
+  __shared__ __align__(16) uint32_t sq[4][32][32];   // per warp: the query rows, 64 channels as 32 packed pairs
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 4 + warp;
+  pdl_wait();
+  if (bh >= B * heads) return;
+  const int h = bh % heads, b = bh / heads;
+  const T* qp = reinterpret_cast<const T*>(q) + (long long)b * Sq * ldq + h * 64;
+  const T* kp = reinterpret_cast<const T*>(k) + (long long)b * Skv * ldk + h * 64;
+  const T* vp = reinterpret_cast<const T*>(v) + (long long)b * Skv * ldv + h * 64;
+  T* op = reinterpret_cast<T*>(out) + (long long)b * Sq * ldo + h * 64;
+  for (int i = 0; i < Sq; ++i) sq[warp][i][lane] = *reinterpret_cast<const uint32_t*>(qp + (long long)i * ldq + 2 * lane);
+  uint4 kr[8];                                       // key row `lane`: 64 channels
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    kr[j] = lane < Skv ? *reinterpret_cast<const uint4*>(kp + (long long)lane * ldk + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+  uint32_t vr[32];                                   // value channels 2*lane, 2*lane+1 of every kv row
+#pragma unroll
+  for (int s2 = 0; s2 < 32; ++s2)
+    vr[s2] = s2 < Skv ? *reinterpret_cast<const uint32_t*>(vp + (long long)s2 * ldv + 2 * lane) : 0u;
+  __syncwarp();
+  for (int i = 0; i < Sq; ++i) {
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 qq = *reinterpret_cast<const uint4*>(&sq[warp][i][4 * j]);   // broadcast read
+      const uint32_t qa[4] = {qq.x, qq.y, qq.z, qq.w}, ka[4] = {kr[j].x, kr[j].y, kr[j].z, kr[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack2<DT>(qa[e]), c = unpack2<DT>(ka[e]);
+        dot = fmaf(a.x, c.x, dot);
+        dot = fmaf(a.y, c.y, dot);
+      }
+    }
+    const float sc = lane < Skv ? dot * scale_log2 : -INFINITY;
+    float mx = sc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float pr = lane < Skv ? exp2f(sc - mx) : 0.f;
+    float sum = pr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s2 = 0; s2 < 32; ++s2) {
+      const float ps = __shfl_sync(0xffffffffu, pr, s2);
+      const float2 vv = unpack2<DT>(vr[s2]);
+      acc.x = fmaf(ps, vv.x, acc.x);
+      acc.y = fmaf(ps, vv.y, acc.y);
+    }
+    const float inv = 1.0f / sum;
+    *reinterpret_cast<uint32_t*>(op + (long long)i * ldo + 2 * lane) = pack2<DT>(acc.x * inv, acc.y * inv);
+  }
+}
+
 }  // namespace pcdm
 
 using namespace pcdm;
@@ -340,6 +410,11 @@ static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, i
   return make_tmap(m, base, 4, dims, strides, box);
 }
 
+static int g_att_small = 1;  // 0: short sequences also take the tcgen05 kernel (A/B hook)
+extern "C" int pcdm_set_attention_small(int on) {
+  g_att_small = on ? 1 : 0;
+  return 0;
+}
 static int g_att_poly = 0;   // 1: half of the exp2 on the FMA pipe (experiment hook; measured slower, see the kernel)
 extern "C" int pcdm_set_attention_poly(int on) {
   g_att_poly = on ? 1 : 0;
@@ -362,6 +437,18 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "attention: bad dtype");
   if (B <= 0 || heads <= 0 || Sq <= 0 || Skv <= 0) return set_error(PCDM_ERR_INVALID, "attention: empty problem");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error(PCDM_ERR_UNSUPPORTED, "attention: strides must be multiples of 8");
+  if (g_att_small && head_dim == 64 && Sq <= 32 && Skv <= 32) {   // short sequences: CUDA-core kernel, one warp per (batch, head)
+    const int grid_s = (B * heads + 3) / 4;
+    const float sl2 = scale * 1.4426950408889634f;
+    if (dtype == DT_F16)
+      PCDM_CUDA(launch_kernel(attention_small_kernel<DT_F16>, dim3(grid_s), dim3(128), 0, stream, 1, q, ldq, k, ldk, v,
+                              ldv, out, ldo, B, heads, Sq, Skv, sl2));
+    else
+      PCDM_CUDA(launch_kernel(attention_small_kernel<DT_BF16>, dim3(grid_s), dim3(128), 0, stream, 1, q, ldq, k, ldk, v,
+                              ldv, out, ldo, B, heads, Sq, Skv, sl2));
+    PCDM_CUDA(cudaGetLastError());
+    return 0;
+  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and

@@ -741,6 +741,13 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
 
 }  // namespace pcdm
 
+namespace pcdm {
+int skinny_gemm_try(const void* a, long long lda, const void* w, void* out, long long ldo, const float* bias,
+                    const float* rowvec, long long ld_rowvec, int rows_per_image, const void* residual, long long ldr,
+                    int M, int N, int K, int dtype, int flags, cudaStream_t stream, const float* ln_gamma,
+                    const float* ln_beta, float ln_eps);   // skinny.cu
+}
+
 using namespace pcdm;
 
 extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w,
@@ -756,6 +763,11 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
   const bool geglu = flags & PCDM_FLAG_GEGLU;
   if (geglu && (N % 64)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU needs N % 64 == 0");
   if ((lda % 8) || (ldo % 8) || (residual && (ldr % 8))) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: strides must be multiples of 8");
+  if (!a2 && bn == 0) {   // M <= 32 activation rows: a weight stream, not a 128-row tile problem (skinny.cu)
+    const int taken = skinny_gemm_try(a, lda, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N,
+                                      K, dtype, flags, stream, nullptr, nullptr, 0.f);
+    if (taken != 0) return taken < 0 ? taken : 0;
+  }
   IGemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.num_kb = K / 64;
@@ -869,4 +881,27 @@ extern "C" int pcdm_set_gemm_max_stages(int n) {
 extern "C" int pcdm_set_gemm_debug(int mask) {
   g_gemm_dbg = mask;
   return 0;
+}
+
+/* LayerNorm over K fused in front of a GEMM: out = act( LN(x; gamma, beta, eps) . W^T + bias + rowvec + residual ).
+ * For M <= 32 rows that fit (K <= 2048, M * (K + 8) * 2 <= 100 KB) this is ONE launch of the skinny kernel, which normalises the
+ * rows itself; otherwise pcdm_layernorm writes the normalised rows to `scratch` ([M, K] 16-bit, row stride K) and
+ * pcdm_gemm follows. */
+extern "C" int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
+                            const void* w, void* out, long long ldo, const float* bias, const float* rowvec,
+                            long long ld_rowvec, int rows_per_image, const void* residual, long long ldr, int M, int N,
+                            int K, int dtype, int flags, void* stream_) {
+  if (!x || !gamma || !beta || !w || !out) return set_error(PCDM_ERR_INVALID, "ln_gemm: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "ln_gemm: dtype must be 0 (f16) or 1 (bf16)");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(PCDM_ERR_INVALID, "ln_gemm: empty problem");
+  if (K % 64 || N % 32) return set_error(PCDM_ERR_UNSUPPORTED, "ln_gemm: K must be a multiple of 64 and N of 32");
+  if ((ldx % 8) || (ldo % 8) || (residual && (ldr % 8))) return set_error(PCDM_ERR_UNSUPPORTED, "ln_gemm: strides must be multiples of 8");
+  const int taken = skinny_gemm_try(x, ldx, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N, K,
+                                    dtype, flags, (cudaStream_t)stream_, gamma, beta, eps);
+  if (taken != 0) return taken < 0 ? taken : 0;
+  if (!scratch) return set_error(PCDM_ERR_INVALID, "ln_gemm: this shape needs the scratch buffer");
+  const int rc = pcdm_layernorm(x, ldx, scratch, K, gamma, beta, eps, M, K, dtype, stream_);
+  if (rc != 0) return rc;
+  return pcdm_gemm(scratch, K, nullptr, 0, 0, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N,
+                   K, dtype, flags, 0, stream_);
 }

@@ -96,6 +96,29 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     return out
 
 
+def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_per_image=1, residual=None,
+            out_f32=False, silu=False, gelu=False):
+    """out[M, N] = act(LayerNorm(x[M, K]; gamma, beta, eps) @ w[N, K]^T (+bias) (+rowvec) (+residual)) — one launch for
+    M <= 32 rows (the skinny kernel normalises the rows itself), otherwise pcdm_layernorm + pcdm_gemm inside the call."""
+    lib = _l.load()
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x.stride(1) == 1 and w.is_contiguous()
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    scratch = None if M <= 32 and K <= 2048 and M * (K + 8) * 2 <= 100 * 1024 else torch.empty((M, K), device=x.device, dtype=x.dtype)
+    flags = ((_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_GELU if gelu else 0))
+    rc = lib.pcdm_ln_gemm(
+        _l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)), C.c_float(eps), _l.ptr(scratch),
+        _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
+        C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), C.c_int(rows_per_image), _l.ptr(residual),
+        C.c_longlong(residual.stride(0) if residual is not None else 0), C.c_int(M), C.c_int(N), C.c_int(K),
+        C.c_int(_dt(x)), C.c_int(flags), _stream(x))
+    _l.check(rc, kernels=1 if scratch is None else 2)
+    return out
+
+
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
             pad_br=False, bn=0):
     """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout].

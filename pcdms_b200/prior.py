@@ -6,8 +6,11 @@ as driven by /root/reference/stage1_batchtest_prior_model.py:57-113.
 The prior denoises ONE CLIP image embedding (1024 values) with a 20-block transformer over six tokens —
 [source pose, target pose, source-image embedding, timestep, noisy embedding, learned query] — so a step is ~1.0 G
 weight parameters streamed against 6 (12 under CFG) activation rows: weight-bandwidth work.  Everything runs through
-the C ABI: the q/k/v projections as one GEMM, bias / GELU / residual in the GEMM epilogues, LayerNorm, the d = 64
-attention kernel over the 6 tokens, the positional embedding added in the epilogue of whichever GEMM produces a token
+the C ABI: with 6-12 rows every linear layer is a weight stream — `pcdm_gemm` routes them to the skinny mma.sync kernel
+(16 weight rows per CTA, weights requested before the programmatic-dependency wait so that they stream in under the
+previous kernel); the q/k/v projections are one GEMM, bias / GELU / residual live in its epilogue, attention over the 6
+tokens is a one-warp-per-head kernel (a LayerNorm-in-front-of-the-GEMM variant, `pcdm_ln_gemm`, exists but measured
+slower and is off by default), the positional embedding added in the epilogue of whichever GEMM produces a token
 (`rowvec`), the UnCLIP scheduler step fused with the CFG combine (`pcdm_cfg_unclip_step`).  Step-invariant tokens
 (both poses, the source embedding, the query) are computed once per call; the loop is one CUDA graph replayed
 `num_inference_steps` times (device-side step counter, as the stage-2 engine).  Only the last token reaches the output
@@ -44,7 +47,17 @@ class _NoopProcessor:
     `enable_xformers_memory_efficient_attention` (stage1_batchtest_prior_model.py:59) are harmless."""
 
 
+def _ln_then_gemm(x, gamma, beta, eps, w, **kw):
+    """A/B path (`fuse_layernorm = False`): the LayerNorm as its own launch."""
+    return ops.gemm(ops.layernorm(x, gamma, beta, eps), w, **kw)
+
+
 class B200Stage1PriorTransformer:
+    # LayerNorm fused in front of the consuming GEMM (pcdm_ln_gemm: 106 instead of 147 launches per step) measured
+    # SLOWER on B200 (1.18 vs 0.94 ms per step, profiles/r1_s3_prior_ab.md): every CTA of the GEMM re-normalises the
+    # rows on its critical path, behind the dependency wait.  Kept as an option; tools/bench_stage1.py flips it.
+    fuse_layernorm = os.environ.get("PCDM_PRIOR_FUSE_LN", "0") != "0"
+
     def __init__(self, dtype: torch.dtype = torch.float16, device="cuda", **kw):
         cfg = dict(_DEFAULT_CONFIG)
         cfg.update({k: v for k, v in kw.items() if k in cfg})
@@ -303,17 +316,17 @@ class B200Stage1PriorTransformer:
                  rowvec=pos[3:4], rows_per_image=B)
         ops.gemm(x_rows, w["proj_in.weight"], out=tok[:, 4], bias=w["proj_in.bias"], rowvec=pos[4:5], rows_per_image=B)
         x = tok.view(B * 6, C)
+        ln_gemm = ops.ln_gemm if self.fuse_layernorm else _ln_then_gemm
         for i in range(c.num_layers):
-            n = ops.layernorm(x, w[f"{i}.norm1.weight"], w[f"{i}.norm1.bias"], 1e-5)
-            qkv = ops.gemm(n, w[f"{i}.qkv.weight"], bias=w[f"{i}.qkv.bias"])
+            qkv = ln_gemm(x, w[f"{i}.norm1.weight"], w[f"{i}.norm1.bias"], 1e-5, w[f"{i}.qkv.weight"],
+                              bias=w[f"{i}.qkv.bias"])
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
             x = ops.gemm(att, w[f"{i}.out.weight"], bias=w[f"{i}.out.bias"], residual=x)
-            n = ops.layernorm(x, w[f"{i}.norm3.weight"], w[f"{i}.norm3.bias"], 1e-5)
-            h = ops.gemm(n, w[f"{i}.ff1.weight"], bias=w[f"{i}.ff1.bias"], gelu=True)
+            h = ln_gemm(x, w[f"{i}.norm3.weight"], w[f"{i}.norm3.bias"], 1e-5, w[f"{i}.ff1.weight"],
+                            bias=w[f"{i}.ff1.bias"], gelu=True)
             x = ops.gemm(h, w[f"{i}.ff2.weight"], bias=w[f"{i}.ff2.bias"], residual=x)
-        last = ops.layernorm(x.view(B, 6, C)[:, 5], w["norm_out.weight"], w["norm_out.bias"], 1e-5)
-        return ops.gemm(last, w["proj_to_clip_embeddings.weight"], bias=w["proj_to_clip_embeddings.bias"],
-                        out_f32=out_f32)
+        return ln_gemm(x.view(B, 6, C)[:, 5], w["norm_out.weight"], w["norm_out.bias"], 1e-5,
+                           w["proj_to_clip_embeddings.weight"], bias=w["proj_to_clip_embeddings.bias"], out_f32=out_f32)
 
     def __call__(self, *a, **k):
         return self.forward(*a, **k)

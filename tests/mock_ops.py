@@ -43,6 +43,13 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     return y
 
 
+def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_per_image=1, residual=None,
+            out_f32=False, silu=False, gelu=False):
+    n = layernorm(x, gamma, beta, eps)
+    return gemm(n, w, out, bias=bias, rowvec=rowvec, rows_per_image=rows_per_image, residual=residual,
+                out_f32=out_f32, silu=silu, gelu=gelu)
+
+
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
             pad_br=False, bn=0):
     B, H, W, Cin = x.shape
@@ -230,7 +237,7 @@ def ensure_workspace(device, nbytes=0):
     return None
 
 
-_NAMES = ["ensure_workspace", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
+_NAMES = ["ensure_workspace", "gemm", "ln_gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
           "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step", "cfg_unipc_step",
           "unipc_step", "softmax_rows", "gaussian_sample", "cfg_unclip_step", "unclip_step"]
 

@@ -289,3 +289,108 @@ def test_softmax_rows(ops, dt, M, N):
     want = torch.softmax(x * scale, dim=-1)
     torch.testing.assert_close(got.float().cpu(), want, rtol=(2 ** -7 if dt == torch.bfloat16 else 2 ** -10), atol=1e-6)
     assert torch.equal(got, ops.softmax_rows(x.cuda(), scale, dt))
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N,K,kw", [
+    (6, 2048, 2048, {"resid": True}), (12, 6144, 2048, {}), (6, 8192, 2048, {"gelu": True}),
+    (6, 2048, 8192, {"resid": True}), (1, 2048, 1024, {"rowvec": True}), (8, 512, 64, {"gelu": True}),
+    (16, 1280, 320, {"silu": True}), (16, 20160, 1280, {"f32": True}), (24, 1024, 2048, {"f32": True, "bias": False}),
+    (32, 2048, 1024, {"resid": True, "rowvec": True}), (9, 64, 128, {}),
+])
+def test_skinny_gemm(ops, dt, M, N, K, kw):
+    """pcdm_gemm with M <= 32 rows: the weight-streaming mma.sync kernel (skinny.cu) against torch fp32 on the same 16-bit
+    inputs, against the tcgen05 tile path it replaces (pcdm_set_skinny_gemm(0)), through strided views, and run to run."""
+    import ctypes as C
+    from pcdms_b200 import lib
+    g = torch.Generator().manual_seed(M + N + K)
+    a_full = torch.randn(M, 3, K, generator=g).to(dt)              # rows taken as a strided view (token 1 of 3)
+    a = a_full[:, 1]
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt)
+    b = torch.randn(N, generator=g) if kw.get("bias", True) else None
+    r = torch.randn(M, N, generator=g).to(dt) if kw.get("resid") else None
+    rv = torch.randn(2, N, generator=g) if kw.get("rowvec") else None
+    rpi = (M + 1) // 2
+    ref = a.float() @ w.float().t()
+    if b is not None:
+        ref = ref + b
+    if rv is not None:
+        ref = ref + rv.repeat_interleave(rpi, 0)[:M]
+    if r is not None:
+        ref = ref + r.float()
+    if kw.get("silu"):
+        ref = F.silu(ref)
+    if kw.get("gelu"):
+        ref = F.gelu(ref)
+    ad = a_full.cuda()[:, 1]
+    assert ad.stride(0) == 3 * K
+    args = dict(bias=b.cuda() if b is not None else None, residual=r.cuda() if r is not None else None,
+                rowvec=rv.cuda() if rv is not None else None, rows_per_image=rpi, silu=bool(kw.get("silu")),
+                gelu=bool(kw.get("gelu")), out_f32=bool(kw.get("f32")))
+    out_buf = torch.zeros(M, 2 * N, device="cuda", dtype=torch.float32 if kw.get("f32") else dt)
+    before = lib.launch_count
+    out = ops.gemm(ad, w.cuda(), out=out_buf[:, :N], **args)
+    assert lib.launch_count == before + 1
+    assert out.dtype == (torch.float32 if kw.get("f32") else dt) and not out_buf[:, N:].any()
+    close(out, ref, dt)
+    assert torch.equal(out, ops.gemm(ad, w.cuda(), **args))            # bit-reproducible
+    if N % 32 == 0:                                                     # the tile path needs N % 32 == 0
+        L = lib.load()
+        L.pcdm_set_skinny_gemm(C.c_int(0))
+        try:
+            tiles = ops.gemm(ad, w.cuda(), **args)
+        finally:
+            L.pcdm_set_skinny_gemm(C.c_int(1))
+        close(out, tiles.float().cpu(), dt, mult=2.0)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,heads,Sq,Skv", [(1, 32, 6, 6), (2, 32, 6, 6), (3, 5, 32, 32), (2, 3, 1, 17), (1, 2, 20, 3)])
+def test_attention_short_sequences(ops, dt, B, heads, Sq, Skv):
+    """Sq, Skv <= 32 at head_dim 64: the one-warp-per-head CUDA-core kernel (the stage-1 prior's six tokens); q / k / v
+    are column slices of fused buffers."""
+    g = torch.Generator().manual_seed(B * 100 + Sq + Skv)
+    C_ = heads * 64
+    q = torch.randn(B * Sq, C_ + 64, generator=g).to(dt)
+    kv = torch.randn(B * Skv, 2 * C_, generator=g).to(dt)
+    q4 = q[:, :C_].float().view(B, Sq, heads, 64).transpose(1, 2)
+    k4 = kv[:, :C_].float().view(B, Skv, heads, 64).transpose(1, 2)
+    v4 = kv[:, C_:].float().view(B, Skv, heads, 64).transpose(1, 2)
+    want = (torch.softmax(q4 @ k4.transpose(-1, -2) * 0.125, -1) @ v4).transpose(1, 2).reshape(B * Sq, C_)
+    qd, kvd = q.cuda(), kv.cuda()
+    got = ops.attention(qd[:, :C_], kvd[:, :C_], kvd[:, C_:], B, heads)
+    close(got, want, dt)
+    assert torch.equal(got, ops.attention(qd[:, :C_], kvd[:, :C_], kvd[:, C_:], B, heads))
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N,K,kw", [(6, 6144, 2048, {}), (12, 8192, 2048, {"gelu": True}), (2, 1024, 2048, {"f32": True}),
+                                      (24, 640, 320, {"resid": True}), (40, 640, 320, {"gelu": True}),
+                                      (32, 512, 2048, {})])
+def test_ln_gemm(ops, dt, M, N, K, kw):
+    """pcdm_ln_gemm: LayerNorm fused in front of the skinny GEMM (M <= 32 rows that fit) or layernorm + gemm inside the
+    call (M = 40; M = 32 x K = 2048 exceeds the shared-memory budget) — against torch fp32 with the normalised rows
+    rounded to 16 bits, as both paths do."""
+    from pcdms_b200 import lib
+    g = torch.Generator().manual_seed(M + N + K)
+    x_full = (2.0 * torch.randn(M, 2, K, generator=g) + 0.5).to(dt)
+    x = x_full[:, 1]
+    gamma, beta = 1.0 + 0.1 * torch.randn(K, generator=g), 0.1 * torch.randn(K, generator=g)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt)
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g).to(dt) if kw.get("resid") else None
+    n16 = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5).to(dt).float()
+    ref = n16 @ w.float().t() + b
+    if r is not None:
+        ref = ref + r.float()
+    if kw.get("gelu"):
+        ref = F.gelu(ref)
+    xd = x_full.cuda()[:, 1]
+    before = lib.launch_count
+    out = ops.ln_gemm(xd, gamma.cuda(), beta.cuda(), 1e-5, w.cuda(), bias=b.cuda(),
+                      residual=r.cuda() if r is not None else None, gelu=bool(kw.get("gelu")), out_f32=bool(kw.get("f32")))
+    fused = M <= 32 and M * (K + 8) * 2 <= 100 * 1024
+    assert lib.launch_count - before == (1 if fused else 2)
+    # a rounding flip of a normalised value (fp32 mean / rstd evaluated in a different order) moves an output by one
+    # 16-bit ulp of that value times a weight: allow 2x the single-rounding tolerance
+    close(out, ref, dt, mult=2.0)

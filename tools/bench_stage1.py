@@ -21,7 +21,7 @@ from pcdms_b200.prior import B200Stage1PriorPipeline, B200Stage1PriorTransformer
 out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bench_stage1.json"
 dev = "cuda"
 try:
-    HBM = json.load(open("MEASURED_PEAKS.json")).get("hbm_gbps")
+    HBM = json.load(open("MEASURED_PEAKS.json")).get("hbm_gbs")
 except Exception:
     HBM = None
 
@@ -41,6 +41,13 @@ def timed(fn, k=5, warm=3):
 
 res = {"hbm_peak_gbps": HBM}
 dt = torch.float16
+import ctypes as _C
+import os
+from pcdms_b200 import lib as _lib
+_L = _lib.load()
+_L.pcdm_set_skinny_gemm(_C.c_int(int(os.environ.get("PCDM_SKINNY", "1"))))          # A/B hooks
+_L.pcdm_set_attention_small(_C.c_int(int(os.environ.get("PCDM_ATT_SMALL", "1"))))
+ONLY_PRIOR = os.environ.get("PCDM_ONLY_PRIOR") == "1"
 
 prior = B200Stage1PriorTransformer(dtype=dt, device=dev, num_embeddings=2, embedding_dim=1024)
 prior.load_state_dict(prior.synthetic_state_dict(seed=0))
@@ -76,6 +83,9 @@ for name, n, guidance in (("prior_n1", 1, 0.0), ("prior_n1_cfg", 1, 2.0), ("prio
     print(name, json.dumps(res[name]), flush=True)
 del pipe, prior
 torch.cuda.empty_cache()
+if ONLY_PRIOR:
+    json.dump(res, open(out_path, "w"), indent=1)
+    sys.exit(0)
 
 clip = B200CLIPVisionModelWithProjection(dtype=dt, device=dev)
 clip.load_state_dict(clip.synthetic_state_dict(seed=1))
