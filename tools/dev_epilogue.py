@@ -24,7 +24,11 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 
+import os
 masks = [0, 1, 2, 4, 7, 10, 16, 26]
+if os.environ.get("PCDM_STAGES"):      # ring-depth sweep: do queued mainloop loads delay the epilogue's TMA traffic?
+    L.pcdm_set_gemm_max_stages(C.c_int(int(os.environ["PCDM_STAGES"])))
+    masks = [0, 10]
 print("mask:" + "".join(f"{m:8d}" for m in masks))
 for M, N, K, res in ((32768, 320, 320, True), (32768, 320, 320, False), (8192, 640, 640, True), (2048, 1280, 1280, True),
                      (32768, 320, 1280, True), (32768, 960, 320, False)):
