@@ -62,6 +62,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     mode = os.environ.get("PCDM_GEMM_CTA_GROUP")  # tuning hook: 1 = single-CTA tiles, 2 = CTA pairs, unset = auto
     if mode:
         lib.pcdm_set_gemm_cta_group(C.c_int(int(mode)))
+    if os.environ.get("PCDM_SKINNY") is not None:      # A/B hooks: 0 = M <= 32 GEMMs / short attention on the tcgen05 kernels
+        lib.pcdm_set_skinny_gemm(C.c_int(int(os.environ["PCDM_SKINNY"])))
+    if os.environ.get("PCDM_ATT_SMALL") is not None:
+        lib.pcdm_set_attention_small(C.c_int(int(os.environ["PCDM_ATT_SMALL"])))
     if os.environ.get("PCDM_PDL") is not None:   # tuning hook: 0 disables programmatic dependent launch
         lib.pcdm_set_pdl(C.c_int(int(os.environ["PCDM_PDL"])))
     _lib = lib

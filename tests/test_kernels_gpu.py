@@ -334,6 +334,10 @@ def test_skinny_gemm(ops, dt, M, N, K, kw):
     assert out.dtype == (torch.float32 if kw.get("f32") else dt) and not out_buf[:, N:].any()
     close(out, ref, dt)
     assert torch.equal(out, ops.gemm(ad, w.cuda(), **args))            # bit-reproducible
+    if M > 1 and rv is None:   # a row's result does not depend on how many other rows ride along (shard independence)
+        k = M // 2
+        sub = dict(args, residual=args["residual"][:k] if args["residual"] is not None else None)
+        assert torch.equal(ops.gemm(ad[:k], w.cuda(), **sub), out[:k])
     if N % 32 == 0:                                                     # the tile path needs N % 32 == 0
         L = lib.load()
         L.pcdm_set_skinny_gemm(C.c_int(0))
