@@ -294,9 +294,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     uint8_t* slots = epi_smem + e * p.nbuf * IG_SLOT_BYTES;
     const uint32_t slots_s = smem_u32(slots);
     uint64_t* rbar = res_bar + e * IG_RES_SLOTS;
+    uint32_t cnt = 0;         // chunks staged by this warp so far (slot rotation when there is no residual)
     uint32_t rphase = 0;      // bit i: parity of the next completion of residual barrier i
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int nbuf = p.nbuf;
     const uint32_t tempty_addr[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
@@ -355,12 +357,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         //      ALL residual chunks this warp owns in the tile are TMA-prefetched (one slot each) before the wait for the
         //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
         //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
-        //      One staging slot per chunk the warp owns in the tile and ONE proxy fence per tile: the chunks are all
-        //      written to shared memory first, then fenced once, then stored.
         const bool use_res = p.has_res && !(p.dbg & 2);
-        if (lane == 0) {
-          bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
-          if (use_res) {
+        if (use_res) {
+          if (lane == 0) {
+            bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
             int i = 0;
             for (int c = half; c * 32 < cols_here; c += 2, ++i) {
               mbar_expect_tx(&rbar[i], IG_SLOT_BYTES);
@@ -368,15 +368,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             }
           }
         }
-        __syncwarp();
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         int ci = 0;
 #pragma unroll 1
         for (int c = half; c * 32 < cols_here && !(p.dbg & 8); c += 2, ++ci) {
           const int n0 = n_tile0 + c * 32;
-          const uint32_t slot = (uint32_t)ci;
+          const uint32_t slot = use_res ? (uint32_t)ci : (cnt & (uint32_t)(nbuf - 1));   // nbuf is 2 or 4
+          uint8_t* sl = slots + slot * IG_SLOT_BYTES;
           const uint32_t sl_s = slots_s + slot * IG_SLOT_BYTES;
+          if (!use_res) {
+            if (lane == 0) bulk_wait_read<1>();   // every store but the most recent has finished reading its slot
+            __syncwarp();
+          }
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tc_wait_ld();
@@ -427,26 +431,26 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             u.w = pack2<DT>(v[j * 4 + 3].x, v[j * 4 + 3].y);
             sts128(sl_s + sw64(lane, j), u);
           }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && !(p.dbg & 1)) {
-          int i = 0;
-          for (int c = half; c * 32 < cols_here && !(p.dbg & 8); c += 2, ++i)   // rows >= M / columns >= N are clipped
-            tma_store_2d(&p.tmOut, slots + i * IG_SLOT_BYTES, n_tile0 + c * 32, m_warp0);
-          bulk_commit();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
+            bulk_commit();
+          }
+          ++cnt;
         }
       } else {
         // ---- GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate) ----
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
-        int ci = 0;
 #pragma unroll 1
-        for (int c = half; c * 64 < cols_here; c += 2, ++ci) {
+        for (int c = half; c * 64 < cols_here; c += 2) {
           const int n0 = n_tile0 + c * 64;
-          const uint32_t sl_s = slots_s + (uint32_t)ci * IG_SLOT_BYTES;
+          const uint32_t slot = cnt & (uint32_t)(nbuf - 1);
+          uint8_t* sl = slots + slot * IG_SLOT_BYTES;
+          const uint32_t sl_s = slots_s + slot * IG_SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
           uint32_t rh[32], rg[32];
           tmem_ld32(t_row + c * 64, rh);
           tmem_ld32(t_row + c * 64 + 32, rg);
@@ -473,14 +477,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          int i = 0;
-          for (int c = half; c * 64 < cols_here; c += 2, ++i)
-            tma_store_2d(&p.tmOut, slots + i * IG_SLOT_BYTES, (n_tile0 + c * 64) >> 1, m_warp0);
-          bulk_commit();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, sl, n0 >> 1, m_warp0);
+            bulk_commit();
+          }
+          ++cnt;
         }
       }
       tc_fence_before();
@@ -573,7 +576,7 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
     PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
     configured = true;
   }
-  p.nbuf = IG_RES_SLOTS;   // one slot per chunk a warp owns in a tile (<= 4)
+  p.nbuf = p.has_res ? IG_RES_SLOTS : 2;
   p.dbg = g_gemm_dbg;
   const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
