@@ -125,21 +125,49 @@ __global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, l
   const int step = *step_counter;
   const float4 cf = coef[step];
   const long long total = (long long)n * HW;
+  const bool vec_eps = eps_dt == 2 && (ld_eps & 3) == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0;
+  const bool vec_x9 = x9_dt != 2 && (ld_x9 & 3) == 0 && (reinterpret_cast<uintptr_t>(x9) & 7) == 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % HW);
     const int b = (int)(i / HW);
+    // the UNet's fp32 output rows: the four epsilon channels of a pixel are one 16-byte load per CFG half
+    float eu4[4], ec4[4];
+    if (vec_eps) {
+      const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eps) + ((long long)b * HW + p) * ld_eps);
+      const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eps) + ((long long)(b + n) * HW + p) * ld_eps);
+      eu4[0] = u.x; eu4[1] = u.y; eu4[2] = u.z; eu4[3] = u.w;
+      ec4[0] = c.x; ec4[1] = c.y; ec4[2] = c.z; ec4[3] = c.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        eu4[c] = load_any(eps, ((long long)b * HW + p) * ld_eps + c, eps_dt);
+        ec4[c] = load_any(eps, ((long long)(b + n) * HW + p) * ld_eps + c, eps_dt);
+      }
+    }
+    float xp4[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float eu = load_any(eps, ((long long)b * HW + p) * ld_eps + c, eps_dt);
-      const float ec = load_any(eps, ((long long)(b + n) * HW + p) * ld_eps + c, eps_dt);
+      const float eu = eu4[c], ec = ec4[c];
       const float e = eu + guidance * (ec - eu);
       const long long li = ((long long)b * 4 + c) * HW + p;
       const float x = latents[li];
       const float x0 = (x - cf.y * e) * cf.x;
       const float xp = cf.z * x0 + cf.w * e;
-      latents[li] = xp;
-      store_any(x9, ((long long)b * HW + p) * ld_x9 + c, x9_dt, xp);
-      store_any(x9, ((long long)(b + n) * HW + p) * ld_x9 + c, x9_dt, xp);
+      latents[li] = xp;                      // NCHW planes: consecutive threads write consecutive pixels
+      xp4[c] = xp;
+    }
+    if (vec_x9) {                            // 16-bit NHWC rows: the four latent channels are one 8-byte store per half
+      uint2 o;
+      if (x9_dt == 0) { o.x = pack2<DT_F16>(xp4[0], xp4[1]); o.y = pack2<DT_F16>(xp4[2], xp4[3]); }
+      else { o.x = pack2<DT_BF16>(xp4[0], xp4[1]); o.y = pack2<DT_BF16>(xp4[2], xp4[3]); }
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(x9) + ((long long)b * HW + p) * ld_x9) = o;
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(x9) + ((long long)(b + n) * HW + p) * ld_x9) = o;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        store_any(x9, ((long long)b * HW + p) * ld_x9 + c, x9_dt, xp4[c]);
+        store_any(x9, ((long long)(b + n) * HW + p) * ld_x9 + c, x9_dt, xp4[c]);
+      }
     }
   }
   __syncthreads();
@@ -170,6 +198,49 @@ __global__ void add_noise_kernel(const void* __restrict__ x0, const void* __rest
     const float a = alphas_cumprod[t[b]];
     const float sa = sqrtf(a), sb = sqrtf(1.f - a);
     store_any(out, i, dt, sa * load_any(x0, i, dt) + sb * load_any(noise, i, dt));
+  }
+}
+
+// Vectorised forms for same-dtype 16-bit tensors (what the training / protocol callers pass): 16 bytes = 8 elements
+// per thread per access, fully coalesced; identical per-element arithmetic to the scalar kernels above / below.
+template <int DT>
+__global__ void add_noise_vec_kernel(const uint4* __restrict__ x0, const uint4* __restrict__ noise, uint4* __restrict__ out,
+                                     const float* __restrict__ alphas_cumprod, const long long* __restrict__ t,
+                                     long long nvec, long long per_sample) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)((v * 8) / per_sample);          // per_sample % 8 == 0: a vector never straddles two samples
+    const float a = alphas_cumprod[t[b]];
+    const float sa = sqrtf(a), sb = sqrtf(1.f - a);
+    const uint4 xv = x0[v], nv = noise[v];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 xf = unpack2<DT>(xs[i]), nf = unpack2<DT>(ns[i]);
+      o[i] = pack2<DT>(sa * xf.x + sb * nf.x, sa * xf.y + sb * nf.y);
+    }
+    out[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <int DT>
+__global__ void ddim_step_vec_kernel(const uint4* __restrict__ eps, const uint4* __restrict__ x, uint4* __restrict__ out,
+                                     float c0, float c1, float c2, float c3, long long nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const uint4 ev = eps[v], xv = x[v];
+    const uint32_t es[4] = {ev.x, ev.y, ev.z, ev.w}, xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 e = unpack2<DT>(es[i]), xf = unpack2<DT>(xs[i]);
+      const float a0 = (xf.x - c1 * e.x) * c0, a1 = (xf.y - c1 * e.y) * c0;
+      o[i] = pack2<DT>(c2 * a0 + c3 * e.x, c2 * a1 + c3 * e.y);
+    }
+    out[v] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -526,6 +597,16 @@ extern "C" int pcdm_add_noise(const void* x0, const void* noise, void* out, int 
   if (dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "add_noise: bad dtype");
   if (B <= 0 || per_sample <= 0) return set_error(PCDM_ERR_INVALID, "add_noise: empty problem");
   const long long total = (long long)B * per_sample;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (dtype != 2 && per_sample % 8 == 0 && aligned) {   // 16-byte vector path
+    const long long nvec = total / 8;
+    if (dtype == 0)
+      PCDM_CUDA(launch_kernel(add_noise_vec_kernel<DT_F16>, dim3(grid_for(nvec, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, reinterpret_cast<const uint4*>(x0), reinterpret_cast<const uint4*>(noise), reinterpret_cast<uint4*>(out), alphas_cumprod, timesteps, nvec, per_sample));
+    else
+      PCDM_CUDA(launch_kernel(add_noise_vec_kernel<DT_BF16>, dim3(grid_for(nvec, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, reinterpret_cast<const uint4*>(x0), reinterpret_cast<const uint4*>(noise), reinterpret_cast<uint4*>(out), alphas_cumprod, timesteps, nvec, per_sample));
+    PCDM_CUDA(cudaGetLastError());
+    return 0;
+  }
   PCDM_CUDA(launch_kernel(add_noise_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, x0, noise, out, dtype, alphas_cumprod, timesteps, B, per_sample));
   PCDM_CUDA(cudaGetLastError());
   return 0;
@@ -537,6 +618,16 @@ extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const voi
   if (!model_output || !sample || !prev_sample) return set_error(PCDM_ERR_INVALID, "ddim_step: null pointer");
   if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "ddim_step: bad dtype");
   if (numel <= 0) return set_error(PCDM_ERR_INVALID, "ddim_step: empty problem");
+  const bool aligned = ((reinterpret_cast<uintptr_t>(model_output) | reinterpret_cast<uintptr_t>(sample) | reinterpret_cast<uintptr_t>(prev_sample)) & 15) == 0;
+  if (dtype != 2 && eps_dtype == dtype && numel % 8 == 0 && aligned) {   // 16-byte vector path
+    const long long nvec = numel / 8;
+    if (dtype == 0)
+      PCDM_CUDA(launch_kernel(ddim_step_vec_kernel<DT_F16>, dim3(grid_for(nvec, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, reinterpret_cast<const uint4*>(model_output), reinterpret_cast<const uint4*>(sample), reinterpret_cast<uint4*>(prev_sample), inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, nvec));
+    else
+      PCDM_CUDA(launch_kernel(ddim_step_vec_kernel<DT_BF16>, dim3(grid_for(nvec, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, reinterpret_cast<const uint4*>(model_output), reinterpret_cast<const uint4*>(sample), reinterpret_cast<uint4*>(prev_sample), inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, nvec));
+    PCDM_CUDA(cudaGetLastError());
+    return 0;
+  }
   PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, numel));
   PCDM_CUDA(cudaGetLastError());
   return 0;

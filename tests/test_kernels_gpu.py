@@ -398,3 +398,25 @@ def test_ln_gemm(ops, dt, M, N, K, kw):
     # a rounding flip of a normalised value (fp32 mean / rstd evaluated in a different order) moves an output by one
     # 16-bit ulp of that value times a weight: allow 2x the single-rounding tolerance
     close(out, ref, dt, mult=2.0)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("shape", [(2, 4, 16, 32), (3, 4, 3, 3)])    # 16-byte vector path / scalar path (numel % 8 != 0)
+def test_scheduler_protocol_16bit_vector_paths(ops, dt, shape):
+    """DDIMScheduler.step and DDPMScheduler.add_noise on same-dtype 16-bit tensors (the reference's fp16 loop tensors,
+    stage2_inpaint_pipeline.py:431-501; training add_noise, stage2_train_inpaint_model.py:361): the vectorised kernels
+    against the fp32 formulas on the same 16-bit inputs."""
+    from oracle.schedulers import OracleDDIMScheduler, ddpm_add_noise
+    from pcdms_b200.scheduler import B200DDIMScheduler, B200DDPMScheduler
+    g = torch.Generator().manual_seed(sum(shape))
+    e, s = torch.randn(shape, generator=g).to(dt), torch.randn(shape, generator=g).to(dt)
+    sch, osch = B200DDIMScheduler(), OracleDDIMScheduler()
+    sch.set_timesteps(10)
+    osch.set_timesteps(10)
+    out = sch.step(e.cuda(), 501, s.cuda(), return_dict=False)[0]
+    assert out.dtype == dt
+    close(out, osch.step(e.float(), 501, s.float(), return_dict=False)[0], dt)
+    ts = torch.tensor([0, 500, 999][: shape[0]])
+    out = B200DDPMScheduler().add_noise(s.cuda(), e.cuda(), ts.cuda())
+    assert out.dtype == dt
+    close(out, ddpm_add_noise(s.float(), e.float(), ts), dt)
