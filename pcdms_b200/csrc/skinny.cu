@@ -7,11 +7,13 @@
 //
 //   * roles swapped — the weight rows are the M dimension of `mma.sync.m16n8k16` (16 output features per CTA), the
 //     activation rows are its 8-wide N dimension (one n-tile per 8 activation rows);
-//   * a CTA owns 16 weight rows and ALL of K: its 16 warps interleave over 64-element K chunks, so the CTA reads 2 KB
-//     contiguous per row per round and every lane issues plain 16-byte loads that are consumed in registers in exactly
-//     the layout the MMA fragments want (the k-slots of a fragment are a permutation of physical k, the same one for
-//     both operands — a dot product does not care); two chunks are in flight per warp (128 B of weights per lane),
-//     and they are requested before the programmatic-dependency wait: weights do not depend on the previous kernel;
+//   * a CTA works on 16 weight rows and ALL of K at a time: its 16 warps interleave over 64-element K chunks, so the
+//     CTA reads 2 KB contiguous per row per round and every lane issues plain 16-byte loads that are consumed in
+//     registers in exactly the layout the MMA fragments want (the k-slots of a fragment are a permutation of physical
+//     k, the same one for both operands — a dot product does not care); two or four chunks are in flight per warp
+//     (128 / 256 B of weights per lane), the first of them requested before the programmatic-dependency wait (weights
+//     do not depend on the previous kernel), and the kernel is persistent over row blocks so that the stream keeps
+//     flowing while a row block is reduced and written;
 //   * the 16 per-warp partial tiles meet in shared memory and are summed in fixed warp order (bit-reproducible);
 //     bias / per-image row vector / residual / SiLU / GELU are applied there, 16-bit or fp32 output.
 //
@@ -63,24 +65,29 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {   // weights: read 
   return u;
 }
 
-// NT = number of 8-row activation tiles (M <= 8 NT).  LN: the activation rows are layer-normalised first (each CTA
-// normalises the <= 32 rows itself — 4 KB per row out of L2 — into shared memory, rounded to 16 bits exactly as the
-// stand-alone LayerNorm kernel would have stored them), which removes a launch from a chain of launch-bound kernels.
-template <int DT, int NT, bool LN>
-__global__ void __launch_bounds__(SK_THREADS, (NT == 1 && !LN) ? 2 : 1) skinny_gemm_kernel(const SkinnyParams p) {
+// NT = number of 8-row activation tiles (M <= 8 NT).  PF = weight chunks in flight per warp (2: 64 registers, two CTAs
+// per SM; 3 / 4: one CTA per SM).  LN: the activation rows are layer-normalised first (each CTA normalises the <= 32 rows
+// itself — 4 KB per row out of L2 — into shared memory, rounded to 16 bits exactly as the stand-alone LayerNorm kernel
+// would have stored them).
+//
+// The kernel is PERSISTENT over 16-row blocks of W (grid = min(N / 16, resident CTAs)): a warp walks the flattened
+// sequence (row block, its K chunks) with PF chunks always in flight, so the loads of the next row block are already
+// under way while the current one is reduced and written — the stream does not drain between row blocks.
+template <int DT, int NT, bool LN, int PF>
+__global__ void __launch_bounds__(SK_THREADS, (NT == 1 && !LN && PF == 2) ? 2 : 1)
+skinny_gemm_kernel(const SkinnyParams p) {
   __shared__ float red[SK_WARPS][NT][SK_ROWS][8 + 1];
   extern __shared__ __align__(16) uint8_t sk_dyn[];   // LN: normalised activations [M][K + 8] 16-bit
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int n0 = blockIdx.x * SK_ROWS;
   const int nchunks = p.K >> 6;
+  const int n_rb = p.N / SK_ROWS;
   using T = typename TypeOf<DT>::T;
   const T* W = reinterpret_cast<const T*>(p.w);
   const T* A = reinterpret_cast<const T*>(p.a);
-  // rows beyond N (N % 16 != 0 is excluded by the host) never occur; activation rows beyond M read as zero
-  const T* w_lo = W + (long long)(n0 + g) * p.K + 16 * t;
-  const T* w_hi = w_lo + 8LL * p.K;
+  const T* w_lane = W + (long long)g * p.K + 16 * t;   // + row block * 16 * K + chunk * 64; rows g and g + 8
+  const long long hi = 8LL * p.K;
   const T* a_row[NT];
   bool a_ok[NT];
 #pragma unroll
@@ -88,23 +95,25 @@ __global__ void __launch_bounds__(SK_THREADS, (NT == 1 && !LN) ? 2 : 1) skinny_g
     a_ok[nt] = nt * 8 + g < p.M;
     a_row[nt] = A + (long long)(a_ok[nt] ? nt * 8 + g : 0) * p.lda + 16 * t;
   }
-  float acc[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 
-  // Weights never depend on the stream predecessor: the first TWO chunks of this warp (all of the CTA's weights when
-  // K <= 2048) are requested BEFORE the programmatic-dependency wait, so the weight stream of this kernel overlaps
-  // the tail (and, in a chain of small kernels, most of the body) of the previous one; only activations wait.
-  auto load_w = [&](uint4 (&dst)[4], int chunk) {
-    dst[0] = ldg_stream(w_lo + (chunk << 6)); dst[1] = ldg_stream(w_lo + (chunk << 6) + 8);
-    dst[2] = ldg_stream(w_hi + (chunk << 6)); dst[3] = ldg_stream(w_hi + (chunk << 6) + 8);
+  // Weights never depend on the stream predecessor: the first PF chunks of this warp are requested BEFORE the
+  // programmatic-dependency wait, so the weight stream of this kernel overlaps the tail (and, in a chain of small
+  // kernels, most of the body) of the previous one; only activations wait.
+  auto load_w = [&](uint4 (&dst)[4], int rb, int chunk) {
+    const T* q = w_lane + (long long)rb * SK_ROWS * p.K + (chunk << 6);
+    dst[0] = ldg_stream(q); dst[1] = ldg_stream(q + 8);
+    dst[2] = ldg_stream(q + hi); dst[3] = ldg_stream(q + hi + 8);
   };
-  uint4 cur[4], nxt[4];
-  int c = warp;
-  if (c < nchunks) load_w(cur, c);
-  if (c + SK_WARPS < nchunks) load_w(nxt, c + SK_WARPS);
+  uint4 buf[PF][4];
+  int nrb = warp < nchunks ? (int)blockIdx.x : n_rb, nc = warp;   // the next (row block, chunk) to request
+  auto advance = [&]() {
+    nc += SK_WARPS;
+    if (nc >= nchunks) { nc = warp; nrb += gridDim.x; }
+  };
+#pragma unroll
+  for (int j = 0; j < PF; ++j) {
+    if (nrb < n_rb) { load_w(buf[j], nrb, nc); advance(); }
+  }
   pdl_wait();
   const int lds = p.K + 8;   // padded row stride of the normalised activations
   if (LN) {
@@ -164,61 +173,72 @@ __global__ void __launch_bounds__(SK_THREADS, (NT == 1 && !LN) ? 2 : 1) skinny_g
     }
     __syncthreads();
   }
-  while (c < nchunks) {
-    uint4 b0[NT], b1[NT];
+  for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+    float acc[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      b0[nt] = make_uint4(0u, 0u, 0u, 0u);
-      b1[nt] = b0[nt];
-      if (a_ok[nt]) {
-        if (LN) {
-          const T* ar = reinterpret_cast<const T*>(sk_dyn) + (long long)(nt * 8 + g) * lds + 16 * t + (c << 6);
-          b0[nt] = *reinterpret_cast<const uint4*>(ar);
-          b1[nt] = *reinterpret_cast<const uint4*>(ar + 8);
-        } else {
-          b0[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6)));
-          b1[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6) + 8));
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    for (int c = warp; c < nchunks; c += SK_WARPS) {
+      uint4 b0[NT], b1[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        b0[nt] = make_uint4(0u, 0u, 0u, 0u);
+        b1[nt] = b0[nt];
+        if (a_ok[nt]) {
+          if (LN) {
+            const T* ar = reinterpret_cast<const T*>(sk_dyn) + (long long)(nt * 8 + g) * lds + 16 * t + (c << 6);
+            b0[nt] = *reinterpret_cast<const uint4*>(ar);
+            b1[nt] = *reinterpret_cast<const uint4*>(ar + 8);
+          } else {
+            b0[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6)));
+            b1[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6) + 8));
+          }
         }
       }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma16816<DT>(acc[nt], buf[0][0].x, buf[0][2].x, buf[0][0].y, buf[0][2].y, b0[nt].x, b0[nt].y);
+        mma16816<DT>(acc[nt], buf[0][0].z, buf[0][2].z, buf[0][0].w, buf[0][2].w, b0[nt].z, b0[nt].w);
+        mma16816<DT>(acc[nt], buf[0][1].x, buf[0][3].x, buf[0][1].y, buf[0][3].y, b1[nt].x, b1[nt].y);
+        mma16816<DT>(acc[nt], buf[0][1].z, buf[0][3].z, buf[0][1].w, buf[0][3].w, b1[nt].z, b1[nt].w);
+      }
+      // rotate the register ring and request the chunk PF items ahead (it may belong to this CTA's next row block)
+#pragma unroll
+      for (int j = 0; j + 1 < PF; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) buf[j][i] = buf[j + 1][i];
+      if (nrb < n_rb) { load_w(buf[PF - 1], nrb, nc); advance(); }
     }
+    // accumulator fragment: c0/c1 = (weight row g, activation rows 2t, 2t+1), c2/c3 = (weight row g + 8, same)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      mma16816<DT>(acc[nt], cur[0].x, cur[2].x, cur[0].y, cur[2].y, b0[nt].x, b0[nt].y);
-      mma16816<DT>(acc[nt], cur[0].z, cur[2].z, cur[0].w, cur[2].w, b0[nt].z, b0[nt].w);
-      mma16816<DT>(acc[nt], cur[1].x, cur[3].x, cur[1].y, cur[3].y, b1[nt].x, b1[nt].y);
-      mma16816<DT>(acc[nt], cur[1].z, cur[3].z, cur[1].w, cur[3].w, b1[nt].z, b1[nt].w);
+      red[warp][nt][g][2 * t] = acc[nt][0];
+      red[warp][nt][g][2 * t + 1] = acc[nt][1];
+      red[warp][nt][g + 8][2 * t] = acc[nt][2];
+      red[warp][nt][g + 8][2 * t + 1] = acc[nt][3];
     }
-    c += SK_WARPS;
+    __syncthreads();
+    // one thread per output element: fixed summation order over the warps, then the epilogue
+    const int n0 = rb * SK_ROWS;
+    for (int idx = threadIdx.x; idx < NT * 8 * SK_ROWS; idx += SK_THREADS) {
+      const int r = idx & (SK_ROWS - 1);      // weight row inside the block (fastest: consecutive output columns)
+      const int m = idx >> 4;                 // activation row
+      if (m >= p.M) continue;
+      const int nt = m >> 3, mc = m & 7;
+      float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-    if (c + SK_WARPS < nchunks) load_w(nxt, c + SK_WARPS);
-  }
-  // accumulator fragment: c0/c1 = (weight row g, activation rows 2t, 2t+1), c2/c3 = (weight row g + 8, same)
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    red[warp][nt][g][2 * t] = acc[nt][0];
-    red[warp][nt][g][2 * t + 1] = acc[nt][1];
-    red[warp][nt][g + 8][2 * t] = acc[nt][2];
-    red[warp][nt][g + 8][2 * t + 1] = acc[nt][3];
-  }
-  __syncthreads();
-  // one thread per output element: fixed summation order over the warps, then the epilogue
-  for (int idx = threadIdx.x; idx < NT * 8 * SK_ROWS; idx += SK_THREADS) {
-    const int r = idx & (SK_ROWS - 1);      // weight row inside the CTA (fastest: consecutive output columns)
-    const int m = idx >> 4;                 // activation row
-    if (m >= p.M) continue;
-    const int nt = m >> 3, mc = m & 7;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < SK_WARPS; ++w) v += red[w][nt][r][mc];
-    const int n = n0 + r;
-    if (p.bias) v += p.bias[n];
-    if (p.rowvec) v += p.rowvec[(long long)(m / p.hw) * p.ld_rowvec + n];
-    if (p.residual) v += (float)reinterpret_cast<const T*>(p.residual)[(long long)m * p.ldr + n];
-    if (p.act == 1) v = silu_f(v);
-    else if (p.act == 2) v = gelu_erf_f(v);
-    if (p.out_f32) reinterpret_cast<float*>(p.out)[(long long)m * p.ldo + n] = v;
-    else reinterpret_cast<T*>(p.out)[(long long)m * p.ldo + n] = (T)v;
+      for (int w = 0; w < SK_WARPS; ++w) v += red[w][nt][r][mc];
+      const int n = n0 + r;
+      if (p.bias) v += p.bias[n];
+      if (p.rowvec) v += p.rowvec[(long long)(m / p.hw) * p.ld_rowvec + n];
+      if (p.residual) v += (float)reinterpret_cast<const T*>(p.residual)[(long long)m * p.ldr + n];
+      if (p.act == 1) v = silu_f(v);
+      else if (p.act == 2) v = gelu_erf_f(v);
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[(long long)m * p.ldo + n] = v;
+      else reinterpret_cast<T*>(p.out)[(long long)m * p.ldo + n] = (T)v;
+    }
+    __syncthreads();   // the partial-sum buffer is reused by the next row block
   }
 }
 
@@ -228,26 +248,34 @@ constexpr int SK_LN_SMEM_LIMIT = 100 * 1024;   // fused LayerNorm: M * (K + 8) *
 
 template <int DT, bool LN>
 static cudaError_t launch_skinny(const SkinnyParams& p, cudaStream_t stream) {
-  const dim3 grid(p.N / SK_ROWS), block(SK_THREADS);
+  const int n_rb = p.N / SK_ROWS;
   const int nt = (p.M + 7) / 8;
   const size_t dyn = LN ? (size_t)p.M * (p.K + 8) * 2 : 0;
-#define SK_CASE(NT_)                                                                                                 \
+  // Two CTAs per SM (64 registers, two chunks in flight per warp) when the problem has more row blocks than SMs;
+  // otherwise — or with more than 8 rows, where the accumulators take the registers anyway — one CTA per SM with four
+  // chunks in flight per warp.
+  const bool deep = LN || nt > 1 || n_rb <= num_sms();
+  const int resident = (deep ? 1 : 2) * num_sms();
+  const dim3 grid(n_rb < resident ? n_rb : resident), block(SK_THREADS);
+#define SK_CASE(NT_, PF_)                                                                                            \
   do {                                                                                                               \
     if (LN) {                                                                                                        \
       static bool configured = false;                                                                                \
       if (!configured) {                                                                                             \
-        cudaFuncSetAttribute(skinny_gemm_kernel<DT, NT_, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+        cudaFuncSetAttribute(skinny_gemm_kernel<DT, NT_, LN, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                              SK_LN_SMEM_LIMIT);                                                                      \
         configured = true;                                                                                           \
       }                                                                                                              \
     }                                                                                                                \
-    return launch_kernel(skinny_gemm_kernel<DT, NT_, LN>, grid, block, dyn, stream, 1, p);                           \
+    return launch_kernel(skinny_gemm_kernel<DT, NT_, LN, PF_>, grid, block, dyn, stream, 1, p);                      \
   } while (0)
   switch (nt) {
-    case 1: SK_CASE(1);
-    case 2: SK_CASE(2);
-    case 3: SK_CASE(3);
-    default: SK_CASE(4);
+    case 1:
+      if (deep) SK_CASE(1, 4);
+      else SK_CASE(1, 2);
+    case 2: SK_CASE(2, 3);
+    case 3: SK_CASE(3, 3);
+    default: SK_CASE(4, 3);
   }
 #undef SK_CASE
 }

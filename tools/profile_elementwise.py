@@ -21,6 +21,7 @@ def timed(fn, reps=20):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(20_000_000)   # ~10 ms of spin: the CPU queues every launch behind it (GPU-bound timing)
     e0.record()
     for _ in range(reps):
         fn()
@@ -64,9 +65,9 @@ for n in (8, 256):
     coef = sch.coefficient_table(dev)
     counter = torch.zeros(2, dtype=torch.int32, device=dev)
 
-    def fused():
-        counter.zero_()
+    def fused():   # the step counter walks the 50-row coefficient table: 23 calls per timing stay inside it
         ops.cfg_ddim_step(eps, lat, x9, coef, counter, 2.0)
+    counter.zero_()
     us = timed(fused)
     b = n * 4 * h * w * 28          # 28 B per latent element (2 eps reads, latents r/w, 2 x9 writes)
     res[f"cfg_ddim_step n={n}"] = {"us": us, "algorithmic_bytes": b, "gbs": b / us / 1e3}
