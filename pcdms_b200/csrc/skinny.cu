@@ -104,15 +104,14 @@ skinny_gemm_kernel(const SkinnyParams p) {
     dst[0] = ldg_stream(q); dst[1] = ldg_stream(q + 8);
     dst[2] = ldg_stream(q + hi); dst[3] = ldg_stream(q + hi + 8);
   };
+  // Register ring with STATIC slots: a row block is walked in groups of PF chunks, chunk j of a group always lives in
+  // buf[j]; when slot j has been consumed it is refilled with the chunk PF positions ahead — in the same row block, or
+  // slot j of the first group of this CTA's NEXT row block — so PF chunks (or the whole next row block) are in flight.
   uint4 buf[PF][4];
-  int nrb = warp < nchunks ? (int)blockIdx.x : n_rb, nc = warp;   // the next (row block, chunk) to request
-  auto advance = [&]() {
-    nc += SK_WARPS;
-    if (nc >= nchunks) { nc = warp; nrb += gridDim.x; }
-  };
 #pragma unroll
   for (int j = 0; j < PF; ++j) {
-    if (nrb < n_rb) { load_w(buf[j], nrb, nc); advance(); }
+    const int c = warp + j * SK_WARPS;
+    if (c < nchunks && (int)blockIdx.x < n_rb) load_w(buf[j], blockIdx.x, c);
   }
   pdl_wait();
   const int lds = p.K + 8;   // padded row stride of the normalised activations
@@ -179,36 +178,40 @@ skinny_gemm_kernel(const SkinnyParams p) {
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-    for (int c = warp; c < nchunks; c += SK_WARPS) {
-      uint4 b0[NT], b1[NT];
+    for (int c0 = warp; c0 < nchunks; c0 += PF * SK_WARPS) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        b0[nt] = make_uint4(0u, 0u, 0u, 0u);
-        b1[nt] = b0[nt];
-        if (a_ok[nt]) {
-          if (LN) {
-            const T* ar = reinterpret_cast<const T*>(sk_dyn) + (long long)(nt * 8 + g) * lds + 16 * t + (c << 6);
-            b0[nt] = *reinterpret_cast<const uint4*>(ar);
-            b1[nt] = *reinterpret_cast<const uint4*>(ar + 8);
-          } else {
-            b0[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6)));
-            b1[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6) + 8));
+      for (int j = 0; j < PF; ++j) {
+        const int c = c0 + j * SK_WARPS;
+        if (c < nchunks) {
+          uint4 b0[NT], b1[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            b0[nt] = make_uint4(0u, 0u, 0u, 0u);
+            b1[nt] = b0[nt];
+            if (a_ok[nt]) {
+              if (LN) {
+                const T* ar = reinterpret_cast<const T*>(sk_dyn) + (long long)(nt * 8 + g) * lds + 16 * t + (c << 6);
+                b0[nt] = *reinterpret_cast<const uint4*>(ar);
+                b1[nt] = *reinterpret_cast<const uint4*>(ar + 8);
+              } else {
+                b0[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6)));
+                b1[nt] = __ldg(reinterpret_cast<const uint4*>(a_row[nt] + (c << 6) + 8));
+              }
+            }
           }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            mma16816<DT>(acc[nt], buf[j][0].x, buf[j][2].x, buf[j][0].y, buf[j][2].y, b0[nt].x, b0[nt].y);
+            mma16816<DT>(acc[nt], buf[j][0].z, buf[j][2].z, buf[j][0].w, buf[j][2].w, b0[nt].z, b0[nt].w);
+            mma16816<DT>(acc[nt], buf[j][1].x, buf[j][3].x, buf[j][1].y, buf[j][3].y, b1[nt].x, b1[nt].y);
+            mma16816<DT>(acc[nt], buf[j][1].z, buf[j][3].z, buf[j][1].w, buf[j][3].w, b1[nt].z, b1[nt].w);
+          }
+          // refill this slot with the chunk PF positions ahead
+          int nc = c + PF * SK_WARPS, nrb = rb;
+          if (nc >= nchunks) { nc = warp + j * SK_WARPS; nrb = rb + gridDim.x; }
+          if (nrb < n_rb && nc < nchunks) load_w(buf[j], nrb, nc);
         }
       }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        mma16816<DT>(acc[nt], buf[0][0].x, buf[0][2].x, buf[0][0].y, buf[0][2].y, b0[nt].x, b0[nt].y);
-        mma16816<DT>(acc[nt], buf[0][0].z, buf[0][2].z, buf[0][0].w, buf[0][2].w, b0[nt].z, b0[nt].w);
-        mma16816<DT>(acc[nt], buf[0][1].x, buf[0][3].x, buf[0][1].y, buf[0][3].y, b1[nt].x, b1[nt].y);
-        mma16816<DT>(acc[nt], buf[0][1].z, buf[0][3].z, buf[0][1].w, buf[0][3].w, b1[nt].z, b1[nt].w);
-      }
-      // rotate the register ring and request the chunk PF items ahead (it may belong to this CTA's next row block)
-#pragma unroll
-      for (int j = 0; j + 1 < PF; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) buf[j][i] = buf[j + 1][i];
-      if (nrb < n_rb) { load_w(buf[PF - 1], nrb, nc); advance(); }
     }
     // accumulator fragment: c0/c1 = (weight row g, activation rows 2t, 2t+1), c2/c3 = (weight row g + 8, same)
 #pragma unroll
@@ -269,13 +272,14 @@ static cudaError_t launch_skinny(const SkinnyParams& p, cudaStream_t stream) {
     }                                                                                                                \
     return launch_kernel(skinny_gemm_kernel<DT, NT_, LN, PF_>, grid, block, dyn, stream, 1, p);                      \
   } while (0)
-  switch (nt) {
+  switch (nt) {   // the LayerNorm variants keep two chunks in flight (the row registers of the prologue crowd the ring)
     case 1:
-      if (deep) SK_CASE(1, 4);
+      if constexpr (LN) SK_CASE(1, 2);
+      else if (deep) SK_CASE(1, 4);
       else SK_CASE(1, 2);
-    case 2: SK_CASE(2, 3);
-    case 3: SK_CASE(3, 3);
-    default: SK_CASE(4, 3);
+    case 2: SK_CASE(2, (LN ? 2 : 3));
+    case 3: SK_CASE(3, (LN ? 2 : 3));
+    default: SK_CASE(4, (LN ? 2 : 3));
   }
 #undef SK_CASE
 }
