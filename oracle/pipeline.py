@@ -73,6 +73,36 @@ def denoise_loop(unet, scheduler, *, latents, cond, num_inference_steps, guidanc
 
 
 @torch.no_grad()
+def denoise_loop_simple(unet, scheduler, *, latents, s_img_proj_f, st_pose_f, masked_latents, height, width,
+                        num_inference_steps, num_images_per_prompt=1, guidance_scale=2.0, mask=None,
+                        dtype=torch.float32):
+    """`Simple_Stage2_InpaintDiffusionPipeline.__call__`, /root/reference/src/pipelines/stage2_inpaint_pipeline.py:
+    757-877: the stage-2 loop WITHOUT the predicted-embedding inputs — tokens are `s_img_proj_f` alone (:815), zeros for
+    the unconditional half (:818-820), no class embedding in the UNet call (:861-863); pose / mask / masked latents
+    are repeated for both CFG halves (:793-812)."""
+    bs = s_img_proj_f.shape[0]
+    rep = 2 * num_images_per_prompt
+    pose_cond = torch.cat([st_pose_f] * rep).to(dtype)                                    # :793-794
+    if mask is None:                                                                      # :797-800
+        mask = torch.cat([torch.ones((bs, 1, int(height / 8), int(width / 16))),
+                          torch.zeros((bs, 1, int(height / 8), int(width / 16)))], dim=3)
+    mask = torch.cat([mask.float()] * rep).to(dtype)                                      # :801-803
+    masked = torch.cat([masked_latents] * rep)                                            # :808
+    feature_f = s_img_proj_f.repeat(bs * num_images_per_prompt, 1, 1).to(dtype)           # :811
+    feature_f = torch.cat([torch.zeros_like(feature_f), feature_f], dim=0)                # :814-816
+    scheduler.set_timesteps(num_inference_steps)
+    latents = latents.to(dtype)
+    for t in scheduler.timesteps:
+        x = torch.cat([latents] * 2)                                                      # :853
+        x = scheduler.scale_model_input(x, t)
+        x9 = torch.cat([x, mask, masked], dim=1).to(dtype)                                # :856
+        eps = unet(x9, t, encoder_hidden_states=feature_f, my_pose_cond=pose_cond, return_dict=False)[0]
+        eps = cfg_combine(eps, guidance_scale)                                            # :866-868
+        latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :872
+    return latents
+
+
+@torch.no_grad()
 def denoise_loop_pcdms(unet, scheduler, *, latents, mask, simg_mask_latents, cond_pose, prompt_embeds,
                        negative_prompt_embeds, num_inference_steps, guidance_scale=2.0, dtype=torch.float32):
     """Demo driver loop, /root/reference/src/pipelines/PCDMs_pipeline.py:1062-1063 (CFG token batch = [negative ;

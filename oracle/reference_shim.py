@@ -210,3 +210,21 @@ def run_reference_prior_pipeline(ref_prior, *, s_embed, s_pose, t_pose, latents,
     out = pipe(s_embed=s_embed, s_pose=s_pose, t_pose=t_pose, num_images_per_prompt=1,
                num_inference_steps=num_inference_steps, latents=latents, guidance_scale=guidance_scale)
     return out[0] if isinstance(out, tuple) else (out["image_embeds"], out["negative_image_embeds"])
+
+
+def run_reference_simple_stage2_pipeline(cfg, oracle_unet_half, *, latents, s_img_proj_f, st_pose_f, masked_latents,
+                                         height, width, num_inference_steps, guidance_scale, num_images_per_prompt):
+    """Run Simple_Stage2_InpaintDiffusionPipeline.__call__ (stage2_inpaint_pipeline.py:757-877) unmodified on CPU over
+    the oracle UNet without class embedding (fp16, as the reference hard-codes :794,803,811,843,856).  Returns the
+    final latents (identity VAE)."""
+    _enable()
+    from diffusers.schedulers import DDIMScheduler
+    from src.pipelines.stage2_inpaint_pipeline import Simple_Stage2_InpaintDiffusionPipeline
+
+    pipe = Simple_Stage2_InpaintDiffusionPipeline(vae=_EncodeVAE(masked_latents), unet=_DemoUNetAdapter(oracle_unet_half, cfg),
+                                                  scheduler=DDIMScheduler())
+    h, w = latents.shape[-2:]
+    out = pipe(height=height, width=width, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+               num_images_per_prompt=num_images_per_prompt, latents=latents.half(), output_type="pt",
+               vae_image=torch.zeros(1, 3, h * 8, w * 8), s_img_proj_f=s_img_proj_f, st_pose_f=st_pose_f)
+    return out.images

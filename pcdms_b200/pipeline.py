@@ -334,6 +334,50 @@ class B200Stage2InpaintPipeline(_B200DenoisingPipeline):
         return self._finish(latents, output_type, return_dict)
 
 
+class B200SimpleStage2InpaintPipeline(_B200DenoisingPipeline):
+    """`Simple_Stage2_InpaintDiffusionPipeline` (/root/reference/src/pipelines/stage2_inpaint_pipeline.py:544-877): the
+    stage-2 call surface without the predicted-embedding path — tokens are `s_img_proj_f` alone, the UNet has no class
+    embedding; `pred_t_img_embed` is accepted and ignored, as in the reference (:783, never read)."""
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None, latents=None,
+                 prompt_embeds=None, negative_prompt_embeds=None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback=None, callback_steps: int = 1, cross_attention_kwargs=None,
+                 guidance_rescale: float = 0.0,
+                 vae_image=None, mask=None, s_img_proj_f=None, st_pose_f=None, pred_t_img_embed=None,
+                 masked_latents=None):
+        self._common_checks(cross_attention_kwargs, guidance_rescale, guidance_scale, height, width, callback_steps)
+        dev, dt = self.unet.device, self.unet.dtype
+        bs, num, _ = s_img_proj_f.shape
+        if bs != 1:
+            raise NotImplementedError("the reference drivers run one source/target pair per call (bs == 1)")
+        n = bs * num_images_per_prompt
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        B = 2 * n
+        pose_cond = torch.cat([st_pose_f.to(dev)] * B).to(dt)                                    # :793-794
+        if mask is None:                                                                          # :797-800
+            m1 = torch.ones((bs, 1, h, w // 2), dtype=torch.float32, device=dev)
+            m0 = torch.zeros((bs, 1, h, w // 2), dtype=torch.float32, device=dev)
+            mask = torch.cat([m1, m0], dim=3)
+        mask = torch.cat([mask.to(dev, torch.float32)] * B)                                       # :801-803
+        if masked_latents is None:                                                                # :806-807
+            if self.vae is None:
+                raise ValueError("pass masked_latents= when the pipeline has no VAE")
+            masked_latents = self.vae.encode(vae_image.to(device=dev, dtype=dt)).latent_dist.sample(generator=generator)
+            masked_latents = masked_latents * self.vae.config.scaling_factor
+        masked_latents = torch.cat([masked_latents.to(dev, torch.float32)] * B)                   # :808
+        feature_f = s_img_proj_f.to(dev).repeat(n, 1, 1).to(dt)                                   # :811
+        feature_f = torch.cat([torch.zeros_like(feature_f), feature_f], dim=0)                    # :814-816
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        latents = self._initial_latents(latents, n, h, w, generator)
+        extra = torch.cat([mask, masked_latents], dim=1)
+        latents = self._denoise(latents, extra, pose_cond, feature_f, None, guidance_scale, num_inference_steps, eta,
+                                generator, callback, callback_steps)
+        return self._finish(latents, output_type, return_dict)
+
+
 class B200PCDMsPipeline(_B200DenoisingPipeline):
     """Demo driver surface (PCDMs_pipeline.py:889-926 signature; pcdms_demo.ipynb call): image-token conditioning comes
     in as `prompt_embeds` / `negative_prompt_embeds`, there is no class embedding."""

@@ -91,3 +91,21 @@ def test_reference_demo_pipeline_equals_oracle_loop():
     want = rs.run_reference_demo_pipeline(cfg, oracle, **kw)
     got = denoise_loop_pcdms(oracle, OracleDDIMScheduler(), dtype=torch.float16, **kw)
     assert torch.equal(got, want)
+
+
+def test_reference_simple_stage2_pipeline_equals_oracle_loop():
+    """The reference's own Simple_Stage2_InpaintDiffusionPipeline.__call__ (stage2_inpaint_pipeline.py:757-877; fp16 as it
+    hard-codes) against oracle.pipeline.denoise_loop_simple: bit-equal."""
+    from dataclasses import replace
+    from oracle.pipeline import denoise_loop_simple
+    cfg = replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True)
+    oracle = make_unet(cfg, seed=12).half()
+    h, w = 8, 16
+    g = torch.Generator().manual_seed(51)
+    kw = dict(latents=torch.randn(2, 4, h, w, generator=g), masked_latents=torch.randn(1, 4, h, w, generator=g).half(),
+              st_pose_f=(0.1 * torch.randn(1, cfg.block_out_channels[0], h, w, generator=g)).half(),
+              s_img_proj_f=torch.randn(1, 7, cfg.cross_attention_dim, generator=g).half(), height=h * 8, width=w * 8,
+              num_inference_steps=3, guidance_scale=2.0, num_images_per_prompt=2)
+    want = rs.run_reference_simple_stage2_pipeline(cfg, oracle, **kw)
+    got = denoise_loop_simple(oracle, OracleDDIMScheduler(), dtype=torch.float16, **kw)
+    assert torch.equal(got, want)

@@ -53,6 +53,22 @@ def _demo_case(dtype, device, steps):
     return pipe, call, want
 
 
+def _simple_case(dtype, device, steps):
+    """Simple_Stage2_InpaintDiffusionPipeline (stage2_inpaint_pipeline.py:544-877): tokens only, no class embedding."""
+    from oracle.pipeline import denoise_loop_simple
+    from pcdms_b200.pipeline import B200SimpleStage2InpaintPipeline
+    cfg = replace(UNetConfig.tiny(in_channels=9, stage2=False), use_pose_cond=True)
+    o, m = _unet(cfg, dtype, device)
+    h, w = 8, 16
+    kw = dict(latents=torch.randn(2, 4, h, w, generator=_g(1)), masked_latents=torch.randn(1, 4, h, w, generator=_g(2)),
+              st_pose_f=0.1 * torch.randn(1, 64, h, w, generator=_g(3)), s_img_proj_f=torch.randn(1, 7, 128, generator=_g(4)),
+              height=h * 8, width=w * 8, num_inference_steps=steps, guidance_scale=2.0, num_images_per_prompt=2)
+    want = denoise_loop_simple(o, OracleDDIMScheduler(), **kw)
+    pipe = B200SimpleStage2InpaintPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    call = lambda: pipe(output_type="latent", pred_t_img_embed=torch.zeros(1, 1, 128), **kw).images
+    return pipe, call, want
+
+
 def _stage3_case(dtype, device, steps):
     cfg = UNetConfig.tiny(in_channels=8, stage2=False)
     o, m = _unet(cfg, dtype, device)
@@ -67,7 +83,7 @@ def _stage3_case(dtype, device, steps):
     return pipe, call, want
 
 
-@pytest.mark.parametrize("case", [_demo_case, _stage3_case])
+@pytest.mark.parametrize("case", [_demo_case, _stage3_case, _simple_case])
 def test_driver_orchestration_matches_oracle(case):
     pipe, call, want = case(torch.float32, "cpu", 4)
     pipe.use_cuda_graph = False
@@ -135,7 +151,7 @@ def _rel(got, want):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [_demo_case, _stage3_case])
+@pytest.mark.parametrize("case", [_demo_case, _stage3_case, _simple_case])
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_drivers_gpu(case, use_graph):
     pipe, call, want = case(torch.float16, "cuda", 8)
@@ -212,3 +228,13 @@ def test_drivers_against_reference_goldens_gpu():
                width=128, num_images_per_prompt=1, guidance_scale=i["guidance_scale"], latents=i["latents"],
                num_inference_steps=i["num_inference_steps"], output_type="latent").images
     assert _rel(got, g["latents"].float()) < 4e-3
+    g = torch.load(gold / "ref_simple_tiny.pt")            # Simple_Stage2_InpaintDiffusionPipeline (no class embedding)
+    _, m = _unet(cfg, torch.float16, "cuda", seed=g["seed"])
+    i = g["inputs"]
+    from pcdms_b200.pipeline import B200SimpleStage2InpaintPipeline
+    pipe = B200SimpleStage2InpaintPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    got = pipe(height=i["height"], width=i["width"], num_inference_steps=i["num_inference_steps"],
+               guidance_scale=i["guidance_scale"], num_images_per_prompt=i["num_images_per_prompt"], latents=i["latents"],
+               s_img_proj_f=i["s_img_proj_f"], st_pose_f=i["st_pose_f"], masked_latents=i["masked_latents"],
+               output_type="latent").images
+    assert got.shape == (2, 4, 8, 16) and _rel(got, g["latents"].float()) < 4e-3

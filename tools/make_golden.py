@@ -9,6 +9,7 @@ Fixtures (tiny topology-preserving config so the files stay small):
                         the reference hard-codes them; DDIM, 4 steps, guidance 2.0, 2 images per prompt)
   ref_stage3_tiny.pt    inputs + final latents of Stage3_RefinedPipeline.__call__ (fp16 loop tensors, fp32 UNet; DDIM)
   ref_demo_tiny.pt      inputs + final latents of PCDMsPipeline.__call__ (the pcdms_demo.ipynb driver; fp16; DDIM)
+  ref_simple_tiny.pt    inputs + final latents of Simple_Stage2_InpaintDiffusionPipeline.__call__ (fp16; DDIM, 3 steps)
   ref_prior_tiny.pt     inputs + outputs of Stage1_PriorTransformer.forward (plain and test_flag) and of
                         Stage1_PriorPipeline.__call__ (fp32, 4 UnCLIP steps, guidance 0 as the batch-test driver) with
                         the variance noise the global generator produced
@@ -78,6 +79,15 @@ def main():
     outd = rs.run_reference_demo_pipeline(cfgd, ud, **kwd)
     torch.save({"seed": 9, "inputs": kwd, "latents": outd}, GOLD / "ref_demo_tiny.pt")
     print("ref_demo_tiny", outd.shape, outd.dtype)
+
+    us = make_unet(cfgd, seed=12).half()
+    kws = dict(latents=torch.randn(2, 4, h, w, generator=g), masked_latents=torch.randn(1, 4, h, w, generator=g).half(),
+               st_pose_f=(0.1 * torch.randn(1, cfgd.block_out_channels[0], h, w, generator=g)).half(),
+               s_img_proj_f=torch.randn(1, 7, cfgd.cross_attention_dim, generator=g).half(), height=h * 8, width=w * 8,
+               num_inference_steps=3, guidance_scale=2.0, num_images_per_prompt=2)
+    outs = rs.run_reference_simple_stage2_pipeline(cfgd, us, **kws)
+    torch.save({"seed": 12, "inputs": kws, "latents": outs}, GOLD / "ref_simple_tiny.pt")
+    print("ref_simple_tiny", outs.shape, outs.dtype)
 
     from oracle.prior import TINY, make_prior, make_prior_inputs
     op = make_prior(seed=13, **TINY)
