@@ -41,6 +41,7 @@ struct SkinnyParams {
   const float* ln_gamma;         // LN variant: A is layer-normalised over K on the way in (fused torch.nn.LayerNorm)
   const float* ln_beta;
   float ln_eps;
+  int w_static;                  // W is not written by the stream predecessor: it may be read before the dependency wait
 };
 
 template <int DT>
@@ -96,9 +97,9 @@ skinny_gemm_kernel(const SkinnyParams p) {
     a_row[nt] = A + (long long)(a_ok[nt] ? nt * 8 + g : 0) * p.lda + 16 * t;
   }
 
-  // Weights never depend on the stream predecessor: the first PF chunks of this warp are requested BEFORE the
-  // programmatic-dependency wait, so the weight stream of this kernel overlaps the tail (and, in a chain of small
-  // kernels, most of the body) of the previous one; only activations wait.
+  // Model weights do not depend on the stream predecessor (PCDM_FLAG_W_STATIC): the first PF chunks of this warp are
+  // then requested BEFORE the programmatic-dependency wait, so the weight stream of this kernel overlaps the tail (and,
+  // in a chain of small kernels, most of the body) of the previous one; only activations wait.
   auto load_w = [&](uint4 (&dst)[4], int rb, int chunk) {
     const T* q = w_lane + (long long)rb * SK_ROWS * p.K + (chunk << 6);
     dst[0] = ldg_stream(q); dst[1] = ldg_stream(q + 8);
@@ -108,12 +109,13 @@ skinny_gemm_kernel(const SkinnyParams p) {
   // buf[j]; when slot j has been consumed it is refilled with the chunk PF positions ahead — in the same row block, or
   // slot j of the first group of this CTA's NEXT row block — so PF chunks (or the whole next row block) are in flight.
   uint4 buf[PF][4];
+  if (!p.w_static) pdl_wait();   // W produced on this stream (e.g. K of an attention written as a GEMM): wait first
 #pragma unroll
   for (int j = 0; j < PF; ++j) {
     const int c = warp + j * SK_WARPS;
     if (c < nchunks && (int)blockIdx.x < n_rb) load_w(buf[j], blockIdx.x, c);
   }
-  pdl_wait();
+  if (p.w_static) pdl_wait();
   const int lds = p.K + 8;   // padded row stride of the normalised activations
   if (LN) {
     T* act_s = reinterpret_cast<T*>(sk_dyn);
@@ -294,6 +296,7 @@ int skinny_gemm_try(const void* a, long long lda, const void* w, void* out, long
   if (ln_gamma && ((size_t)M * (K + 8) * 2 > (size_t)SK_LN_SMEM_LIMIT || K > 2048)) return 0;   // row held in registers
   SkinnyParams p;
   p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
+  p.w_static = (flags & PCDM_FLAG_W_STATIC) ? 1 : 0;
   p.a = a; p.lda = lda; p.w = w; p.out = out; p.ldo = ldo; p.bias = bias;
   p.rowvec = rowvec; p.ld_rowvec = ld_rowvec; p.hw = rows_per_image > 0 ? rows_per_image : 1;
   p.residual = residual; p.ldr = ldr;

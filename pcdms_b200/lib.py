@@ -17,7 +17,7 @@ HEADER_PATH = PKG_DIR.parent / "include" / "pcdm_b200.h"
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
 DT_F16, DT_BF16 = 0, 1
-FLAG_GEGLU, FLAG_OUT_F32, FLAG_SILU, FLAG_GELU, FLAG_PAD_BR = 1, 2, 4, 8, 16
+FLAG_GEGLU, FLAG_OUT_F32, FLAG_SILU, FLAG_GELU, FLAG_PAD_BR, FLAG_W_STATIC = 1, 2, 4, 8, 16, 32
 
 
 class PcdmError(RuntimeError):

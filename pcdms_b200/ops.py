@@ -70,8 +70,10 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # K1/K2
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0):
-    """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual)."""
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True):
+    """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual).
+    w_static: `w` holds model weights (not written by the kernel launched just before on this stream); pass False when
+    `w` is an activation (the VAE's QK^T / PV products written as GEMMs)."""
     lib = _l.load()
     M, k1 = a.shape
     N, K = w.shape
@@ -86,7 +88,7 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     flags = ((_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) |
-             (_l.FLAG_GELU if gelu else 0))
+             (_l.FLAG_GELU if gelu else 0) | (_l.FLAG_W_STATIC if w_static else 0))
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
@@ -108,7 +110,8 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
         out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
     assert out.shape == (M, N) and out.stride(1) == 1
     scratch = None if M <= 32 and K <= 2048 and M * (K + 8) * 2 <= 100 * 1024 else torch.empty((M, K), device=x.device, dtype=x.dtype)
-    flags = ((_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_GELU if gelu else 0))
+    flags = ((_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_GELU if gelu else 0) |
+             _l.FLAG_W_STATIC)
     rc = lib.pcdm_ln_gemm(
         _l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)), C.c_float(eps), _l.ptr(scratch),
         _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),

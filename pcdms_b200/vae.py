@@ -327,10 +327,10 @@ class B200AutoencoderKL:
         vt = torch.empty((C, S), device=x.device, dtype=dt)
         for b in range(B):
             rows = slice(b * S, (b + 1) * S)
-            ops.gemm(q[rows], k[rows], out=scores, out_f32=True)
+            ops.gemm(q[rows], k[rows], out=scores, out_f32=True, w_static=False)
             ops.softmax_rows(scores, C ** -0.5, dt, out=probs)
-            ops.gemm(w[f"{p}.to_v.weight"], hn[rows], out=vt)
-            ops.gemm(probs, vt, out=o[rows], bias=w[f"{p}.to_v.bias"])
+            ops.gemm(w[f"{p}.to_v.weight"], hn[rows], out=vt, w_static=False)
+            ops.gemm(probs, vt, out=o[rows], bias=w[f"{p}.to_v.bias"], w_static=False)
         out = ops.gemm(o, w[f"{p}.to_out.0.weight"], bias=w[f"{p}.to_out.0.bias"], residual=x.view(B * S, C))
         return out.view(B, H, W, C)
 

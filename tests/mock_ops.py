@@ -18,7 +18,7 @@ def _rt(x, dtype):
 
 
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0):
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
     if geglu:
