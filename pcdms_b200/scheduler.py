@@ -33,6 +33,11 @@ def _alphas_cumprod(num_train_timesteps, beta_start, beta_end, beta_schedule):
         betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
     elif beta_schedule == "linear":
         betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+    elif beta_schedule == "squaredcos_cap_v2":   # diffusers betas_for_alpha_bar (stage-1 training: stage1_train_prior_model.py:155)
+        def abar(x):
+            return math.cos((x + 0.008) / 1.008 * math.pi / 2) ** 2
+        n = num_train_timesteps
+        betas = torch.tensor([min(1 - abar((i + 1) / n) / abar(i / n), 0.999) for i in range(n)], dtype=torch.float32)
     else:
         raise NotImplementedError(beta_schedule)
     return torch.cumprod(1.0 - betas, dim=0)
@@ -115,11 +120,14 @@ class B200DDIMScheduler:
 
 
 class B200DDPMScheduler:
-    """Only what the training caller needs (stage2_train_inpaint_model.py:361): add_noise on the B200."""
+    """Only what the training callers need: add_noise on the B200 (stage2_train_inpaint_model.py:361 with the SD
+    "scaled_linear" schedule; stage1_train_prior_model.py:155,287 with `beta_schedule="squaredcos_cap_v2",
+    prediction_type="sample"`)."""
 
-    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear"):
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 prediction_type="epsilon"):
         self.config = _AttrDict(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
-                                beta_schedule=beta_schedule)
+                                beta_schedule=beta_schedule, prediction_type=prediction_type)
         self.alphas_cumprod = _alphas_cumprod(num_train_timesteps, beta_start, beta_end, beta_schedule)
 
     def add_noise(self, original_samples, noise, timesteps):

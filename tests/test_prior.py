@@ -155,6 +155,20 @@ def test_b200_unclip_scheduler_tables_match_oracle():
         p.step(torch.zeros(1, 4), 500, torch.zeros(1, 4))       # no CPU path
 
 
+def test_stage1_training_noise_schedule():
+    """stage1_train_prior_model.py:155,287: DDPMScheduler(beta_schedule='squaredcos_cap_v2', prediction_type='sample')
+    .add_noise — the B200 class carries the same cumulative-alpha table as the sampler's schedule (the per-element
+    arithmetic is the schedule-independent pcdm_add_noise kernel, tests/test_kernels_gpu.py); no CPU path."""
+    from pcdms_b200.scheduler import B200DDPMScheduler
+    s = B200DDPMScheduler(beta_schedule="squaredcos_cap_v2", prediction_type="sample")
+    assert torch.equal(s.alphas_cumprod, _sched().alphas_cumprod) and s.config.prediction_type == "sample"
+    assert torch.equal(s.alphas_cumprod, _sched(B200UnCLIPScheduler).alphas_cumprod)
+    with pytest.raises(RuntimeError):
+        s.add_noise(torch.zeros(2, 8), torch.zeros(2, 8), torch.tensor([0, 999]))
+    with pytest.raises(NotImplementedError):
+        B200DDPMScheduler(beta_schedule="sigmoid")
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # host logic of the product classes (mock kernels, CPU)
 # ------------------------------------------------------------------------------------------------------------------
