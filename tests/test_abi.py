@@ -43,3 +43,39 @@ def test_product_does_not_import_oracle():
     root = pathlib.Path(__file__).resolve().parent.parent / "pcdms_b200"
     for p in root.rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M), p
+
+
+def test_new_entry_points_validate_before_touching_the_device():
+    """Argument checks of the entry points added for the stage-1 prior / CLIP encoder run before any CUDA call, so
+    they can be exercised here: head widths, null pointers, shapes, dtypes."""
+    from pcdms_b200 import lib
+    cdll = lib.load()
+    p, f, ll, i = ctypes.c_void_p(256), ctypes.c_float, ctypes.c_longlong, ctypes.c_int
+    # attention: head_dim must be 64 or 128; strides multiples of 8
+    rc = cdll.pcdm_attention_hd(p, ll(640), p, ll(640), p, ll(640), p, ll(640), i(1), i(8), i(6), i(6), i(80), f(0.1),
+                                i(0), None)
+    assert rc == lib.ERR_UNSUPPORTED and b"head_dim" in cdll.pcdm_last_error()
+    rc = cdll.pcdm_attention_hd(None, ll(128), p, ll(128), p, ll(128), p, ll(128), i(1), i(1), i(6), i(6), i(128), f(0.1),
+                                i(0), None)
+    assert rc == lib.ERR_INVALID
+    rc = cdll.pcdm_attention_hd(p, ll(130), p, ll(128), p, ll(128), p, ll(128), i(1), i(1), i(6), i(6), i(128), f(0.1),
+                                i(0), None)
+    assert rc == lib.ERR_UNSUPPORTED
+    # LayerNorm + GEMM: K % 64, N % 32, null gamma
+    rc = cdll.pcdm_ln_gemm(p, ll(72), p, p, f(1e-5), None, p, p, ll(64), None, None, ll(0), i(1), None, ll(0), i(4), i(64),
+                           i(72), i(0), i(0), None)
+    assert rc == lib.ERR_UNSUPPORTED
+    rc = cdll.pcdm_ln_gemm(p, ll(64), None, p, f(1e-5), None, p, p, ll(64), None, None, ll(0), i(1), None, ll(0), i(4),
+                           i(64), i(64), i(0), i(0), None)
+    assert rc == lib.ERR_INVALID
+    # UnCLIP step: null pointers, dtype codes, a noisy step without noise
+    row = (ctypes.c_float * 8)(0.5, 0.5, 0.1, 10.0, 1.0, 0.0, 0.0, 0.0)
+    assert cdll.pcdm_unclip_step(None, i(2), p, p, p, i(2), row, ll(8), None) == lib.ERR_INVALID
+    assert cdll.pcdm_unclip_step(p, i(7), p, p, p, i(2), row, ll(8), None) == lib.ERR_INVALID
+    assert cdll.pcdm_unclip_step(p, i(2), p, None, p, i(2), row, ll(8), None) == lib.ERR_INVALID
+    assert b"noise" in cdll.pcdm_last_error()
+    rc = cdll.pcdm_cfg_unclip_step(p, ll(8), p, p, i(0), ll(4), p, p, p, f(2.0), i(1), i(2), i(8), None, None, None)
+    assert rc == lib.ERR_INVALID            # ld_xin < E
+    # hooks are plain setters
+    assert cdll.pcdm_set_skinny_gemm(i(1)) == 0 and cdll.pcdm_set_attention_small(i(1)) == 0
+    assert cdll.pcdm_set_gemm_debug(i(0)) == 0
