@@ -1,0 +1,64 @@
+"""One packed weight arena per model, shipped to the other ranks with ONE broadcast.
+
+The reference's drivers start one process per GPU and every process `torch.load`s the full checkpoints from disk
+(/root/reference/stage2_batchtest_inpaint_model.py:103-104,266-285; stage1_batchtest_prior_model.py:53-61,170-183;
+stage3_batchtest_refined_model.py likewise).  Here rank 0 packs a model once (`load_state_dict`), `consolidate()` moves
+every packed tensor into one contiguous arena, and `broadcast_weights()` ships layout + arena — a single
+`ncclBroadcast` over NVLink / NVSwitch per model; no collective is used afterwards (the sampling loops shard by
+independent work items).
+
+A model class mixes this in and keeps its packed tensors in `self._w` (name -> tensor on `self._device`); anything else
+the forward needs must live in `_w` too, so that a receiving rank is complete after the broadcast.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class WeightArenaMixin:
+    _arena = None
+    _arena_layout = None
+
+    def _after_adopt(self):
+        """Hook: invalidate caches derived from the weights."""
+
+    def consolidate(self):
+        """Move every packed tensor into one contiguous arena (256-byte aligned slots); returns the arena."""
+        layout, off = [], 0
+        for k, t in self._w.items():
+            nbytes = t.numel() * t.element_size()
+            layout.append((k, tuple(t.shape), t.dtype, off, nbytes))
+            off = (off + nbytes + 255) // 256 * 256
+        arena = torch.empty(off, dtype=torch.uint8, device=self._device)
+        self._adopt(arena, layout, copy_from=self._w)
+        return arena
+
+    def _adopt(self, arena, layout, copy_from=None):
+        new = {}
+        for k, shape, dtype, off, nbytes in layout:
+            view = arena[off:off + nbytes].view(dtype).view(shape)
+            if copy_from is not None:
+                view.copy_(copy_from[k])
+            new[k] = view
+        self._w = new
+        self._arena, self._arena_layout = arena, layout
+        self._loaded = True
+        self._after_adopt()
+
+    def broadcast_weights(self, src: int = 0, group=None):
+        """Rank `src` holds packed weights; every other rank receives the layout (object broadcast) and then the arena
+        itself with ONE broadcast.  Returns the arena size in bytes."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        if rank == src:
+            if self._arena is None:
+                self.consolidate()
+            meta = [self._arena_layout, self._arena.numel()]
+        else:
+            meta = [None, None]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        if rank != src:
+            arena = torch.empty(meta[1], dtype=torch.uint8, device=self._device)
+            self._adopt(arena, meta[0])
+        dist.broadcast(self._arena, src=src, group=group)
+        return self._arena.numel()

@@ -25,6 +25,7 @@ from typing import Dict
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 from .unet import _Config
 
 # OpenCLIP ViT-H/14 (laion2B) vision tower as shipped in the HF checkpoint the reference points at
@@ -47,7 +48,7 @@ class CLIPVisionOutput(dict):
             raise AttributeError(k) from e
 
 
-class B200CLIPVisionModelWithProjection:
+class B200CLIPVisionModelWithProjection(WeightArenaMixin):
     def __init__(self, config=None, dtype: torch.dtype = torch.float16, device="cuda", **kw):
         cfg = dict(_DEFAULT_CONFIG)
         src = dict(config.to_dict() if hasattr(config, "to_dict") else (config or {}))
@@ -73,7 +74,6 @@ class B200CLIPVisionModelWithProjection:
         self.config = c
         self._dtype, self._device = dtype, torch.device(device)
         self._w: Dict[str, torch.Tensor] = {}
-        self._pos_raw = None
         self._pos_cache = {}
         self._loaded = False
         self.patch_k = c.num_channels * c.patch_size * c.patch_size
@@ -176,9 +176,10 @@ class B200CLIPVisionModelWithProjection:
 
         pw = f(f"{v}.embeddings.patch_embedding.weight").reshape(C, self.patch_k)
         w["patch.weight"] = mat(torch.cat([pw, pw.new_zeros(C, self.patch_k_padded - self.patch_k)], dim=1))
-        self._pos_raw = f(f"{v}.embeddings.position_embedding.weight")          # [1 + n, C]
-        self._cls_raw = f(f"{v}.embeddings.class_embedding").reshape(1, C)
+        w["_pos_raw"] = vec(f(f"{v}.embeddings.position_embedding.weight"))     # [1 + n, C] fp32 (interpolated on demand)
+        w["_cls_raw"] = vec(f(f"{v}.embeddings.class_embedding").reshape(1, C))
         self._pos_cache = {}
+        self._arena = None
         for n in ("pre_layrnorm", "post_layernorm"):
             w[f"{n}.weight"], w[f"{n}.bias"] = vec(f(f"{v}.{n}.weight")), vec(f(f"{v}.{n}.bias"))
         w["proj.weight"] = mat(f("visual_projection.weight"))
@@ -196,6 +197,9 @@ class B200CLIPVisionModelWithProjection:
         self._loaded = True
         from types import SimpleNamespace
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def _after_adopt(self):
+        self._pos_cache = {}
 
     def synthetic_state_dict(self, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
         dev = torch.device(device) if device is not None else self._device
@@ -220,7 +224,7 @@ class B200CLIPVisionModelWithProjection:
         (bicubically interpolated to the gh x gw grid under `interpolate_pos_encoding=True`, as transformers does)."""
         key = (gh, gw)
         if key not in self._pos_cache:
-            pos = self._pos_raw
+            pos = self._w["_pos_raw"].cpu()          # host-side, once per grid (cached below)
             n, C = pos.shape[0] - 1, pos.shape[1]
             patch = pos[1:]
             if not (gh * gw == n and gh == gw):
@@ -232,7 +236,7 @@ class B200CLIPVisionModelWithProjection:
                 patch = torch.nn.functional.interpolate(patch.reshape(1, s, s, C).permute(0, 3, 1, 2), size=(gh, gw),
                                                         mode="bicubic", align_corners=False)
                 patch = patch.permute(0, 2, 3, 1).reshape(gh * gw, C)
-            full = torch.cat([self._cls_raw + pos[:1], patch], dim=0)
+            full = torch.cat([self._w["_cls_raw"].cpu() + pos[:1], patch], dim=0)
             self._pos_cache[key] = full.to(device=self._device, dtype=self._dtype).contiguous()
         return self._pos_cache[key]
 

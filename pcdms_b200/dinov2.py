@@ -23,6 +23,7 @@ from typing import Dict
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 from .unet import _Config
 
 _DEFAULT_CONFIG = dict(hidden_size=1536, num_hidden_layers=40, num_attention_heads=24, mlp_ratio=4, hidden_act="gelu",
@@ -35,7 +36,7 @@ def _pad(n, m):
     return (n + m - 1) // m * m
 
 
-class B200Dinov2Model:
+class B200Dinov2Model(WeightArenaMixin):
     def __init__(self, config=None, dtype: torch.dtype = torch.float16, device="cuda", **kw):
         cfg = dict(_DEFAULT_CONFIG)
         src = dict(config.to_dict() if hasattr(config, "to_dict") else (config or {}))
@@ -53,7 +54,6 @@ class B200Dinov2Model:
         self.config = c
         self._dtype, self._device = dtype, torch.device(device)
         self._w: Dict[str, torch.Tensor] = {}
-        self._pos_raw = None
         self._pos_cache = {}
         self._loaded = False
         hf = int(c.hidden_size * c.mlp_ratio)
@@ -153,9 +153,10 @@ class B200Dinov2Model:
         pw = f("embeddings.patch_embeddings.projection.weight").reshape(C, self.patch_k)
         w["patch.weight"] = mat(torch.cat([pw, pw.new_zeros(C, self.patch_k_padded - self.patch_k)], dim=1))
         w["patch.bias"] = vec(f("embeddings.patch_embeddings.projection.bias"))
-        self._pos_raw = f("embeddings.position_embeddings")
-        self._cls_raw = f("embeddings.cls_token").reshape(1, C)
+        w["_pos_raw"] = vec(f("embeddings.position_embeddings"))               # [1, 1 + n, C] fp32 (interpolated on demand)
+        w["_cls_raw"] = vec(f("embeddings.cls_token").reshape(1, C))
         self._pos_cache = {}
+        self._arena = None
         w["layernorm.weight"], w["layernorm.bias"] = vec(f("layernorm.weight")), vec(f("layernorm.bias"))
         # SwiGLU: hidden = silu(x1) * x2 with (x1 | x2) = chunk(weights_in(x)): x2 is the value, x1 the gate.  Rows are
         # interleaved in groups of [32 value | 32 gate] for the gated GEMM epilogue; the hidden width is zero-padded.
@@ -184,6 +185,9 @@ class B200Dinov2Model:
         self._loaded = True
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
+    def _after_adopt(self):
+        self._pos_cache = {}
+
     def synthetic_state_dict(self, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
         dev = torch.device(device) if device is not None else self._device
         g = torch.Generator(device=dev).manual_seed(seed)
@@ -209,7 +213,7 @@ class B200Dinov2Model:
         interpolated to the gh x gw grid when it differs from the trained one (transformers' interpolate_pos_encoding)."""
         key = (gh, gw)
         if key not in self._pos_cache:
-            pos = self._pos_raw                                   # [1, 1 + n, C] fp32
+            pos = self._w["_pos_raw"].cpu()                       # [1, 1 + n, C] fp32, host-side once per grid
             n = pos.shape[1] - 1
             C = pos.shape[-1]
             patch = pos[:, 1:]
@@ -218,7 +222,7 @@ class B200Dinov2Model:
                 patch = torch.nn.functional.interpolate(patch.reshape(1, s, s, C).permute(0, 3, 1, 2), size=(gh, gw),
                                                         mode="bicubic", align_corners=False)
                 patch = patch.permute(0, 2, 3, 1).reshape(1, gh * gw, C)
-            full = torch.cat([self._cls_raw + pos[0, :1], patch[0]], dim=0)
+            full = torch.cat([self._w["_cls_raw"].cpu() + pos[0, :1], patch[0]], dim=0)
             self._pos_cache[key] = full.to(device=self._device, dtype=self._dtype).contiguous()
         return self._pos_cache[key]
 

@@ -20,13 +20,14 @@ from typing import Dict
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 
 
 def _pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
-class _Module:
+class _Module(WeightArenaMixin):
     def __init__(self, dtype, device):
         self._dtype, self._device = dtype, torch.device(device)
         self._w: Dict[str, torch.Tensor] = {}
@@ -39,6 +40,22 @@ class _Module:
     @property
     def device(self):
         return self._device
+
+    def synthetic_state_dict(self, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
+        """Seeded random weights with the reference's key names and shapes (benches, tests)."""
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for k, shp in self.state_dict_shapes().items():
+            if len(shp) >= 2:
+                fan_in = 1
+                for d in shp[1:]:
+                    fan_in *= d
+                sd[k] = torch.randn(shp, generator=g) * fan_in ** -0.5
+            elif k.endswith(".weight"):      # LayerNorm scale
+                sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+            else:
+                sd[k] = 0.05 * torch.randn(shp, generator=g)
+        return sd
 
     def to(self, *args, **kwargs):
         for a in list(args) + list(kwargs.values()):
@@ -92,6 +109,7 @@ class B200ImageProjModel_p(_Module):
         for k, v in state_dict.items():
             is_mat = k in ("net.0.weight", "net.4.weight")
             self._w[k] = v.detach().to(device=dev, dtype=dt if is_mat else torch.float32).contiguous()
+        self._arena = None
         self._loaded = True
 
     @torch.no_grad()
@@ -143,6 +161,7 @@ class B200ControlNetConditioningEmbedding(_Module):
             b[:cout] = state_dict[f"{k}.bias"].detach().float()
             self._w[f"{k}.weight"] = ops.pack_conv3x3_weight(wt, dt).to(dev)
             self._w[f"{k}.bias"] = b.to(dev)
+        self._arena = None
         self._loaded = True
 
     @torch.no_grad()

@@ -26,6 +26,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 from .scheduler import B200UnCLIPScheduler
 from .unet import _Config
 
@@ -52,7 +53,7 @@ def _ln_then_gemm(x, gamma, beta, eps, w, **kw):
     return ops.gemm(ops.layernorm(x, gamma, beta, eps), w, **kw)
 
 
-class B200Stage1PriorTransformer:
+class B200Stage1PriorTransformer(WeightArenaMixin):
     # LayerNorm fused in front of the consuming GEMM (pcdm_ln_gemm: 106 instead of 147 launches per step) measured
     # SLOWER on B200 (1.18 vs 0.94 ms per step, profiles/r1_s3_prior_ab.md): every CTA of the GEMM re-normalises the
     # rows on its critical path, behind the dependency wait.  Kept as an option; tools/bench_stage1.py flips it.
@@ -241,6 +242,7 @@ class B200Stage1PriorTransformer:
             for n in ("norm1", "norm3"):
                 w[f"{i}.{n}.weight"], w[f"{i}.{n}.bias"] = vec(f(f"{b}.{n}.weight")), vec(f(f"{b}.{n}.bias"))
         w["norm_out.weight"], w["norm_out.bias"] = vec(f("norm_out.weight")), vec(f("norm_out.bias"))
+        self._arena = None
         self._loaded = True
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 

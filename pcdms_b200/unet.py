@@ -24,6 +24,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 
 _DEFAULT_CONFIG = dict(
     sample_size=64, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True, freq_shift=0,
@@ -127,7 +128,7 @@ class B200Attention:
         return out.view(B, S, C)
 
 
-class B200UNet2DConditionModel:
+class B200UNet2DConditionModel(WeightArenaMixin):
     def __init__(self, dtype: torch.dtype = torch.float16, device="cuda", **config):
         cfg = dict(_DEFAULT_CONFIG)
         unknown = set(config) - set(cfg) - {"use_pose_cond"}
@@ -502,6 +503,7 @@ class B200UNet2DConditionModel:
             elif op[0] in ("down", "up"):
                 w[f"{op[1]}.weight"], w[f"{op[1]}.bias"] = conv(f"{op[1]}.weight"), f32(f"{op[1]}.bias")
         self._loaded = True
+        self._arena = None       # a consolidated arena of earlier weights is stale now
         self._ctx_cache = None
         self._pose_cache = None
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
@@ -510,48 +512,11 @@ class B200UNet2DConditionModel:
         return sum(t.numel() * t.element_size() for t in self._w.values())
 
     # -- packed weight arena: one contiguous device buffer, so N ranks need ONE ncclBroadcast ----------------------
-    def consolidate(self):
-        """Move every packed tensor into one contiguous arena (256-byte aligned slots); returns the arena."""
-        layout, off = [], 0
-        for k, t in self._w.items():
-            nbytes = t.numel() * t.element_size()
-            layout.append((k, tuple(t.shape), t.dtype, off, nbytes))
-            off = (off + nbytes + 255) // 256 * 256
-        arena = torch.empty(off, dtype=torch.uint8, device=self._device)
-        self._adopt(arena, layout, copy_from=self._w)
-        return arena
-
-    def _adopt(self, arena, layout, copy_from=None):
-        new = {}
-        for k, shape, dtype, off, nbytes in layout:
-            view = arena[off:off + nbytes].view(dtype).view(shape)
-            if copy_from is not None:
-                view.copy_(copy_from[k])
-            new[k] = view
-        self._w = new
-        self._arena, self._arena_layout = arena, layout
-        self._loaded = True
+    # consolidate() / broadcast_weights(): WeightArenaMixin (arena.py) — replaces the reference's per-rank `torch.load` of
+    # the full checkpoint (stage2_batchtest_inpaint_model.py:103-104) by one NCCL broadcast of the packed arena.
+    def _after_adopt(self):
         self._ctx_cache = None
         self._pose_cache = None
-
-    def broadcast_weights(self, src: int = 0, group=None):
-        """Replaces the reference's per-rank `torch.load` of the full checkpoint (stage2_batchtest_inpaint_model.py:
-        103-104): rank `src` holds packed weights, every other rank receives the layout (object broadcast) and then
-        the arena itself with ONE NCCL broadcast over NVLink.  No collective is used after this."""
-        import torch.distributed as dist
-        rank = dist.get_rank(group)
-        if rank == src:
-            if getattr(self, "_arena", None) is None:
-                self.consolidate()
-            meta = [self._arena_layout, self._arena.numel()]
-        else:
-            meta = [None, None]
-        dist.broadcast_object_list(meta, src=src, group=group)
-        if rank != src:
-            arena = torch.empty(meta[1], dtype=torch.uint8, device=self._device)
-            self._adopt(arena, meta[0])
-        dist.broadcast(self._arena, src=src, group=group)
-        return self._arena.numel()
 
     # ------------------------------------------------------------------------------------------------------------
     # forward

@@ -20,6 +20,7 @@ from typing import Dict
 import torch
 
 from . import ops
+from .arena import WeightArenaMixin
 from .unet import _Config
 
 _DEFAULT_CONFIG = dict(
@@ -52,7 +53,7 @@ class B200DiagonalGaussianDistribution:
         return self.mode()
 
 
-class B200AutoencoderKL:
+class B200AutoencoderKL(WeightArenaMixin):
     def __init__(self, dtype: torch.dtype = torch.float16, device="cuda", **config):
         cfg = dict(_DEFAULT_CONFIG)
         unknown = set(config) - set(cfg)
@@ -290,6 +291,7 @@ class B200AutoencoderKL:
         w["post_quant_conv.weight"], w["post_quant_conv.bias"] = lin("post_quant_conv.weight", n_pad=64, k_pad=64), f32("post_quant_conv.bias", pad=64)
         w["decoder.conv_in.weight"], w["decoder.conv_in.bias"] = conv("decoder.conv_in.weight", pad_in=64), f32("decoder.conv_in.bias")
         w["decoder.conv_out.weight"], w["decoder.conv_out.bias"] = conv("decoder.conv_out.weight", pad_out=32), f32("decoder.conv_out.bias", pad=32)
+        self._arena = None
         self._loaded = True
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
