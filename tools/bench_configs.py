@@ -2,6 +2,7 @@
 classes with synthetic weights: resident-input images/s and ms per CFG UNet step.
 
   cfg2  stage-2, 8 images, 256x256 (32x64 latents), 258 tokens, 50 DDIM        (the bench.py workload, for reference)
+  cfg2_95tokens  the same with BASELINE's "77+18" = 95 conditioning tokens      (secondary figure)
   cfg3  stage-2, 4 images, 512x512 (64x128 latents), 258 tokens, 50 DDIM
   cfg5  stage-3 refiner, 8 images, 512x512 (64x64 latents), 257 tokens, 30 DDIM
   drv   the batch-test driver's defaults (stage2_batchtest_inpaint_model.py:199-211,256-262): 4 images, 512x512,
@@ -43,13 +44,13 @@ def g(seed):
     return torch.Generator().manual_seed(seed)
 
 
-def stage2(n, h, w, steps, dt, sched, vae=None):
+def stage2(n, h, w, steps, dt, sched, vae=None, tokens=257):
     unet = B200UNet2DConditionModel(dtype=dt, device=dev, in_channels=9, class_embed_type="projection",
                                     projection_class_embeddings_input_dim=1024)
     unet.load_state_dict(unet.synthetic_state_dict(seed=0))
     pipe = B200Stage2InpaintPipeline(vae=vae, unet=unet, scheduler=sched)
     kw = dict(height=h * 8, width=w * 8, num_inference_steps=steps, guidance_scale=2.0, num_images_per_prompt=n,
-              latents=torch.randn(n, 4, h, w, generator=g(1)), s_img_proj_f=torch.randn(1, 257, 1024, generator=g(2)),
+              latents=torch.randn(n, 4, h, w, generator=g(1)), s_img_proj_f=torch.randn(1, tokens, 1024, generator=g(2)),
               st_pose_f=0.1 * torch.randn(1, 320, h, w, generator=g(3)),
               pred_t_img_embed=torch.randn(1, 1, 1024, generator=g(4)))
     if vae is None:
@@ -93,6 +94,13 @@ def record(name, n, h, w, steps, call_ms, loop_ms, note):
 
 c, l = stage2(8, 32, 64, 50, torch.bfloat16, B200DDIMScheduler())
 record("cfg2", 8, 32, 64, 50, c, l, "stage-2 b8 256x256 DDIM-50 bf16 (bench.py workload)")
+torch.cuda.empty_cache()
+# BASELINE's "77+18-token" synthetic conditioning (S_kv = 95, the secondary figure next to the
+# reference-faithful 258): 94 image tokens + the appended predicted-embedding token
+c, l = stage2(8, 32, 64, 50, torch.bfloat16, B200DDIMScheduler(), tokens=94)
+TFLOP_ROW[(32, 64)] = 5.998 / 16
+record("cfg2_95tokens", 8, 32, 64, 50, c, l, "stage-2 b8 256x256 DDIM-50 bf16 with 95 conditioning tokens (5.998 TFLOP / fwd)")
+TFLOP_ROW[(32, 64)] = 0.387
 torch.cuda.empty_cache()
 c, l = stage2(4, 64, 128, 50, torch.bfloat16, B200DDIMScheduler())
 record("cfg3", 4, 64, 128, 50, c, l, "stage-2 b4 512x512 DDIM-50 bf16")
