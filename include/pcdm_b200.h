@@ -37,9 +37,11 @@ extern "C" {
 #define PCDM_FLAG_SILU 4    /* gemm/conv epilogue and norm kernels: apply SiLU last */
 #define PCDM_FLAG_GELU 8    /* gemm/conv epilogue: apply GELU (erf form) last */
 #define PCDM_FLAG_PAD_BR 16 /* conv3x3 stride 2: zero padding on the bottom/right only (F.pad(x,(0,1,0,1)) + conv pad 0) */
-#define PCDM_FLAG_W_STATIC 32 /* gemm: W holds model weights, i.e. it is NOT written by the kernel launched just before on the
-                               * same stream — lets the M <= 32 weight-streaming kernel request W before its programmatic-
-                               * dependency wait.  Leave it clear when W is an activation (QK^T / PV written as GEMMs). */
+#define PCDM_FLAG_W_STATIC 32 /* gemm: W holds model weights, i.e. it is NOT written by any kernel of the current chain of
+                               * programmatically-dependent launches on this stream (with dependent launch, a kernel's
+                               * prologue may run while its predecessor AND that one's predecessor are still executing) —
+                               * lets the M <= 32 weight-streaming kernel request W before its dependency wait.  Leave
+                               * it clear when W is an activation (QK^T / PV written as GEMMs). */
 
 int pcdm_abi_version(void);
 /* 1 (default): every kernel is launched with programmatic dependent launch, so its prologue overlaps the tail of its
