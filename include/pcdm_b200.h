@@ -14,6 +14,10 @@
  *   - every function returns 0 on success or a negative PCDM_ERR_* code; pcdm_last_error() returns a thread-local
  *     message.  Nothing allocates, nothing synchronises; the caller owns all buffers.  There is no CPU fallback:
  *     without a CUDA device every compute entry point fails with PCDM_ERR_CUDA.
+ *   - the library holds NO mutable process-wide state: scratch memory comes in per call (pcdm_ext, workspace
+ *     arguments), so calls on different streams / devices / host threads are independent as long as they are given
+ *     different scratch buffers.  (Tuning / experiment setters exist only in the separate experiment build,
+ *     include/pcdm_b200_experiment.h.)
  */
 #ifndef PCDM_B200_H_
 #define PCDM_B200_H_
@@ -22,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCDM_ABI_VERSION 1
+#define PCDM_ABI_VERSION 2
 
 #define PCDM_ERR_INVALID (-1)     /* bad argument */
 #define PCDM_ERR_CUDA (-2)        /* CUDA runtime / driver failure */
@@ -43,11 +47,28 @@ extern "C" {
                                * lets the M <= 32 weight-streaming kernel request W before its dependency wait.  Leave
                                * it clear when W is an activation (QK^T / PV written as GEMMs). */
 
+#define PCDM_FLAG_NO_SKINNY 64   /* gemm: keep M <= 32 problems on the tcgen05 tile kernel (tests: A/B of the two paths) */
+#define PCDM_FLAG_GN_TWO_PASS 64 /* groupnorm: force the statistics + apply kernels (tests) */
+#define PCDM_FLAG_GN_ONE_PASS 128 /* groupnorm: force the single register-resident pass whenever the shape allows (tests) */
+
+/* Optional per-call extras of pcdm_gemm / pcdm_conv3x3 / pcdm_ln_gemm (NULL = none).  Plain pointers and sizes; set
+ * `size = sizeof(pcdm_ext)` (a library built against a longer struct rejects a shorter one). */
+typedef struct pcdm_ext {
+  int size;
+  int force_cta_group;       /* 0 = automatic; 1 = single-CTA 128-row tiles; 2 = CTA pairs (tcgen05 cta_group::2, 256-row
+                              * tiles) wherever the N tile allows */
+  void* workspace;           /* caller-owned scratch for split-K (tile-starved shapes: few output tiles, long K — the
+                              * 4x8 / 8x16 UNet levels): fp32 partial sums.  NULL disables split-K.  One buffer per
+                              * concurrently-used stream; it must outlive every launch (and every captured CUDA graph)
+                              * that was given it.  pcdm_gemm_workspace_bytes() bounds what a problem can use; 64 MiB
+                              * covers every BASELINE configuration.  16-byte aligned. */
+  long long workspace_bytes;
+} pcdm_ext;
+
 int pcdm_abi_version(void);
-/* 1 (default): every kernel is launched with programmatic dependent launch, so its prologue overlaps the tail of its
- * stream predecessor (each kernel waits for that predecessor before its first global-memory access).  0: plain. */
-int pcdm_set_pdl(int enabled);
 const char* pcdm_last_error(void);
+/* Upper bound of the split-K scratch pcdm_gemm / pcdm_conv3x3 can use for an [M, N] output (conv: M = B*H*W, N = Cout). */
+long long pcdm_gemm_workspace_bytes(int M, int N);
 
 /* torch.nn.Linear (+ fused epilogues).  Replaces the nn.Linear calls inside diffusers Transformer2DModel /
  * BasicTransformerBlock / Attention / GEGLU / TimestepEmbedding and the 1x1 conv_shortcut of ResnetBlock2D
@@ -59,7 +80,8 @@ const char* pcdm_last_error(void);
  * K % 64 == 0, N % 32 == 0.  bn = 0 picks the N tile automatically (64/128/160/256 to force one). */
 int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w, void* out,
               long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
-              const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn, void* stream);
+              const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
+              const pcdm_ext* ext, void* stream);
 
 /* torch.nn.LayerNorm(K, eps) followed by torch.nn.Linear, as one call:
  *   out = act( LN(x[M, K]; gamma, beta, eps) . W[N, K]^T + bias + rowvec + residual )
@@ -71,22 +93,7 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
 int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
                  const void* w, void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
                  int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags,
-                 void* stream);
-
-/* Tuning / test hook for the two calls above: 0 = automatic, 1 = single-CTA 128-row tiles only, 2 = CTA pairs
- * (tcgen05 cta_group::2, 256-row tiles) wherever the N tile allows.  Process-wide; not part of the reference surface. */
-int pcdm_set_gemm_cta_group(int mode);
-int pcdm_set_gemm_max_stages(int n); /* experiment hook: cap the smem ring depth (2..8, default 8 = as deep as fits) */
-int pcdm_set_skinny_gemm(int enabled); /* 1 (default): pcdm_gemm with M <= 32 rows (no GEGLU, one K segment, bn = 0) runs
-                                        * the weight-streaming skinny kernel (skinny.cu); 0: always the tcgen05 tiles */
-int pcdm_set_gemm_debug(int mask);   /* experiment hook: switch parts of the kernel off for timing (results WRONG while
-                                      * non-zero): 1 no TMA stores, 2 no residual, 4 no bias/rowvec, 8 no epilogue body,
-                                      * 16 no MMAs */
-
-/* Caller-owned fp32 scratch for pcdm_gemm / pcdm_conv3x3 split-K (used for tile-starved shapes: few output tiles, long
- * K — the 4x8 and 8x16 UNet levels): process-wide, single-stream use; must outlive every launch (and every captured
- * CUDA graph) that may use it.  NULL / 0 disables split-K.  64 MiB covers every BASELINE configuration. */
-int pcdm_set_workspace(void* ptr, long long bytes);
+                 const pcdm_ext* ext, void* stream);
 
 /* torch.nn.Conv2d(Cin, Cout, 3, stride, padding=1) on NHWC activations, implicit GEMM (no im2col buffer).
  * Replaces conv_in, conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2), Upsample2D.conv and conv_out
@@ -98,7 +105,7 @@ int pcdm_set_workspace(void* ptr, long long bytes);
  *   of the VAE encoder's Downsample2D (diffusers: F.pad(x, (0, 1, 0, 1)) then Conv2d(stride 2, padding 0)). */
 int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                  long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride,
-                 int dtype, int flags, int bn, void* stream);
+                 int dtype, int flags, int bn, const pcdm_ext* ext, void* stream);
 
 /* torch.nn.GroupNorm(groups, C, eps) (+ SiLU with PCDM_FLAG_SILU) over NHWC x = [x1 | x2] (x2 may be NULL; x1 then has
  * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out
@@ -106,11 +113,9 @@ int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bi
  * zero-initialised once by the caller (it holds device counters the kernels return to zero); results are
  * bit-reproducible run to run (fixed reduction order, no floating-point atomics).  Small activations (<= 16 MB, >= 8
  * channels per group) run as ONE register-resident pass (one read, one write; pieces of an image share statistics
- * through a thread-block cluster); larger ones take a streaming statistics kernel + an apply kernel.
- * pcdm_set_groupnorm_two_pass(mode) is the tests / A-B timing hook: 0 automatic, 1 always two kernels, 2 single pass
- * whenever the shape allows, 2 + T single pass with T threads per CTA. */
+ * through a thread-block cluster); larger ones take a streaming statistics kernel + an apply kernel
+ * (PCDM_FLAG_GN_TWO_PASS / PCDM_FLAG_GN_ONE_PASS force either path).  One workspace per concurrently-used stream. */
 long long pcdm_groupnorm_workspace_bytes(int B, int groups);
-int pcdm_set_groupnorm_two_pass(int mode);
 int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta, float eps,
                    int B, int HW, int C, int groups, int dtype, int flags, void* workspace, void* stream);
 
@@ -122,8 +127,6 @@ int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const f
  * F.scaled_dot_product_attention behind diffusers' attention processors (stage2_batchtest_inpaint_model.py:133;
  * SURVEY.md §8a a9).  q: element (b, s, h, d) at q[(b*Sq + s)*ldq + h*64 + d]; k, v likewise with Skv; out likewise
  * with ldo — so q/k/v may be column slices of one fused projection buffer. */
-int pcdm_set_attention_small(int on); /* 1 (default): Sq, Skv <= 32 at head_dim 64 run the one-warp-per-head kernel; 0: tcgen05 */
-int pcdm_set_attention_poly(int on); /* experiment hook: 1 = half of the softmax exp2 on the FMA pipe (default 0: measured slower) */
 int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype, void* stream);
 /* The same with an explicit head width: head_dim = 64 or 128; head h of a token row lives at columns

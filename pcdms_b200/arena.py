@@ -18,6 +18,8 @@ import torch
 class WeightArenaMixin:
     _arena = None
     _arena_layout = None
+    _weights_version = 0   # bumped whenever the packed tensors move or change (load_state_dict, consolidate, broadcast):
+                           # captured CUDA graphs hold raw weight pointers, so the pipelines re-capture on a change
 
     def _after_adopt(self):
         """Hook: invalidate caches derived from the weights."""
@@ -43,6 +45,7 @@ class WeightArenaMixin:
         self._w = new
         self._arena, self._arena_layout = arena, layout
         self._loaded = True
+        self._weights_version += 1
         self._after_adopt()
 
     def broadcast_weights(self, src: int = 0, group=None):

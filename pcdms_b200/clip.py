@@ -195,6 +195,7 @@ class B200CLIPVisionModelWithProjection(WeightArenaMixin):
             w[f"{i}.fc1.weight"], w[f"{i}.fc1.bias"] = mat(f(f"{p}.mlp.fc1.weight")), vec(f(f"{p}.mlp.fc1.bias"))
             w[f"{i}.fc2.weight"], w[f"{i}.fc2.bias"] = mat(f(f"{p}.mlp.fc2.weight")), vec(f(f"{p}.mlp.fc2.bias"))
         self._loaded = True
+        self._weights_version += 1
         from types import SimpleNamespace
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 

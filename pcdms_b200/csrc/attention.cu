@@ -410,16 +410,6 @@ static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int S, i
   return make_tmap(m, base, 4, dims, strides, box);
 }
 
-static int g_att_small = 1;  // 0: short sequences also take the tcgen05 kernel (A/B hook)
-extern "C" int pcdm_set_attention_small(int on) {
-  g_att_small = on ? 1 : 0;
-  return 0;
-}
-static int g_att_poly = 0;   // 1: half of the exp2 on the FMA pipe (experiment hook; measured slower, see the kernel)
-extern "C" int pcdm_set_attention_poly(int on) {
-  g_att_poly = on ? 1 : 0;
-  return 0;
-}
 
 extern "C" int pcdm_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                               void* out, long long ldo, int B, int heads, int Sq, int Skv, float scale, int dtype,
@@ -437,7 +427,7 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "attention: bad dtype");
   if (B <= 0 || heads <= 0 || Sq <= 0 || Skv <= 0) return set_error(PCDM_ERR_INVALID, "attention: empty problem");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error(PCDM_ERR_UNSUPPORTED, "attention: strides must be multiples of 8");
-  if (g_att_small && head_dim == 64 && Sq <= 32 && Skv <= 32) {   // short sequences: CUDA-core kernel, one warp per (batch, head)
+  if (g_tune.att_small && head_dim == 64 && Sq <= 32 && Skv <= 32) {   // short sequences: CUDA-core kernel, one warp per (batch, head)
     const int grid_s = (B * heads + 3) / 4;
     const float sl2 = scale * 1.4426950408889634f;
     if (dtype == DT_F16)
@@ -463,12 +453,7 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   const int grid = B * heads * p.q_tiles;
 #define ATT_LAUNCH(DT_, P_, HD_)                                                                                    \
   do {                                                                                                              \
-    static bool configured = false;                                                                                 \
-    if (!configured) {                                                                                              \
-      PCDM_CUDA(cudaFuncSetAttribute(attention_kernel<DT_, P_, HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     att_smem_bytes(HD_)));                                                         \
-      configured = true;                                                                                            \
-    }                                                                                                               \
+    PCDM_ENSURE_SMEM(att_smem_bytes(HD_), attention_kernel<DT_, P_, HD_>);                                          \
     PCDM_CUDA(launch_kernel(attention_kernel<DT_, P_, HD_>, dim3(grid), dim3(ATT_THREADS), att_smem_bytes(HD_),     \
                             stream, 1, p));                                                                         \
   } while (0)
@@ -476,10 +461,10 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
     if (dtype == DT_F16) ATT_LAUNCH(DT_F16, 0, 128);
     else ATT_LAUNCH(DT_BF16, 0, 128);
   } else if (dtype == DT_F16) {
-    if (g_att_poly) ATT_LAUNCH(DT_F16, 2, 64);
+    if (g_tune.att_poly) ATT_LAUNCH(DT_F16, 2, 64);
     else ATT_LAUNCH(DT_F16, 0, 64);
   } else {
-    if (g_att_poly) ATT_LAUNCH(DT_BF16, 2, 64);
+    if (g_tune.att_poly) ATT_LAUNCH(DT_BF16, 2, 64);
     else ATT_LAUNCH(DT_BF16, 0, 64);
   }
 #undef ATT_LAUNCH

@@ -1,10 +1,13 @@
 #include "host_util.h"
+#include "../../include/pcdm_b200_experiment.h"
 #include <stdarg.h>
 
 namespace pcdm {
 
 static thread_local char g_err[512] = "";
-int g_pdl_enabled = 1;
+#ifdef PCDM_EXPERIMENT
+Tuning g_tune;
+#endif
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -14,16 +17,16 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-    n = prop.multiProcessorCount;
+int num_sms() {   // of the CURRENT device (cached per device)
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -79,7 +82,22 @@ extern "C" const char* pcdm_last_error(void) { return pcdm::g_err; }
 
 extern "C" int pcdm_abi_version(void) { return PCDM_ABI_VERSION; }
 
-extern "C" int pcdm_set_pdl(int enabled) {
-  pcdm::g_pdl_enabled = enabled ? 1 : 0;
+#ifdef PCDM_EXPERIMENT
+// ---- experiment hooks (include/pcdm_b200_experiment.h): present in libpcdm_b200_exp.so only ----
+extern "C" int pcdm_set_pdl(int enabled) { pcdm::g_tune.pdl = enabled ? 1 : 0; return 0; }
+extern "C" int pcdm_set_gemm_cta_group(int mode) {
+  if (mode < 0 || mode > 2) return pcdm::set_error(PCDM_ERR_INVALID, "gemm cta group mode must be 0, 1 or 2");
+  pcdm::g_tune.force_cg = mode;
   return 0;
 }
+extern "C" int pcdm_set_gemm_max_stages(int n) {
+  if (n < 2 || n > 8) return pcdm::set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
+  pcdm::g_tune.max_stages = n;
+  return 0;
+}
+extern "C" int pcdm_set_gemm_debug(int mask) { pcdm::g_tune.gemm_dbg = mask; return 0; }
+extern "C" int pcdm_set_skinny_gemm(int enabled) { pcdm::g_tune.skinny = enabled ? 1 : 0; return 0; }
+extern "C" int pcdm_set_attention_small(int on) { pcdm::g_tune.att_small = on ? 1 : 0; return 0; }
+extern "C" int pcdm_set_attention_poly(int on) { pcdm::g_tune.att_poly = on ? 1 : 0; return 0; }
+extern "C" int pcdm_set_groupnorm_two_pass(int mode) { pcdm::g_tune.gn_mode = mode; return 0; }
+#endif

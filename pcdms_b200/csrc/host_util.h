@@ -16,7 +16,26 @@ int num_sms();
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int swizzle_bytes = 128);
 
-extern int g_pdl_enabled;   // pcdm_set_pdl(): 1 = launch with programmatic stream serialization (default), 0 = plain
+// Every tuning knob of the library in one place.  The RELEASE library (libpcdm_b200.so) holds them as compile-time
+// constants: it has no mutable process-wide state, and every entry point is safe to call concurrently from several
+// host threads / on several streams / on several devices (per-call scratch comes in through pcdm_ext).  Built with
+// -DPCDM_EXPERIMENT (libpcdm_b200_exp.so, used by tools/ only) the knobs become a mutable struct behind the
+// pcdm_set_* hooks declared in include/pcdm_b200_experiment.h.
+struct Tuning {
+  int pdl = 1;             // launch with programmatic stream serialization
+  int force_cg = 0;        // 0 auto, 1 single-CTA tiles, 2 CTA pairs wherever the N tile allows
+  int max_stages = 8;      // cap on the GEMM/conv shared-memory ring depth
+  int gemm_dbg = 0;        // experiment mask (results WRONG when non-zero)
+  int skinny = 1;          // M <= 32 GEMMs on the weight-streaming kernel
+  int att_small = 1;       // Sq, Skv <= 32 attention on the one-warp-per-head kernel
+  int att_poly = 0;        // half of the softmax exp2 on the FMA pipe
+  int gn_mode = 0;         // 0 auto, 1 two kernels, 2 single pass, 2 + T single pass with T threads per CTA
+};
+#ifdef PCDM_EXPERIMENT
+extern Tuning g_tune;
+#else
+constexpr Tuning g_tune{};
+#endif
 
 // Launch `kernel` with the PDL attribute (and an optional 1-D cluster size).
 template <typename... KArgs, typename... Args>
@@ -30,7 +49,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   int n = 0;
-  if (g_pdl_enabled) {
+  if (g_tune.pdl) {
     attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -53,6 +72,18 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     if (_e != cudaSuccess)                                                                   \
       return ::pcdm::set_error(PCDM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
                                __LINE__);                                                    \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember which devices a kernel was configured on
+#define PCDM_ENSURE_SMEM(bytes, ...)                                                                             \
+  do {                                                                                                           \
+    static bool _cfg[64] = {};                                                                                   \
+    int _dev = 0;                                                                                                \
+    PCDM_CUDA(cudaGetDevice(&_dev));                                                                             \
+    if (_dev < 0 || _dev >= 64 || !_cfg[_dev]) {                                                                 \
+      PCDM_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));        \
+      if (_dev >= 0 && _dev < 64) _cfg[_dev] = true;                                                             \
+    }                                                                                                            \
   } while (0)
 
 #define PCDM_CHECK(expr, what)                  \

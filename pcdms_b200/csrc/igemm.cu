@@ -20,6 +20,12 @@
 
 namespace pcdm {
 
+#ifdef PCDM_EXPERIMENT
+#define IG_DBG(p, bit) ((p).dbg & (bit))   // experiment build: parts of the kernel can be switched off for timing
+#else
+#define IG_DBG(p, bit) 0
+#endif
+
 constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
 constexpr int IG_EPI_WARPS = 8;
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           const uint32_t a_lo = desc_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
           const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < 4 && !(p.dbg & 16); ++k) {
+          for (int k = 0; k < 4 && !IG_DBG(p, 16); ++k) {
             const uint64_t da = ((uint64_t)kDescHi << 32) | (a_lo + 2u * k);   // +32 B per k16 inside the swizzle atom
             const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + 2u * k);
             if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         //      ALL residual chunks this warp owns in the tile are TMA-prefetched (one slot each) before the wait for the
         //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
         //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
-        const bool use_res = p.has_res && !(p.dbg & 2);
+        const bool use_res = p.has_res && !IG_DBG(p, 2);
         if (use_res) {
           if (lane == 0) {
             bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         tc_fence_after();
         int ci = 0;
 #pragma unroll 1
-        for (int c = half; c * 32 < cols_here && !(p.dbg & 8); c += 2, ++ci) {
+        for (int c = half; c * 32 < cols_here && !IG_DBG(p, 8); c += 2, ++ci) {
           const int n0 = n_tile0 + c * 32;
           const uint32_t slot = use_res ? (uint32_t)ci : (cnt & (uint32_t)(nbuf - 1));   // nbuf is 2 or 4
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           float2 v[16];   // column pairs, packed fp32 (FFMA2 path)
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          if (p.bias && !(p.dbg & 4)) {
+          if (p.bias && !IG_DBG(p, 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
           }
-          if (rv && !(p.dbg & 4)) {
+          if (rv && !IG_DBG(p, 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
+          if (lane == 0 && !IG_DBG(p, 1)) {
             tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
             bulk_commit();
           }
@@ -565,23 +571,17 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
 // host side
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_SMEM_LIMIT = 227 * 1024;
-static int g_max_stages = IG_MAX_STAGES;
-static int g_gemm_dbg = 0;                // experiment mask (pcdm_set_gemm_debug)  // tuning hook: cap on the smem ring depth (pcdm_set_gemm_max_stages)
 
 template <int BN, int DT, int CG>
 static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, CG>;
-  static bool configured = false;
-  if (!configured) {
-    PCDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
-    configured = true;
-  }
+  PCDM_ENSURE_SMEM(IG_SMEM_LIMIT, igemm_kernel<BN, DT, CG>);
   p.nbuf = p.has_res ? IG_RES_SLOTS : 2;
-  p.dbg = g_gemm_dbg;
+  p.dbg = g_tune.gemm_dbg;
   const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
   if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
-  if (stages > g_max_stages) stages = g_max_stages;
+  if (stages > g_tune.max_stages) stages = g_tune.max_stages;
   if (stages < 2) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: not enough shared memory for a 2-stage ring");
   p.stages = stages;
   const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
@@ -632,9 +632,25 @@ static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int forc
   }
 }
 
-static int g_force_cg = 0;  // 0 = auto, 1 / 2 = force (tests and tuning)
-static void* g_ws = nullptr;   // caller-owned fp32 scratch for split-K partials (pcdm_set_workspace)
-static long long g_ws_bytes = 0;
+struct ExtArgs {   // what the caller's pcdm_ext carries (all optional)
+  int force_cg = 0;          // 0 = auto, 1 / 2 = force
+  void* ws = nullptr;        // fp32 scratch for split-K partials; without it the launch never splits K
+  long long ws_bytes = 0;
+};
+
+static int read_ext(const pcdm_ext* ext, ExtArgs* e) {
+  e->force_cg = g_tune.force_cg;
+  if (!ext) return 0;
+  if (ext->size < (int)sizeof(pcdm_ext)) return set_error(PCDM_ERR_INVALID, "pcdm_ext: size field does not match this library's struct");
+  if (ext->force_cta_group < 0 || ext->force_cta_group > 2) return set_error(PCDM_ERR_INVALID, "pcdm_ext: force_cta_group must be 0, 1 or 2");
+  if (ext->workspace_bytes < 0 || (!ext->workspace && ext->workspace_bytes != 0))
+    return set_error(PCDM_ERR_INVALID, "pcdm_ext: bad workspace arguments");
+  if (reinterpret_cast<uintptr_t>(ext->workspace) & 15) return set_error(PCDM_ERR_INVALID, "pcdm_ext: workspace must be 16-byte aligned");
+  if (ext->force_cta_group) e->force_cg = ext->force_cta_group;
+  e->ws = ext->workspace;
+  e->ws_bytes = ext->workspace_bytes;
+  return 0;
+}
 
 struct EpiArgs {   // the fused-epilogue operands as the caller gave them
   const float* bias;
@@ -649,7 +665,10 @@ struct EpiArgs {   // the fused-epilogue operands as the caller gave them
 };
 
 static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, const void* residual, long long ldr,
-                          cudaStream_t stream) {
+                          const ExtArgs& ext, cudaStream_t stream) {
+  void* const g_ws = ext.ws;
+  const long long g_ws_bytes = ext.ws_bytes;
+  const int g_force_cg = ext.force_cg;
   p.splits = 1;
   p.kb_per_split = p.num_kb;
   // ---- split-K for tile-starved problems (the 4x8 / 8x16 levels: M = 64..2048 rows but K up to 23 040): slice K over
@@ -753,8 +772,10 @@ using namespace pcdm;
 extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w,
                          void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
                          int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
-                         void* stream_) {
+                         const pcdm_ext* ext_, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  ExtArgs ext;
+  PCDM_CHECK(read_ext(ext_, &ext), "ext");
   if (!a || !w || !out) return set_error(PCDM_ERR_INVALID, "gemm: null pointer");
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "gemm: dtype must be 0 (f16) or 1 (bf16)");
   if (M <= 0 || N <= 0 || K <= 0) return set_error(PCDM_ERR_INVALID, "gemm: empty problem");
@@ -763,7 +784,7 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
   const bool geglu = flags & PCDM_FLAG_GEGLU;
   if (geglu && (N % 64)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU needs N % 64 == 0");
   if ((lda % 8) || (ldo % 8) || (residual && (ldr % 8))) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: strides must be multiples of 8");
-  if (!a2 && bn == 0) {   // M <= 32 activation rows: a weight stream, not a 128-row tile problem (skinny.cu)
+  if (!a2 && bn == 0 && !(flags & PCDM_FLAG_NO_SKINNY)) {   // M <= 32 activation rows: a weight stream, not a 128-row tile problem (skinny.cu)
     const int taken = skinny_gemm_try(a, lda, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N,
                                       K, dtype, flags, stream, nullptr, nullptr, 0.f);
     if (taken != 0) return taken < 0 ? taken : 0;
@@ -794,13 +815,15 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
   p.geglu = geglu; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: rowvec stride must be a multiple of 4");
   if (p.geglu && p.out_f32) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU with fp32 output");
-  return dispatch_igemm(p, dtype, bn, w, K, residual, ldr, stream);
+  return dispatch_igemm(p, dtype, bn, w, K, residual, ldr, ext, stream);
 }
 
 extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                             long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype,
-                            int flags, int bn, void* stream_) {
+                            int flags, int bn, const pcdm_ext* ext_, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  ExtArgs ext;
+  PCDM_CHECK(read_ext(ext_, &ext), "ext");
   if (!x || !w_packed || !out) return set_error(PCDM_ERR_INVALID, "conv3x3: null pointer");
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "conv3x3: dtype must be 0 (f16) or 1 (bf16)");
   if (stride != 1 && stride != 2) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: stride must be 1 or 2");
@@ -850,37 +873,12 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
   p.out = out; p.ldo = Cout;
   p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: rowvec stride must be a multiple of 4");
-  return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, residual, Cout, stream);
+  return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, residual, Cout, ext, stream);
 }
 
-/* tuning / test hook: 0 = choose automatically, 1 = single-CTA tiles only, 2 = CTA pairs wherever BN >= 128 */
-extern "C" int pcdm_set_gemm_cta_group(int mode) {
-  if (mode < 0 || mode > 2) return set_error(PCDM_ERR_INVALID, "gemm cta group mode must be 0, 1 or 2");
-  g_force_cg = mode;
-  return 0;
-}
-
-/* caller-owned fp32 scratch for split-K partial sums (process-wide, single-stream use); NULL / 0 disables split-K */
-extern "C" int pcdm_set_workspace(void* ptr, long long bytes) {
-  if (bytes < 0 || (ptr == nullptr && bytes != 0)) return set_error(PCDM_ERR_INVALID, "set_workspace: bad arguments");
-  if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(PCDM_ERR_INVALID, "set_workspace: pointer must be 16-byte aligned");
-  g_ws = ptr;
-  g_ws_bytes = bytes;
-  return 0;
-}
-
-/* tuning / experiment hook: cap the shared-memory ring depth of the GEMM/conv mainloop (2..8) */
-extern "C" int pcdm_set_gemm_max_stages(int n) {
-  if (n < 2 || n > IG_MAX_STAGES) return set_error(PCDM_ERR_INVALID, "gemm max stages must be in [2, 8]");
-  g_max_stages = n;
-  return 0;
-}
-
-/* experiment hook (tools/dev_epilogue.py): switch parts of the GEMM/conv kernel off to see what paces it.  Results are
- * wrong while the mask is non-zero.  1 no TMA stores, 2 no residual, 4 no bias / rowvec, 8 no epilogue body, 16 no MMAs */
-extern "C" int pcdm_set_gemm_debug(int mask) {
-  g_gemm_dbg = mask;
-  return 0;
+extern "C" long long pcdm_gemm_workspace_bytes(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return 8LL * M * N * 4;   // at most 8 K-slices of fp32 partials
 }
 
 /* LayerNorm over K fused in front of a GEMM: out = act( LN(x; gamma, beta, eps) . W^T + bias + rowvec + residual ).
@@ -890,7 +888,7 @@ extern "C" int pcdm_set_gemm_debug(int mask) {
 extern "C" int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
                             const void* w, void* out, long long ldo, const float* bias, const float* rowvec,
                             long long ld_rowvec, int rows_per_image, const void* residual, long long ldr, int M, int N,
-                            int K, int dtype, int flags, void* stream_) {
+                            int K, int dtype, int flags, const pcdm_ext* ext_, void* stream_) {
   if (!x || !gamma || !beta || !w || !out) return set_error(PCDM_ERR_INVALID, "ln_gemm: null pointer");
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "ln_gemm: dtype must be 0 (f16) or 1 (bf16)");
   if (M <= 0 || N <= 0 || K <= 0) return set_error(PCDM_ERR_INVALID, "ln_gemm: empty problem");
@@ -903,5 +901,5 @@ extern "C" int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, co
   const int rc = pcdm_layernorm(x, ldx, scratch, K, gamma, beta, eps, M, K, dtype, stream_);
   if (rc != 0) return rc;
   return pcdm_gemm(scratch, K, nullptr, 0, 0, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N,
-                   K, dtype, flags, 0, stream_);
+                   K, dtype, flags, 0, ext_, stream_);
 }

@@ -473,7 +473,6 @@ struct GnFusedCfg { int gset, nv, PY, S, pix_per_cta, K; };
 // Measured (tools/dev_norm_perf.py): the single pass wins while the whole activation is a wave or two of CTAs
 // (<= 16 MB: one launch, one read); above that its load / reduce+cluster-sync / store phases run in lockstep across
 // the chip and the two streaming kernels (statistics, then apply) are faster.
-static int g_gn_max_threads = 0;   // pcdm_set_groupnorm_two_pass(2 + T): experiment hook, force T threads per CTA
 static bool gn_fused_config(int B, int HW, int C, int C1, int groups, GnFusedCfg* c) {
   const int cpg = C / groups;
   if (cpg < 8 || (C1 % 8)) return false;
@@ -483,7 +482,7 @@ static bool gn_fused_config(int B, int HW, int C, int C1, int groups, GnFusedCfg
   static const int kThreads[3] = {1024, 512, 256};
   for (int ti = 0; ti < 3; ++ti) {
     const int T = kThreads[ti];
-    if (g_gn_max_threads && T != g_gn_max_threads) continue;
+    if (g_tune.gn_mode > 2 && T != g_tune.gn_mode - 2) continue;   // experiment hook: force T threads per CTA
     for (int gset = 8; gset >= gmin; gset /= 2) {   // wider sets = longer contiguous runs per pixel
       if (gset % gmin || groups % gset) continue;
       const int nv = gset * cpg / 8;
@@ -529,15 +528,7 @@ static cudaError_t launch_gn_fused(const GnFusedCfg& c, cudaStream_t stream, con
 #undef GN_FUSED
 }
 
-static long long g_gn_fused_max_bytes = 16LL << 20;
-static int g_gn_two_pass = 0;   // pcdm_set_groupnorm_two_pass(): force the two-kernel path (tests / A-B timing)
-// 0: automatic; 1: always statistics + apply kernels; 2: single pass whenever the shape allows; 2 + T: single pass
-// with T threads per CTA (256 / 512 / 1024)
-extern "C" int pcdm_set_groupnorm_two_pass(int mode) {
-  g_gn_two_pass = mode;
-  g_gn_max_threads = mode > 2 ? mode - 2 : 0;
-  return 0;
-}
+constexpr long long kGnFusedMaxBytes = 16LL << 20;
 
 // workspace = [final (mean, rstd) float2 x B x groups][counters x B][partials double2 x B x max_chunks x groups];
 // it must be zero-initialised ONCE by the caller (the counters), afterwards the kernels keep it consistent.
@@ -561,7 +552,9 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
   const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   GnFusedCfg fc;
   const long long in_bytes = 2LL * B * HW * C;
-  const bool want_fused = g_gn_two_pass >= 2 || (g_gn_two_pass == 0 && in_bytes <= g_gn_fused_max_bytes);
+  // path choice: per call through PCDM_FLAG_GN_TWO_PASS / PCDM_FLAG_GN_ONE_PASS (tests), else by size
+  const int mode = (flags & PCDM_FLAG_GN_TWO_PASS) ? 1 : ((flags & PCDM_FLAG_GN_ONE_PASS) ? 2 : g_tune.gn_mode);
+  const bool want_fused = mode >= 2 || (mode == 0 && in_bytes <= kGnFusedMaxBytes);
   if (want_fused && gn_fused_config(B, HW, C, C1, groups, &fc)) {
     PCDM_CUDA(dtype == DT_F16
                   ? launch_gn_fused<DT_F16>(fc, stream, x1, x2, C1, C, HW, groups, B, eps, gamma, beta, silu, y)

@@ -247,7 +247,6 @@ skinny_gemm_kernel(const SkinnyParams p) {
   }
 }
 
-static int g_skinny = 1;
 
 constexpr int SK_LN_SMEM_LIMIT = 100 * 1024;   // fused LayerNorm: M * (K + 8) * 2 bytes of normalised rows must fit
 
@@ -265,11 +264,13 @@ static cudaError_t launch_skinny(const SkinnyParams& p, cudaStream_t stream) {
 #define SK_CASE(NT_, PF_)                                                                                            \
   do {                                                                                                               \
     if (LN) {                                                                                                        \
-      static bool configured = false;                                                                                \
-      if (!configured) {                                                                                             \
+      static bool _cfg[64] = {};                                                                                     \
+      int _dev = 0;                                                                                                  \
+      cudaGetDevice(&_dev);                                                                                          \
+      if (_dev < 0 || _dev >= 64 || !_cfg[_dev]) {                                                                   \
         cudaFuncSetAttribute(skinny_gemm_kernel<DT, NT_, LN, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                              SK_LN_SMEM_LIMIT);                                                                      \
-        configured = true;                                                                                           \
+        if (_dev >= 0 && _dev < 64) _cfg[_dev] = true;                                                               \
       }                                                                                                              \
     }                                                                                                                \
     return launch_kernel(skinny_gemm_kernel<DT, NT_, LN, PF_>, grid, block, dyn, stream, 1, p);                      \
@@ -291,7 +292,7 @@ int skinny_gemm_try(const void* a, long long lda, const void* w, void* out, long
                     const float* rowvec, long long ld_rowvec, int rows_per_image, const void* residual, long long ldr,
                     int M, int N, int K, int dtype, int flags, cudaStream_t stream, const float* ln_gamma,
                     const float* ln_beta, float ln_eps) {
-  if (!g_skinny || M > 32 || (flags & PCDM_FLAG_GEGLU) || (N % SK_ROWS) || (K % 64)) return 0;
+  if (!g_tune.skinny || M > 32 || (flags & PCDM_FLAG_GEGLU) || (N % SK_ROWS) || (K % 64)) return 0;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w)) & 15) return 0;   // 16-byte vector loads
   if (ln_gamma && ((size_t)M * (K + 8) * 2 > (size_t)SK_LN_SMEM_LIMIT || K > 2048)) return 0;   // row held in registers
   SkinnyParams p;
@@ -313,7 +314,3 @@ int skinny_gemm_try(const void* a, long long lda, const void* w, void* out, long
 
 }  // namespace pcdm
 
-extern "C" int pcdm_set_skinny_gemm(int enabled) {
-  pcdm::g_skinny = enabled ? 1 : 0;
-  return 0;
-}

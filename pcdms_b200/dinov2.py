@@ -183,6 +183,7 @@ class B200Dinov2Model(WeightArenaMixin):
             w[f"{p}.ffn_out.weight"] = mat(l2[:, None] * wo_p)
             w[f"{p}.ffn_out.bias"] = vec(l2 * f(f"{p}.mlp.weights_out.bias"))
         self._loaded = True
+        self._weights_version += 1
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     def _after_adopt(self):

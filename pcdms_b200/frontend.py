@@ -111,6 +111,7 @@ class B200ImageProjModel_p(_Module):
             self._w[k] = v.detach().to(device=dev, dtype=dt if is_mat else torch.float32).contiguous()
         self._arena = None
         self._loaded = True
+        self._weights_version += 1
 
     @torch.no_grad()
     def forward(self, x):
@@ -163,6 +164,7 @@ class B200ControlNetConditioningEmbedding(_Module):
             self._w[f"{k}.bias"] = b.to(dev)
         self._arena = None
         self._loaded = True
+        self._weights_version += 1
 
     @torch.no_grad()
     def forward(self, conditioning):

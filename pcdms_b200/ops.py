@@ -5,7 +5,9 @@ NHWC: a tensor of logical shape [B, H, W, C] or [rows, C], contiguous in C.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 
 import torch
 
@@ -33,21 +35,54 @@ def _f32(t):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# split-K scratch (process-wide, kept alive here; see pcdm_set_workspace)
+# split-K scratch.  The C ABI takes it per call (pcdm_ext.workspace): the library itself holds no state.  This layer
+# keeps ONE default buffer per device — allocated once, never replaced or shrunk, because captured CUDA graphs freeze
+# its address — and lets a caller that drives several streams concurrently hand each of them its own buffer.
 # ---------------------------------------------------------------------------------------------------------------
-_workspace = None
+WORKSPACE_BYTES = 64 << 20   # covers every BASELINE configuration (see pcdm_gemm_workspace_bytes)
+_default_ws = {}             # device index -> uint8 tensor
+_tls = threading.local()
 
 
-def ensure_workspace(device, nbytes: int = 64 << 20):
-    """Give the library its fp32 split-K scratch on `device` (idempotent)."""
-    global _workspace
+def _dev_index(device) -> int:
     device = torch.device(device)
     if device.type != "cuda":
+        raise RuntimeError("pcdm_b200 ops need a CUDA device (there is no CPU path)")
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+def ensure_workspace(device, nbytes: int = WORKSPACE_BYTES):
+    """The default split-K scratch of `device` (idempotent: 'cuda' and 'cuda:<current>' name the same buffer; an
+    existing buffer is never freed, so graphs captured earlier stay valid)."""
+    if torch.device(device).type != "cuda":
         return None
-    if _workspace is None or _workspace.device != device or _workspace.numel() < nbytes:
-        _workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _l.check(_l.load().pcdm_set_workspace(_l.ptr(_workspace), C.c_longlong(nbytes)), kernels=0)
-    return _workspace
+    idx = _dev_index(device)
+    ws = _default_ws.get(idx)
+    if ws is None:
+        ws = torch.zeros(max(int(nbytes), WORKSPACE_BYTES), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _default_ws[idx] = ws
+    return ws
+
+
+@contextlib.contextmanager
+def use_workspace(ws):
+    """Route the split-K scratch of every op issued by this host thread inside the block to `ws` (a zero-initialised
+    uint8 CUDA tensor): one buffer per stream that runs concurrently with another."""
+    prev = getattr(_tls, "ws", None)
+    _tls.ws = ws
+    try:
+        yield ws
+    finally:
+        _tls.ws = prev
+
+
+def _ext(t: torch.Tensor, force_cta_group: int = 0):
+    if not t.is_cuda:
+        raise RuntimeError("pcdm_b200 ops need CUDA tensors (there is no CPU path)")
+    ws = getattr(_tls, "ws", None)
+    if ws is None or ws.device != t.device:
+        ws = ensure_workspace(t.device)
+    return _l.Ext(C.sizeof(_l.Ext), int(force_cta_group), ws.data_ptr(), ws.numel())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -70,11 +105,12 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # K1/K2
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0, w_static=True):
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True):
     """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual).
     w_static: `w` holds model weights (not written by the kernel launched just before on this stream); pass False when
     `w` is an activation (the VAE's QK^T / PV products written as GEMMs)."""
     lib = _l.load()
+    _dt(a)   # dtype errors first (TypeError), then device errors
     M, k1 = a.shape
     N, K = w.shape
     k2 = 0
@@ -88,12 +124,14 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     flags = ((_l.FLAG_GEGLU if geglu else 0) | (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) |
-             (_l.FLAG_GELU if gelu else 0) | (_l.FLAG_W_STATIC if w_static else 0))
+             (_l.FLAG_GELU if gelu else 0) | (_l.FLAG_W_STATIC if w_static else 0) |
+             (0 if skinny else _l.FLAG_NO_SKINNY))
+    ext = _ext(a, cta_group)
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
         C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), C.c_int(rows_per_image), _l.ptr(residual), C.c_longlong(residual.stride(0) if residual is not None else 0),
-        C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(_dt(a)), C.c_int(flags), C.c_int(bn), _stream(a))
+        C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(_dt(a)), C.c_int(flags), C.c_int(bn), C.byref(ext), _stream(a))
     _l.check(rc)
     return out
 
@@ -112,18 +150,19 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
     scratch = None if M <= 32 and K <= 2048 and M * (K + 8) * 2 <= 100 * 1024 else torch.empty((M, K), device=x.device, dtype=x.dtype)
     flags = ((_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_GELU if gelu else 0) |
              _l.FLAG_W_STATIC)
+    ext = _ext(x)
     rc = lib.pcdm_ln_gemm(
         _l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)), C.c_float(eps), _l.ptr(scratch),
         _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
         C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), C.c_int(rows_per_image), _l.ptr(residual),
         C.c_longlong(residual.stride(0) if residual is not None else 0), C.c_int(M), C.c_int(N), C.c_int(K),
-        C.c_int(_dt(x)), C.c_int(flags), _stream(x))
+        C.c_int(_dt(x)), C.c_int(flags), C.byref(ext), _stream(x))
     _l.check(rc, kernels=1 if scratch is None else 2)
     return out
 
 
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
-            pad_br=False, bn=0):
+            pad_br=False, bn=0, cta_group=0):
     """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout].
     pad_br (stride 2 only): zero padding on the bottom/right instead of all round (the VAE encoder's downsampler)."""
     lib = _l.load()
@@ -137,9 +176,10 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
     if residual is not None:
         assert residual.is_contiguous() and residual.shape == out.shape
     flags = (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_PAD_BR if pad_br else 0)
+    ext = _ext(x, cta_group)
     rc = lib.pcdm_conv3x3(_l.ptr(x), _l.ptr(w_packed), _l.ptr(out), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
                           C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
-                          C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), _stream(x))
+                          C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), C.byref(ext), _stream(x))
     _l.check(rc)
     return out
 
@@ -162,8 +202,9 @@ def _gn_workspace(device, B, groups):
     return ws
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None):
-    """x1: [B, ..., C1] NHWC (x2 optional second channel segment); returns [B, ..., C1+C2]."""
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None):
+    """x1: [B, ..., C1] NHWC (x2 optional second channel segment); returns [B, ..., C1+C2].
+    path: None (automatic), "two_pass" or "one_pass" (tests)."""
     lib = _l.load()
     lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong
     B = x1.shape[0]
@@ -177,7 +218,9 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None,
         workspace = _gn_workspace(x1.device, B, groups)
     rc = lib.pcdm_groupnorm(_l.ptr(x1), _l.ptr(x2), C.c_int(C1), _l.ptr(out), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)),
                             C.c_float(eps), C.c_int(B), C.c_int(HW), C.c_int(Ct), C.c_int(groups), C.c_int(_dt(x1)),
-                            C.c_int(_l.FLAG_SILU if silu else 0), _l.ptr(workspace), _stream(x1))
+                            C.c_int((_l.FLAG_SILU if silu else 0) | {None: 0, "two_pass": _l.FLAG_GN_TWO_PASS,
+                                                                     "one_pass": _l.FLAG_GN_ONE_PASS}[path]),
+                            _l.ptr(workspace), _stream(x1))
     _l.check(rc, kernels=2)
     return out
 

@@ -25,7 +25,9 @@ or None — then latents must be passed in and `output_type="latent"` is the onl
 from __future__ import annotations
 
 import inspect
+import json
 import os
+import warnings
 from types import SimpleNamespace
 from typing import Optional
 
@@ -48,7 +50,14 @@ class _B200DenoisingPipeline:
         if unet is None or scheduler is None:
             raise ValueError("unet and scheduler are required")
         if hasattr(scheduler, "config") and getattr(scheduler.config, "steps_offset", 1) != 1:
-            raise ValueError("scheduler.config.steps_offset must be 1 (reference :112-123)")
+            # reference :86-98: an outdated steps_offset is patched to 1 with a deprecation warning, never an error
+            # (UniPC's default 0 with linspace spacing does not use the offset at all)
+            warnings.warn(f"The configuration file of this scheduler: {scheduler} is outdated. `steps_offset` should be "
+                          f"set to 1 instead of {scheduler.config.steps_offset}.", FutureWarning)
+            try:
+                scheduler.config["steps_offset"] = 1
+            except TypeError:
+                pass   # immutable foreign config: the reference swaps _internal_dict; nothing here depends on it
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self.vae_scale_factor = (2 ** (len(vae.config.block_out_channels) - 1)) if vae is not None else 8
         self._graphs = {}
@@ -68,7 +77,16 @@ class _B200DenoisingPipeline:
                                                     torch_dtype=torch_dtype)
             if not vae._loaded:
                 vae = None
-        return cls(vae=vae, unet=unet, scheduler=kw.get("scheduler") or B200DDIMScheduler())
+        scheduler = kw.get("scheduler")
+        if scheduler is None:   # <path>/scheduler/scheduler_config.json when present (diffusers layout), else DDIM defaults
+            sc = os.path.join(str(pretrained_model_name_or_path), "scheduler", "scheduler_config.json")
+            cfg = {}
+            if os.path.exists(sc):
+                with open(sc) as f:
+                    cfg = json.load(f)
+            known = set(inspect.signature(B200DDIMScheduler.__init__).parameters) - {"self"}
+            scheduler = B200DDIMScheduler(**{k: v for k, v in cfg.items() if k in known})
+        return cls(vae=vae, unet=unet, scheduler=scheduler)
 
     # -- diffusers pipeline conveniences the reference drivers call ------------------------------------------------
     def to(self, *a, **k):
@@ -198,7 +216,8 @@ class _B200DenoisingPipeline:
                 cls=torch.empty((B, class_labels.shape[-1]), device=dev, dtype=dt) if has_cls else None,
                 t_cur=torch.zeros(1, device=dev, dtype=torch.float32),
                 counter=torch.zeros(2, device=dev, dtype=torch.int32),
-                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None, launches_per_step=0)
+                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None, wver=None,
+                launches_per_step=0)
             self._graphs[key] = st
         x_nchw = torch.cat([torch.cat([latents, latents], dim=0), extra.to(dev, torch.float32)], dim=1).contiguous()
         ops.nchw_to_nhwc_pad(x_nchw, 64, dt, out=st.x9_init)                                    # ref :499-501
@@ -211,8 +230,9 @@ class _B200DenoisingPipeline:
         st.kv = unet.context_kv(feature_f, out=st.kv)   # K/V GEMMs write straight into the graph's static buffers
         coef = sch.coefficient_table(dev)
         t_table = torch.cat([sch.timesteps.to(dev, torch.float32), torch.zeros(1, device=dev)]).contiguous()
-        rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps)
-        st.guidance, st.steps = guidance, steps
+        wver = getattr(unet, "_weights_version", 0)
+        rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps or st.wver != wver)
+        st.guidance, st.steps, st.wver = guidance, steps, wver
         if st.coef is None or st.coef.shape != coef.shape:
             st.coef, st.t_table = coef, t_table
             rebuild = True

@@ -244,6 +244,7 @@ class B200Stage1PriorTransformer(WeightArenaMixin):
         w["norm_out.weight"], w["norm_out.bias"] = vec(f("norm_out.weight")), vec(f("norm_out.bias"))
         self._arena = None
         self._loaded = True
+        self._weights_version += 1
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     def synthetic_state_dict(self, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
@@ -442,8 +443,9 @@ class B200Stage1PriorPipeline:
         st.latents_init.copy_(latents)
         coef = sch.coefficient_table(dev)
         t_table = torch.cat([sch.timesteps.to(dev, torch.float32), torch.zeros(1, device=dev)]).contiguous()
-        rebuild = st.graph is None or st.guidance != guidance_scale or st.steps != steps
-        st.guidance, st.steps = guidance_scale, steps
+        wver = getattr(prior, "_weights_version", 0)
+        rebuild = st.graph is None or st.guidance != guidance_scale or st.steps != steps or getattr(st, "wver", None) != wver
+        st.guidance, st.steps, st.wver = guidance_scale, steps, wver
         if st.coef is None or st.coef.shape != coef.shape:
             st.coef, st.t_table, st.noise = coef, t_table, noise.clone()
             rebuild = True

@@ -293,6 +293,7 @@ class B200AutoencoderKL(WeightArenaMixin):
         w["decoder.conv_out.weight"], w["decoder.conv_out.bias"] = conv("decoder.conv_out.weight", pad_out=32), f32("decoder.conv_out.bias", pad=32)
         self._arena = None
         self._loaded = True
+        self._weights_version += 1
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     def weight_bytes(self) -> int:

@@ -18,7 +18,7 @@ def _rt(x, dtype):
 
 
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0, w_static=True):
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
     if geglu:
@@ -51,7 +51,7 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
 
 
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
-            pad_br=False, bn=0):
+            pad_br=False, bn=0, cta_group=0):
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     w = w_packed.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
@@ -71,7 +71,7 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
     return y if out_f32 else _rt(y, x.dtype)
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None):
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None):
     x = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
     shp = x.shape
     y = F.group_norm(x.float().reshape(shp[0], -1, shp[-1]).transpose(1, 2), groups, gamma, beta, eps)

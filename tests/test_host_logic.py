@@ -142,3 +142,94 @@ def test_scheduler_protocol_and_tables():
     with pytest.raises(RuntimeError):
         s.step(e, 981, x)  # CPU tensors: no fallback
     assert torch.equal(s.scale_model_input(x, 3), x)
+
+
+def test_from_pretrained_ignore_mismatched_sizes_like_the_reference_driver(tmp_path):
+    """stage2_batchtest_inpaint_model.py:125-128: a stock SD-2.1 `unet/` folder (4-channel conv_in, no class
+    embedding) loaded with in_channels=9 + projection class embedding and ignore_mismatched_sizes=True.  Tensors the
+    checkpoint lacks or holds in another shape stay freshly initialised (diffusers semantics), everything else is
+    loaded; then the driver's own `load_state_dict(unet_dict)` (:130) overwrites all of it."""
+    import json
+    from dataclasses import replace
+    cfg = UNetConfig.tiny()
+    stock_cfg = replace(cfg, in_channels=4, class_embed_type=None, projection_class_embeddings_input_dim=None,
+                        use_pose_cond=False)
+    stock = make_unet(stock_cfg, seed=3).state_dict()
+    root = tmp_path / "sd21" / "unet"
+    root.mkdir(parents=True)
+    cj = {k: v for k, v in asdict(stock_cfg).items() if k != "use_pose_cond"}
+    (root / "config.json").write_text(json.dumps(cj))
+    torch.save(stock, root / "diffusion_pytorch_model.bin")
+    m = B200UNet2DConditionModel.from_pretrained(str(tmp_path / "sd21"), subfolder="unet", in_channels=9,
+                                                 class_embed_type="projection",
+                                                 projection_class_embeddings_input_dim=cfg.projection_class_embeddings_input_dim,
+                                                 torch_dtype=torch.float32, low_cpu_mem_usage=False,
+                                                 ignore_mismatched_sizes=True, device="cpu")
+    assert m.config.in_channels == 9 and m._loaded
+    # loaded tensors come from the checkpoint ...
+    k = "down_blocks.0.resnets.0.norm1.weight"
+    assert torch.equal(m._w[k], stock[k])
+    # ... the mismatched conv_in is NOT the zero-padded 4-channel weight but a fresh 9-channel one
+    ci = m._w["conv_in.weight"].view(-1, 3, 3, 64)
+    assert ci[..., 4:9].abs().sum() > 0 and ci[..., 9:].abs().sum() == 0
+    assert "class_embedding.linear_1.weight" in m._w
+    with pytest.raises(RuntimeError):   # strict (the default) still refuses
+        B200UNet2DConditionModel(dtype=torch.float32, device="cpu", **asdict(cfg)).load_state_dict(stock)
+    # the driver's second step: the real stage-2 checkpoint, strict
+    v0 = m._weights_version
+    res = m.load_state_dict(make_unet(cfg, seed=0).state_dict())
+    assert not res.missing_keys and m._weights_version == v0 + 1
+
+
+def test_weight_changes_invalidate_captured_graph_state():
+    """Captured graphs hold raw weight pointers: load_state_dict / consolidate bump the model's weight generation and
+    the pipeline's rebuild test includes it."""
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg)
+    v = m._weights_version
+    m.consolidate()
+    assert m._weights_version == v + 1
+    m.load_state_dict(o.state_dict())
+    assert m._weights_version == v + 2 and m._arena is None
+
+
+def test_pipeline_accepts_unipc_default_scheduler_and_reads_scheduler_config(tmp_path):
+    """constructing with B200UniPCMultistepScheduler() (steps_offset 0, linspace spacing) must not raise —
+    the reference only patches an outdated steps_offset with a deprecation warning (:86-98); from_pretrained reads
+    scheduler/scheduler_config.json when present."""
+    import json
+    import warnings
+    from pcdms_b200.scheduler import B200UniPCMultistepScheduler
+    cfg = UNetConfig.tiny()
+    _, m = _models(cfg)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pipe = B200Stage2InpaintPipeline(vae=None, unet=m, scheduler=B200UniPCMultistepScheduler())
+    assert pipe.scheduler.config.steps_offset == 1 and any("steps_offset" in str(x.message) for x in w)
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(
+        {"_class_name": "DDIMScheduler", "beta_start": 0.001, "beta_end": 0.02, "steps_offset": 1,
+         "clip_sample": False, "set_alpha_to_one": False}))
+    p2 = B200Stage2InpaintPipeline.from_pretrained(str(tmp_path), unet=m)
+    assert p2.scheduler.config.beta_start == 0.001 and p2.scheduler.config.beta_end == 0.02
+
+
+def test_default_workspace_is_per_device_and_never_replaced():
+    """'cuda' and 'cuda:0' must name the same scratch buffer and an existing one is never freed —
+    captured graphs hold its address.  (Host logic only: no GPU here, so the allocation itself is patched.)"""
+    from unittest import mock
+    from pcdms_b200 import ops
+    made = []
+    real_zeros = torch.zeros
+
+    def fake_zeros(n, dtype=None, device=None):
+        made.append((n, str(device)))
+        return real_zeros(8, dtype=torch.uint8)
+
+    with mock.patch.object(ops, "_default_ws", {}), mock.patch("torch.cuda.current_device", return_value=0), \
+            mock.patch("torch.zeros", fake_zeros):
+        a = ops.ensure_workspace("cuda")
+        b = ops.ensure_workspace("cuda:0")
+        c = ops.ensure_workspace(torch.device("cuda", 0), nbytes=1)
+        assert a is b is c and len(made) == 1 and made[0][0] == ops.WORKSPACE_BYTES
+        assert ops.ensure_workspace("cpu") is None

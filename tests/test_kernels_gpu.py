@@ -109,6 +109,54 @@ def test_conv3x3_split_k_matches_single_pass(ops, B, H, W, Cin, Cout):
     assert torch.equal(auto, ops.conv3x3(xd, wd, bias=b.cuda(), rowvec=t.cuda(), residual=rd))  # deterministic
 
 
+def _splitk_problem(dev, seed):
+    dt = torch.float16
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(16, 4, 8, 1280, generator=g).to(dt).to(dev)
+    w = (torch.randn(1280, 9 * 1280, generator=g) / (9 * 1280) ** 0.5).to(dt).to(dev)
+    b = torch.randn(1280, generator=g).to(dev)
+    return x, w, b
+
+
+def test_two_streams_with_their_own_workspaces_are_independent(ops):
+    """The C ABI carries no process-wide state: split-K scratch is a per-call argument.  Two
+    streams running the split-K conv concurrently, each with its own workspace, give exactly the serial results."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    probs = [_splitk_problem(dev, s) for s in (1, 2)]
+    serial = [ops.conv3x3(x, w, bias=b) for x, w, b in probs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    wss = [torch.zeros(ops.WORKSPACE_BYTES, dtype=torch.uint8, device=dev) for _ in streams]
+    outs = [[], []]
+    torch.cuda.synchronize()
+    for it in range(20):                      # interleaved enqueue: the two streams overlap on the device
+        for k, (s, ws) in enumerate(zip(streams, wss)):
+            with torch.cuda.stream(s), ops.use_workspace(ws):
+                x, w, b = probs[k]
+                outs[k].append(ops.conv3x3(x, w, bias=b))
+    torch.cuda.synchronize()
+    for k in range(2):
+        for o in outs[k]:
+            assert torch.equal(o, serial[k])
+
+
+def test_two_devices_from_one_process(ops):
+    """Per-device kernel attributes / SM counts / workspaces: the same problem on cuda:0 and cuda:1 from one process
+    is bit-identical (needs a >= 2-GPU lease; the round-end 8-GPU box runs it)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outs = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            x, w, b = _splitk_problem(torch.device("cuda", d), 3)
+            q = torch.randn(2 * 256, 3 * 320, generator=torch.Generator().manual_seed(4)).half().to(f"cuda:{d}")
+            o1 = ops.conv3x3(x, w, bias=b)
+            o2 = ops.attention(q[:, :320], q[:, 320:640], q[:, 640:], 2, 5)
+            torch.cuda.synchronize()
+            outs.append((o1.cpu(), o2.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_conv3x3_rejects_unsupported_shapes(ops):
     from pcdms_b200.lib import PcdmError
     x = torch.zeros(1, 8, 24, 64, device="cuda", dtype=torch.float16)  # W = 24 does not divide 128
@@ -140,18 +188,12 @@ def test_groupnorm(ops, dt, B, H, W, C1, C2, silu):
     close(out.permute(0, 3, 1, 2), ref, dt)
     # the single-pass (register-resident, cluster-reduced) path and the statistics + apply path agree to rounding,
     # and each is bit-reproducible
-    from pcdms_b200 import lib as L
     args = (x1.permute(0, 2, 3, 1).contiguous().cuda(), gamma.cuda(), beta.cuda(), 1e-5)
     kw = dict(x2=x2.permute(0, 2, 3, 1).contiguous().cuda() if C2 else None, silu=silu)
     assert torch.equal(out, ops.groupnorm(*args, **kw))
-    try:
-        L.load().pcdm_set_groupnorm_two_pass(1)
-        two = ops.groupnorm(*args, **kw)
-        L.load().pcdm_set_groupnorm_two_pass(2)
-        one = ops.groupnorm(*args, **kw)
-        assert torch.equal(one, ops.groupnorm(*args, **kw))
-    finally:
-        L.load().pcdm_set_groupnorm_two_pass(0)
+    two = ops.groupnorm(*args, path="two_pass", **kw)
+    one = ops.groupnorm(*args, path="one_pass", **kw)
+    assert torch.equal(one, ops.groupnorm(*args, path="one_pass", **kw))
     close(two.permute(0, 3, 1, 2), ref, dt)
     close(one.permute(0, 3, 1, 2), ref, dt)
     torch.testing.assert_close(one.float(), two.float(), rtol=1e-2, atol=1e-2)
@@ -300,7 +342,7 @@ def test_softmax_rows(ops, dt, M, N):
 ])
 def test_skinny_gemm(ops, dt, M, N, K, kw):
     """pcdm_gemm with M <= 32 rows: the weight-streaming mma.sync kernel (skinny.cu) against torch fp32 on the same 16-bit
-    inputs, against the tcgen05 tile path it replaces (pcdm_set_skinny_gemm(0)), through strided views, and run to run."""
+    inputs, against the tcgen05 tile path it replaces (PCDM_FLAG_NO_SKINNY), through strided views, and run to run."""
     import ctypes as C
     from pcdms_b200 import lib
     g = torch.Generator().manual_seed(M + N + K)
@@ -339,12 +381,7 @@ def test_skinny_gemm(ops, dt, M, N, K, kw):
         sub = dict(args, residual=args["residual"][:k] if args["residual"] is not None else None)
         assert torch.equal(ops.gemm(ad[:k], w.cuda(), **sub), out[:k])
     if N % 32 == 0:                                                     # the tile path needs N % 32 == 0
-        L = lib.load()
-        L.pcdm_set_skinny_gemm(C.c_int(0))
-        try:
-            tiles = ops.gemm(ad, w.cuda(), **args)
-        finally:
-            L.pcdm_set_skinny_gemm(C.c_int(1))
+        tiles = ops.gemm(ad, w.cuda(), skinny=False, **args)
         close(out, tiles.float().cpu(), dt, mult=2.0)
 
 

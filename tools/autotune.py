@@ -4,6 +4,7 @@ and time it under each (bn, cta_group) variant plus the automatic choice.  Outpu
 import json
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 from pcdms_b200.unet import B200UNet2DConditionModel

@@ -12,6 +12,7 @@ import json
 import sys
 
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 
 from pcdms_b200.clip import B200CLIPVisionModelWithProjection

@@ -1,6 +1,7 @@
 """Dev check (GPU): attention kernel — share of exp2 on the FMA pipe (0..3 of 4 column pairs): correctness vs an fp32
 softmax reference and timing."""
 import sys; sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 L = lib.load(); dev = "cuda"

@@ -4,6 +4,7 @@ parts of the kernel switched off through pcdm_set_gemm_debug (results are wrong 
 import ctypes as C
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 dev, dt = "cuda", torch.bfloat16

@@ -3,6 +3,7 @@ import sys, time, json
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 from pcdms_b200 import ops
 
 torch.manual_seed(0)

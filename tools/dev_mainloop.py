@@ -4,6 +4,7 @@ the loop was paced by the issuing THREAD — ~330 cycles of barrier handshake + 
 `lane == 0` branch — not by loads or MMAs; see profiles/r1_mainloop_experiment.md.)"""
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 dev = "cuda"; dt = torch.bfloat16

@@ -2,6 +2,7 @@
 buffer pair (L2-warm) and once rotating over 8 buffer pairs (> L2: HBM-cold), next to a device copy of the same size."""
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 dev = "cuda"; dt = torch.bfloat16

@@ -1,6 +1,7 @@
 """A handful of representative launches for `ncu --set full` (one warm-up + one profiled launch each)."""
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 dev = "cuda"; dt = torch.bfloat16

@@ -2,6 +2,7 @@
 shapes, with a same-size device copy as the bandwidth yardstick."""
 import sys
 sys.path.insert(0, ".")
+import tools._explib  # noqa: F401  (experiment build: pcdm_set_* hooks)
 import torch
 from pcdms_b200 import ops, lib
 dev = "cuda"; dt = torch.bfloat16
