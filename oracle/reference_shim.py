@@ -157,16 +157,19 @@ class _DemoUNetAdapter(torch.nn.Module):
 
 
 def run_reference_demo_pipeline(cfg, oracle_unet_half, *, latents, mask, simg_mask_latents, cond_pose, prompt_embeds,
-                                negative_prompt_embeds, num_inference_steps, guidance_scale):
+                                negative_prompt_embeds, num_inference_steps, guidance_scale, scheduler=None,
+                                raw_unet=False):
     """Run PCDMsPipeline.__call__ (PCDMs_pipeline.py:889-1180, the pcdms_demo.ipynb driver) unmodified on CPU.  The
     reference hard-codes fp16 for the UNet input (:1115), so the UNet and the conditioning are fp16 here.  Returns the
-    final latents (identity VAE)."""
+    final latents (identity VAE).  `raw_unet=True` hands the given object to the pipeline as `unet` without the adapter
+    (plug-in tests: a B200UNet2DConditionModel), `scheduler` replaces the shim's DDIM."""
     _enable()
     from diffusers.schedulers import DDIMScheduler
     from src.pipelines.PCDMs_pipeline import PCDMsPipeline
 
     pipe = PCDMsPipeline(vae=_EncodeVAE(latents), text_encoder=None, tokenizer=None,
-                         unet=_DemoUNetAdapter(oracle_unet_half, cfg), scheduler=DDIMScheduler(), safety_checker=None,
+                         unet=oracle_unet_half if raw_unet else _DemoUNetAdapter(oracle_unet_half, cfg),
+                         scheduler=scheduler or DDIMScheduler(), safety_checker=None,
                          feature_extractor=None, requires_safety_checker=False)
     h, w = latents.shape[-2:]
     out = pipe(simg_mask_latents=simg_mask_latents, mask=mask, cond_pose=cond_pose.half(),

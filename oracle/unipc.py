@@ -60,6 +60,7 @@ class UniPCMultistepScheduler:
     def from_config(cls, config, **kw):
         keys = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "solver_order", "prediction_type",
                 "predict_x0", "solver_type", "lower_order_final", "timestep_spacing", "steps_offset")
+        config = {k: config[k] for k in config.keys()} if hasattr(config, "keys") else dict(vars(config))
         d = {k: config[k] for k in keys if k in config}
         d.update(kw)
         return cls(**d)

@@ -28,6 +28,12 @@ def _stream(t: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    """The product has no CPU compute path: boundary classes call this before dispatching to the kernels."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} runs on CUDA tensors only (no CPU fallback)")
+
+
 def _f32(t):
     if t is not None and t.dtype != torch.float32:
         raise TypeError("bias / rowvec vectors must be fp32")

@@ -20,6 +20,13 @@ import torch
 from . import ops
 
 
+def _config_dict(config):
+    """A scheduler config as a plain dict: diffusers hands a FrozenDict (a mapping), some callers an attribute bag."""
+    if hasattr(config, "keys"):
+        return {k: config[k] for k in config.keys()}
+    return dict(vars(config))
+
+
 class _AttrDict(dict):
     def __getattr__(self, k):
         try:
@@ -67,6 +74,7 @@ class B200DDIMScheduler:
     def from_config(cls, config, **kw):
         keys = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "clip_sample", "set_alpha_to_one",
                 "steps_offset", "prediction_type", "timestep_spacing")
+        config = _config_dict(config)
         d = {k: config[k] for k in keys if k in config}
         d.update(kw)
         return cls(**d)
@@ -104,8 +112,7 @@ class B200DDIMScheduler:
             raise NotImplementedError("B200DDIMScheduler: eta must be 0 (as in the reference drivers)")
         if self.num_inference_steps is None:
             raise ValueError("call set_timesteps() first")
-        if not sample.is_cuda:
-            raise RuntimeError("B200DDIMScheduler.step runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(sample, "B200DDIMScheduler.step")
         c = self.step_coefficients(timestep)
         prev = ops.ddim_step(model_output.contiguous(), sample.contiguous(), c)
         if not return_dict:
@@ -182,7 +189,7 @@ class B200UniPCMultistepScheduler:
         one does not know (skip_prk_steps, set_alpha_to_one, clip_sample, ...) are ignored, as diffusers does."""
         import inspect
         known = set(inspect.signature(cls.__init__).parameters) - {"self"}
-        d = {k: v for k, v in dict(config).items() if k in known}
+        d = {k: v for k, v in _config_dict(config).items() if k in known}
         d.update(kw)
         return cls(**d)
 
@@ -305,8 +312,7 @@ class B200UniPCMultistepScheduler:
     def step(self, model_output, timestep, sample, return_dict: bool = True):
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' first")
-        if not sample.is_cuda:
-            raise RuntimeError("B200UniPCMultistepScheduler.step runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(sample, "B200UniPCMultistepScheduler.step")
         if self._step_index is None:
             self._init_step_index(timestep)
         if self._hist is None or self._hist.shape[1] != sample.numel() or self._hist.device != sample.device:
@@ -382,6 +388,7 @@ class B200UnCLIPScheduler:
     def from_config(cls, config, **kw):
         keys = ("num_train_timesteps", "variance_type", "clip_sample", "clip_sample_range", "prediction_type",
                 "beta_schedule")
+        config = _config_dict(config)
         d = {k: config[k] for k in keys if k in config}
         d.update(kw)
         return cls(**d)

@@ -99,6 +99,9 @@ class B200Attention:
     def set_use_memory_efficient_attention_xformers(self, *a, **k):  # reference calls enable_xformers...(): no-op
         return None
 
+    def children(self):
+        return iter(())
+
     def prepare_attention_mask(self, attention_mask, target_length, batch_size, out_dim=3):
         if attention_mask is not None:
             raise NotImplementedError
@@ -142,6 +145,7 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         self.use_pose_cond = config.get("use_pose_cond", cfg["class_embed_type"] == "projection")
         self._w: Dict[str, torch.Tensor] = {}
         self._attn: Dict[str, B200Attention] = {}
+        self.encoder_hid_proj = None   # read by PCDMsPipeline (PCDMs_pipeline.py:1067); never configured on this path
         self._loaded = False
         self._weights_version = 0   # bumped whenever the packed weight tensors move (load_state_dict, consolidate, broadcast)
         self._ctx_cache = None   # (tensor id, version, shape) -> per-block K/V
@@ -235,6 +239,12 @@ class B200UNet2DConditionModel(WeightArenaMixin):
     def modules(self):
         yield self
         yield from self._attn.values()
+
+    def children(self):   # diffusers' recursive walks (enable_xformers..., _execution_device) use children()/modules()
+        yield from self._attn.values()
+
+    def set_use_memory_efficient_attention_xformers(self, *a, **k):
+        return None  # the fused tcgen05 attention kernel is always on (stage2_batchtest_inpaint_model.py:133)
 
     def parameters(self):
         return iter(self._w.values())
@@ -547,8 +557,7 @@ class B200UNet2DConditionModel(WeightArenaMixin):
             if v is not None:
                 raise NotImplementedError(f"pcdm_b200 UNet: `{name}` is not supported (never passed on the reference "
                                           f"path, stage2_inpaint_pipeline.py:504-506)")
-        if not sample.is_cuda:
-            raise RuntimeError("pcdm_b200 UNet runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(sample, "pcdm_b200 UNet")
         cfg = self.config
         B, Cin, H, W = sample.shape
         if Cin != cfg.in_channels:
