@@ -156,10 +156,25 @@ int pcdm_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, 
  * 0..3 of the next UNet input for both CFG halves (reference stage2_inpaint_pipeline.py:499-501,510-512,519).
  * coef_table[step] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} (float4, device);
  * step_counter: int[2] device {step, scratch=0}; the kernel advances step, so one CUDA graph serves every step.
- * t_table (steps+1 fp32 timesteps, device) / t_cur (device scalar) are optional: when given, *t_cur = t_table[step+1]. */
+ * t_table (steps+1 fp32 timesteps, device) / t_cur (device scalar) are optional: when given, *t_cur = t_table[step+1].
+ * rescale_ratio (device, n floats from pcdm_cfg_rescale_ratio; NULL = off) / guidance_rescale: the reference's
+ * rescale_noise_cfg (:52-63, applied at :514-516), i.e. eps = r * (cfg * ratio[b]) + (1 - r) * cfg. */
 int pcdm_cfg_ddim_step(const void* eps, int eps_dtype, long long ld_eps, float* latents, void* x9, int x9_dtype,
                        long long ld_x9, const float* coef_table, int* step_counter, float guidance_scale, int n,
-                       int HW, const float* t_table, float* t_cur, void* stream);
+                       int HW, const float* t_table, float* t_cur, const float* rescale_ratio, float guidance_rescale,
+                       void* stream);
+
+/* Classifier-free guidance on its own (reference stage2_inpaint_pipeline.py:510-516).
+ * pcdm_cfg_rescale_ratio: ratio[b] = std(eps_cond[b]) / std(cfg[b]) over (C, H, W) (unbiased, as torch.std), cfg = e_u +
+ *   g (e_c - e_u); element (b, c, p) of the 2n-sample epsilon batch (samples [0, n) unconditional) is read at
+ *   eps[b * stride_b + c * stride_c + p * stride_p] (strides in elements: NCHW tensors and NHWC rows both fit);
+ *   one CTA per sample, fixed reduction order.
+ * pcdm_cfg_combine: out[n, per_sample] = cfg of eps[2n, per_sample] (contiguous), rescaled when rescale_ratio != NULL.
+ * dtypes: 0 f16, 1 bf16, 2 f32. */
+int pcdm_cfg_rescale_ratio(const void* eps, int eps_dtype, long long stride_b, long long stride_c, long long stride_p,
+                           int n, int C, int HW, float guidance_scale, float* ratio, void* stream);
+int pcdm_cfg_combine(const void* eps, int eps_dtype, void* out, int out_dtype, int n, long long per_sample,
+                     float guidance_scale, const float* rescale_ratio, float guidance_rescale, void* stream);
 
 /* DDIMScheduler.step (eta 0) on its own, for callers that drive the scheduler protocol tensor by tensor
  * (stage2_inpaint_pipeline.py:519): prev = sqrt_a_prev * (sample - sqrt_one_minus_a_t * eps) * inv_sqrt_a_t
@@ -185,7 +200,8 @@ int pcdm_add_noise(const void* x0, const void* noise, void* out, int dtype, cons
  * last_sample / m0 / m1 are fp32 history buffers of numel entries owned by the caller; coef_row_host: 16 HOST floats. */
 int pcdm_cfg_unipc_step(const void* eps, int eps_dtype, long long ld_eps, float* state, void* x9, int x9_dtype,
                         long long ld_x9, const float* coef_table, int* step_counter, float guidance_scale, int n,
-                        int HW, const float* t_table, float* t_cur, void* stream);
+                        int HW, const float* t_table, float* t_cur, const float* rescale_ratio, float guidance_rescale,
+                        void* stream);
 int pcdm_unipc_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
                     float* last_sample, float* m0, float* m1, const float* coef_row_host, long long numel,
                     void* stream);

@@ -53,7 +53,7 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
 
 @torch.no_grad()
 def denoise_loop(unet, scheduler, *, latents, cond, num_inference_steps, guidance_scale=2.0, dtype=torch.float32,
-                 return_trajectory=False):
+                 return_trajectory=False, guidance_rescale=0.0):
     """ref :472-520.  `latents`: [n, 4, h, w] initial noise (already times init_noise_sigma); `cond` from
     prepare_conditioning.  Returns the final latents (and, optionally, the per-step (eps, latents) list)."""
     scheduler.set_timesteps(num_inference_steps)
@@ -65,7 +65,10 @@ def denoise_loop(unet, scheduler, *, latents, cond, num_inference_steps, guidanc
         x9 = torch.cat([x, cond["mask"], cond["masked_latents"]], dim=1).to(dtype)       # :501
         eps = unet(x9, t, class_labels=cond["prior_embed"], encoder_hidden_states=cond["feature_f"],
                    my_pose_cond=cond["pose_cond"], return_dict=False)[0]                  # :504-506
+        eps_text = eps.chunk(2)[1]
         eps = cfg_combine(eps, guidance_scale)                                            # :510-512
+        if guidance_rescale > 0.0:                                                        # :514-516
+            eps = rescale_noise_cfg(eps, eps_text, guidance_rescale=guidance_rescale)
         latents = scheduler.step(eps, t, latents, return_dict=False)[0]                   # :519
         if return_trajectory:
             traj.append((eps.clone(), latents.clone()))

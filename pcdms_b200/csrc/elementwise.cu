@@ -107,6 +107,83 @@ __global__ void upsample_nearest2x_kernel(const uint4* __restrict__ x, uint4* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Classifier-free guidance with rescale (reference rescale_noise_cfg, src/pipelines/stage2_inpaint_pipeline.py:52-63;
+// applied at :514-516 when guidance_rescale > 0 — off in the shipped drivers):
+//     cfg = e_u + g (e_c - e_u);   ratio = std(e_c) / std(cfg)   per sample over (C, H, W), unbiased (torch.std);
+//     out = r * (cfg * ratio) + (1 - r) * cfg
+// cfg_rescale_ratio_kernel: one CTA per sample, two passes over the sample (means, then squared deviations — no
+// catastrophic cancellation), fixed reduction order (bit-reproducible).  Element (b, c, p) of the 2n-row epsilon
+// batch lives at eps[b * sb + c * sc + p * sp]: NCHW tensors and the UNet's NHWC output rows are both addressable.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {   // all threads get the total; fixed order
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(512) cfg_rescale_ratio_kernel(const void* __restrict__ eps, int dt, long long sb,
+                                                                long long sc, long long sp, int n, int C, int HW,
+                                                                float guidance, float* __restrict__ ratio) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[16];
+  const int b = blockIdx.x;
+  const long long total = (long long)C * HW;
+  double s_t = 0.0, s_c = 0.0;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = (int)(i / HW), p = (int)(i % HW);
+    const float eu = load_any(eps, b * sb + c * sc + p * sp, dt);
+    const float ec = load_any(eps, (long long)(b + n) * sb + c * sc + p * sp, dt);
+    s_t += (double)ec;
+    s_c += (double)__fadd_rn(eu, __fmul_rn(guidance, __fsub_rn(ec, eu)));
+  }
+  const double m_t = block_sum(s_t, red) / (double)total;
+  const double m_c = block_sum(s_c, red) / (double)total;
+  double q_t = 0.0, q_c = 0.0;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = (int)(i / HW), p = (int)(i % HW);
+    const float eu = load_any(eps, b * sb + c * sc + p * sp, dt);
+    const float ec = load_any(eps, (long long)(b + n) * sb + c * sc + p * sp, dt);
+    const double dt_ = (double)ec - m_t;
+    const double dc = (double)__fadd_rn(eu, __fmul_rn(guidance, __fsub_rn(ec, eu))) - m_c;
+    q_t += dt_ * dt_;
+    q_c += dc * dc;
+  }
+  q_t = block_sum(q_t, red);
+  q_c = block_sum(q_c, red);
+  if (threadIdx.x == 0) {
+    const double denom = (double)(total > 1 ? total - 1 : 1);
+    ratio[b] = __fdiv_rn((float)sqrt(q_t / denom), (float)sqrt(q_c / denom));
+  }
+}
+
+// e = e_u + g (e_c - e_u), optionally rescaled: r * (e * ratio[b]) + (1 - r) * e  (reference operation order)
+__device__ __forceinline__ float cfg_value(float eu, float ec, float guidance, const float* ratio, int b, float rescale) {
+  float e = __fadd_rn(eu, __fmul_rn(guidance, __fsub_rn(ec, eu)));
+  if (ratio) e = __fadd_rn(__fmul_rn(rescale, __fmul_rn(e, ratio[b])), __fmul_rn(__fsub_rn(1.0f, rescale), e));
+  return e;
+}
+
+// The CFG combine on its own, for callers that drive the scheduler protocol tensor by tensor (the generic loop):
+// eps: [2n, per_sample] contiguous (rows [0, n) unconditional), out: [n, per_sample].
+__global__ void cfg_combine_kernel(const void* __restrict__ eps, int dt, void* __restrict__ out, int out_dt, int n,
+                                   long long per_sample, float guidance, const float* __restrict__ ratio, float rescale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)n * per_sample;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const float eu = load_any(eps, i, dt), ec = load_any(eps, i + total, dt);
+    store_any(out, i, out_dt, cfg_value(eu, ec, guidance, ratio, b, rescale));
+  }
+}
+
 // Fused per-step kernel.  eps: UNet output rows [2n, HW, ld_eps] (channels 0..3; [uncond ; cond] batch halves).
 // latents: [n, 4, HW] fp32 scheduler state, updated in place:
 //     e      = e_u + g (e_c - e_u)
@@ -119,7 +196,8 @@ __global__ void upsample_nearest2x_kernel(const uint4* __restrict__ x, uint4* __
 __global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, long long ld_eps,
                                      float* __restrict__ latents, void* __restrict__ x9, int x9_dt, long long ld_x9,
                                      const float4* __restrict__ coef, int* __restrict__ step_counter, float guidance,
-                                     int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur) {
+                                     int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur,
+                                     const float* __restrict__ ratio, float rescale) {
   pdl_launch_dependents();
   pdl_wait();
   const int step = *step_counter;
@@ -148,7 +226,7 @@ __global__ void cfg_ddim_step_kernel(const void* __restrict__ eps, int eps_dt, l
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float eu = eu4[c], ec = ec4[c];
-      const float e = eu + guidance * (ec - eu);
+      const float e = ratio ? cfg_value(eu, ec, guidance, ratio, b, rescale) : eu + guidance * (ec - eu);
       const long long li = ((long long)b * 4 + c) * HW + p;
       const float x = latents[li];
       const float x0 = (x - cf.y * e) * cf.x;
@@ -299,7 +377,8 @@ __device__ __forceinline__ void unipc_update(const UniPCRow& r, float e, float& 
 __global__ void cfg_unipc_step_kernel(const void* __restrict__ eps, int eps_dt, long long ld_eps,
                                       float* __restrict__ state, void* __restrict__ x9, int x9_dt, long long ld_x9,
                                       const UniPCRow* __restrict__ coef, int* __restrict__ step_counter, float guidance,
-                                      int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur) {
+                                      int n, int HW, const float* __restrict__ t_table, float* __restrict__ t_cur,
+                                      const float* __restrict__ ratio, float rescale) {
   pdl_launch_dependents();
   pdl_wait();
   const int step = *step_counter;
@@ -313,7 +392,7 @@ __global__ void cfg_unipc_step_kernel(const void* __restrict__ eps, int eps_dt, 
     for (int c = 0; c < 4; ++c) {
       const float eu = load_any(eps, ((long long)b * HW + p) * ld_eps + c, eps_dt);
       const float ec = load_any(eps, ((long long)(b + n) * HW + p) * ld_eps + c, eps_dt);
-      const float e = __fadd_rn(eu, __fmul_rn(guidance, __fsub_rn(ec, eu)));
+      const float e = cfg_value(eu, ec, guidance, ratio, b, rescale);
       const long long li = ((long long)b * 4 + c) * HW + p;
       float x = state[li], last = state[plane + li], ma = state[2 * plane + li], mb = state[3 * plane + li];
       unipc_update(r, e, x, last, ma, mb);
@@ -580,13 +659,38 @@ extern "C" int pcdm_upsample_nearest2x(const void* x, void* y, int B, int H, int
 extern "C" int pcdm_cfg_ddim_step(const void* eps, int eps_dtype, long long ld_eps, float* latents, void* x9,
                                   int x9_dtype, long long ld_x9, const float* coef_table, int* step_counter,
                                   float guidance_scale, int n, int HW, const float* t_table, float* t_cur,
-                                  void* stream_) {
+                                  const float* rescale_ratio, float guidance_rescale, void* stream_) {
   if (!eps || !latents || !x9 || !coef_table || !step_counter) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: null pointer");
   if (eps_dtype < 0 || eps_dtype > 2 || x9_dtype < 0 || x9_dtype > 1) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: bad dtype");
   if (n <= 0 || HW <= 0 || ld_eps < 4 || ld_x9 < 4) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: bad shape");
   if (reinterpret_cast<uintptr_t>(coef_table) & 15) return set_error(PCDM_ERR_INVALID, "cfg_ddim_step: coef table must be 16-byte aligned");
   const long long total = (long long)n * HW;
-  PCDM_CUDA(launch_kernel(cfg_ddim_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, latents, x9, x9_dtype, ld_x9, reinterpret_cast<const float4*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur));
+  PCDM_CUDA(launch_kernel(cfg_ddim_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, latents, x9, x9_dtype, ld_x9, reinterpret_cast<const float4*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur, rescale_ratio, guidance_rescale));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_cfg_rescale_ratio(const void* eps, int eps_dtype, long long stride_b, long long stride_c,
+                                      long long stride_p, int n, int C, int HW, float guidance_scale, float* ratio,
+                                      void* stream_) {
+  if (!eps || !ratio) return set_error(PCDM_ERR_INVALID, "cfg_rescale_ratio: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2) return set_error(PCDM_ERR_INVALID, "cfg_rescale_ratio: bad dtype");
+  if (n <= 0 || C <= 0 || HW <= 0 || stride_b <= 0 || stride_c <= 0 || stride_p <= 0)
+    return set_error(PCDM_ERR_INVALID, "cfg_rescale_ratio: bad shape");
+  PCDM_CUDA(launch_kernel(cfg_rescale_ratio_kernel, dim3(n), dim3(512), 0, (cudaStream_t)stream_, 1, eps, eps_dtype,
+                          stride_b, stride_c, stride_p, n, C, HW, guidance_scale, ratio));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_cfg_combine(const void* eps, int eps_dtype, void* out, int out_dtype, int n, long long per_sample,
+                                float guidance_scale, const float* rescale_ratio, float guidance_rescale, void* stream_) {
+  if (!eps || !out) return set_error(PCDM_ERR_INVALID, "cfg_combine: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || out_dtype < 0 || out_dtype > 2) return set_error(PCDM_ERR_INVALID, "cfg_combine: bad dtype");
+  if (n <= 0 || per_sample <= 0) return set_error(PCDM_ERR_INVALID, "cfg_combine: empty problem");
+  const long long total = (long long)n * per_sample;
+  PCDM_CUDA(launch_kernel(cfg_combine_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, eps,
+                          eps_dtype, out, out_dtype, n, per_sample, guidance_scale, rescale_ratio, guidance_rescale));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -636,12 +740,12 @@ extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const voi
 extern "C" int pcdm_cfg_unipc_step(const void* eps, int eps_dtype, long long ld_eps, float* state, void* x9,
                                    int x9_dtype, long long ld_x9, const float* coef_table, int* step_counter,
                                    float guidance_scale, int n, int HW, const float* t_table, float* t_cur,
-                                   void* stream_) {
+                                   const float* rescale_ratio, float guidance_rescale, void* stream_) {
   if (!eps || !state || !x9 || !coef_table || !step_counter) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: null pointer");
   if (eps_dtype < 0 || eps_dtype > 2 || x9_dtype < 0 || x9_dtype > 1) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: bad dtype");
   if (n <= 0 || HW <= 0 || ld_eps < 4 || ld_x9 < 4) return set_error(PCDM_ERR_INVALID, "cfg_unipc_step: bad shape");
   const long long total = (long long)n * HW;
-  PCDM_CUDA(launch_kernel(cfg_unipc_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, state, x9, x9_dtype, ld_x9, reinterpret_cast<const UniPCRow*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur));
+  PCDM_CUDA(launch_kernel(cfg_unipc_step_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream_, 1, eps, eps_dtype, ld_eps, state, x9, x9_dtype, ld_x9, reinterpret_cast<const UniPCRow*>(coef_table), step_counter, guidance_scale, n, HW, t_table, t_cur, rescale_ratio, guidance_rescale));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -322,8 +322,50 @@ def upsample_nearest2x(x, out=None):
     return out
 
 
-def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
-    """eps_rows: [2n, H, W, ld] UNet output rows; latents: [n, 4, H, W] fp32 (in place); x9: [2n, H, W, ld9]."""
+def cfg_rescale_ratio(eps, guidance_scale, out=None, *, nhwc_channels=None):
+    """Per-sample std(eps_cond) / std(cfg) of the reference's rescale_noise_cfg.  eps: the 2n-sample epsilon batch, either
+    NCHW [2n, C, H, W] contiguous or (nhwc_channels=C) NHWC rows [2n, H, W, ld] of which the first C channels count.
+    Returns [n] fp32."""
+    lib = _l.load()
+    assert eps.is_contiguous() and eps.shape[0] % 2 == 0
+    n = eps.shape[0] // 2
+    if nhwc_channels is None:
+        Cc, HW = eps.shape[1], eps[0, 0].numel()
+        sb, sc, sp = Cc * HW, HW, 1
+    else:
+        Cc, ld = nhwc_channels, eps.shape[-1]
+        HW = eps[0].numel() // ld
+        sb, sc, sp = HW * ld, 1, ld
+    if out is None:
+        out = torch.empty(n, device=eps.device, dtype=torch.float32)
+    rc = lib.pcdm_cfg_rescale_ratio(_l.ptr(eps), C.c_int(_any_dt(eps)), C.c_longlong(sb), C.c_longlong(sc),
+                                    C.c_longlong(sp), C.c_int(n), C.c_int(Cc), C.c_int(HW), C.c_float(guidance_scale),
+                                    _l.ptr(out), _stream(eps))
+    _l.check(rc)
+    return out
+
+
+def cfg_combine(eps, guidance_scale, guidance_rescale=0.0, out=None):
+    """eps: [2n, ...] contiguous (rows [0, n) unconditional) -> [n, ...]: e_u + g (e_c - e_u), then the reference's
+    rescale_noise_cfg when guidance_rescale > 0 (stage2_inpaint_pipeline.py:510-516)."""
+    lib = _l.load()
+    assert eps.is_contiguous() and eps.shape[0] % 2 == 0
+    n = eps.shape[0] // 2
+    if out is None:
+        out = torch.empty((n, *eps.shape[1:]), device=eps.device, dtype=eps.dtype)
+    ratio = cfg_rescale_ratio(eps.view(2 * n, eps.shape[1], -1) if eps.dim() > 2 else eps.view(2 * n, 1, -1),
+                              guidance_scale) if guidance_rescale > 0.0 else None
+    rc = lib.pcdm_cfg_combine(_l.ptr(eps), C.c_int(_any_dt(eps)), _l.ptr(out), C.c_int(_any_dt(out)), C.c_int(n),
+                              C.c_longlong(eps[0].numel()), C.c_float(guidance_scale), _l.ptr(ratio),
+                              C.c_float(guidance_rescale), _stream(eps))
+    _l.check(rc)
+    return out
+
+
+def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None,
+                  ratio=None, guidance_rescale=0.0):
+    """eps_rows: [2n, H, W, ld] UNet output rows; latents: [n, 4, H, W] fp32 (in place); x9: [2n, H, W, ld9].
+    ratio: [n] fp32 from cfg_rescale_ratio (guidance_rescale > 0) or None."""
     lib = _l.load()
     n = latents.shape[0]
     HW = latents.shape[2] * latents.shape[3]
@@ -332,7 +374,8 @@ def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scal
     rc = lib.pcdm_cfg_ddim_step(_l.ptr(eps_rows), C.c_int(_any_dt(eps_rows)), C.c_longlong(eps_rows.shape[-1]),
                                 _l.ptr(latents), _l.ptr(x9), C.c_int(_any_dt(x9)), C.c_longlong(x9.shape[-1]),
                                 _l.ptr(coef_table), _l.ptr(step_counter), C.c_float(guidance_scale), C.c_int(n),
-                                C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _stream(latents))
+                                C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _l.ptr(ratio), C.c_float(guidance_rescale),
+                                _stream(latents))
     _l.check(rc)
 
 
@@ -364,7 +407,8 @@ def ddim_step(model_output, sample, coefs, out=None):
 UNIPC_ROW = 16  # floats per step in the UniPC coefficient table (include/pcdm_b200.h)
 
 
-def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None,
+                   ratio=None, guidance_rescale=0.0):
     """eps_rows: [2n, H, W, ld] UNet output rows; state: [4, n, 4, H, W] fp32 {sample, last_sample, m0, m1} (in
     place); x9: [2n, H, W, ld9]; coef_table: [steps, 16] fp32 device."""
     lib = _l.load()
@@ -376,7 +420,8 @@ def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale
     rc = lib.pcdm_cfg_unipc_step(_l.ptr(eps_rows), C.c_int(_any_dt(eps_rows)), C.c_longlong(eps_rows.shape[-1]),
                                  _l.ptr(state), _l.ptr(x9), C.c_int(_any_dt(x9)), C.c_longlong(x9.shape[-1]),
                                  _l.ptr(coef_table), _l.ptr(step_counter), C.c_float(guidance_scale), C.c_int(n),
-                                 C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _stream(state))
+                                 C.c_int(HW), _l.ptr(t_table), _l.ptr(t_cur), _l.ptr(ratio), C.c_float(guidance_rescale),
+                                 _stream(state))
     _l.check(rc)
 
 

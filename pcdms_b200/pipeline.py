@@ -133,8 +133,6 @@ class _B200DenoisingPipeline:
     def _common_checks(self, cross_attention_kwargs, guidance_rescale, guidance_scale, height, width, callback_steps):
         if cross_attention_kwargs is not None:
             raise NotImplementedError("cross_attention_kwargs are not supported")
-        if guidance_rescale and guidance_rescale > 0.0:
-            raise NotImplementedError("guidance_rescale > 0 is disabled by the reference drivers and not implemented")
         self.check_inputs(height, width, callback_steps)
         if not guidance_scale > 1.0:
             raise NotImplementedError("guidance_scale <= 1: the reference's non-CFG branch is inconsistent "
@@ -149,7 +147,7 @@ class _B200DenoisingPipeline:
         return latents.to(device=dev, dtype=torch.float32) * self.scheduler.init_noise_sigma
 
     def _denoise(self, latents, extra, pose_cond, feature_f, class_labels, guidance_scale, num_inference_steps, eta,
-                 generator, callback, callback_steps):
+                 generator, callback, callback_steps, guidance_rescale=0.0):
         """latents [n,4,h,w] fp32; extra [2n,Ce,h,w] (the non-latent input channels of both CFG halves); pose_cond
         [2n,320,h,w] or None; feature_f [2n,S,D]; class_labels [2n,1,D] or None."""
         fast = (isinstance(self.unet, B200UNet2DConditionModel)
@@ -158,11 +156,12 @@ class _B200DenoisingPipeline:
                 and all(isinstance(a.processor, B200AttnProcessor) for a in self.unet._attn.values()))
         if fast:
             st = self.prepare_fused(latents.contiguous().clone(), extra, pose_cond, feature_f, class_labels,
-                                    float(guidance_scale), num_inference_steps)
+                                    float(guidance_scale), num_inference_steps, float(guidance_rescale or 0.0))
             self.replay_fused(st)
             return st.latents.clone()
         return self._denoise_generic(latents, extra, pose_cond, feature_f, class_labels, guidance_scale,
-                                     self.scheduler.timesteps, eta, generator, callback, callback_steps)
+                                     self.scheduler.timesteps, eta, generator, callback, callback_steps,
+                                     float(guidance_rescale or 0.0))
 
     def _finish(self, latents, output_type, return_dict, generator=None):
         dt = self.unet.dtype
@@ -191,7 +190,7 @@ class _B200DenoisingPipeline:
     # ------------------------------------------------------------------------------------------------------------
     # fused engine
     # ------------------------------------------------------------------------------------------------------------
-    def prepare_fused(self, latents, extra, pose_cond, feature_f, class_labels, guidance, steps):
+    def prepare_fused(self, latents, extra, pose_cond, feature_f, class_labels, guidance, steps, rescale=0.0):
         """Per-call set-up of the fused loop: lays the conditioning out in the graph's static buffers (NHWC, 16-bit),
         projects the cross-attention K/V once, uploads the step tables and (re)captures the one-step CUDA graph when
         the shapes / guidance / step count changed.  Returns the state object `replay_fused` consumes."""
@@ -216,7 +215,8 @@ class _B200DenoisingPipeline:
                 cls=torch.empty((B, class_labels.shape[-1]), device=dev, dtype=dt) if has_cls else None,
                 t_cur=torch.zeros(1, device=dev, dtype=torch.float32),
                 counter=torch.zeros(2, device=dev, dtype=torch.int32),
-                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None, wver=None,
+                guidance=None, graph=None, kv=None, coef=None, t_table=None, steps=None, wver=None, rescale=0.0,
+                ratio=torch.ones(n, device=dev, dtype=torch.float32),
                 launches_per_step=0)
             self._graphs[key] = st
         x_nchw = torch.cat([torch.cat([latents, latents], dim=0), extra.to(dev, torch.float32)], dim=1).contiguous()
@@ -231,8 +231,9 @@ class _B200DenoisingPipeline:
         coef = sch.coefficient_table(dev)
         t_table = torch.cat([sch.timesteps.to(dev, torch.float32), torch.zeros(1, device=dev)]).contiguous()
         wver = getattr(unet, "_weights_version", 0)
-        rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps or st.wver != wver)
-        st.guidance, st.steps, st.wver = guidance, steps, wver
+        rebuild = (st.graph is None or first or st.guidance != guidance or st.steps != steps or st.wver != wver
+                   or st.rescale != rescale)
+        st.guidance, st.steps, st.wver, st.rescale = guidance, steps, wver, rescale
         if st.coef is None or st.coef.shape != coef.shape:
             st.coef, st.t_table = coef, t_table
             rebuild = True
@@ -259,10 +260,15 @@ class _B200DenoisingPipeline:
 
     def _one_step(self, st):
         eps_rows = self.unet.forward_nhwc(st.x9, st.t_cur, st.kv, st.cls, st.pose)
+        ratio = None
+        if st.rescale > 0.0:   # reference rescale_noise_cfg (:52-63, :514-516): per-sample std ratio, one small launch
+            ratio = ops.cfg_rescale_ratio(eps_rows, st.guidance, out=st.ratio, nhwc_channels=4)
         if st.unipc:
-            ops.cfg_unipc_step(eps_rows, st.state, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
+            ops.cfg_unipc_step(eps_rows, st.state, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur,
+                               ratio=ratio, guidance_rescale=st.rescale)
         else:
-            ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur)
+            ops.cfg_ddim_step(eps_rows, st.latents, st.x9, st.coef, st.counter, st.guidance, st.t_table, st.t_cur,
+                              ratio=ratio, guidance_rescale=st.rescale)
 
     def _reset_state(self, st):
         st.x9.copy_(st.x9_init)
@@ -283,8 +289,9 @@ class _B200DenoisingPipeline:
                 self._one_step(st)
 
     def _denoise_generic(self, latents, extra, pose_cond, feature_f, class_labels, guidance_scale, timesteps, eta,
-                         generator, callback, callback_steps):
-        """Protocol loop (reference :496-525) for foreign unet / scheduler objects."""
+                         generator, callback, callback_steps, guidance_rescale=0.0):
+        """Protocol loop (reference :496-525) for foreign unet / scheduler objects, callbacks and custom attention
+        processors.  The CFG combine (+ rescale) is the pcdm_cfg_combine kernel — no eager-torch arithmetic here."""
         dt = self.unet.dtype
         step_kw = self.prepare_extra_step_kwargs(generator, eta)
         extra = extra.to(latents.device, dt)
@@ -299,8 +306,7 @@ class _B200DenoisingPipeline:
             x = self.scheduler.scale_model_input(x, t)
             xin = torch.cat([x, extra], dim=1).to(dt)
             eps = self.unet(xin, t, encoder_hidden_states=feature_f, return_dict=False, **kw)[0]
-            eu, ec = eps.chunk(2)
-            eps = eu + guidance_scale * (ec - eu)
+            eps = ops.cfg_combine(eps.contiguous(), float(guidance_scale), guidance_rescale)       # :510-516
             latents = self.scheduler.step(eps, t, latents, **step_kw, return_dict=False)[0]
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
@@ -350,7 +356,7 @@ class B200Stage2InpaintPipeline(_B200DenoisingPipeline):
         latents = self._initial_latents(latents, n, h, w, generator)
         extra = torch.cat([mask, masked_latents], dim=1)
         latents = self._denoise(latents, extra, pose_cond, feature_f, prior_embed, guidance_scale,
-                                num_inference_steps, eta, generator, callback, callback_steps)
+                                num_inference_steps, eta, generator, callback, callback_steps, guidance_rescale)
         return self._finish(latents, output_type, return_dict)
 
 
@@ -394,7 +400,7 @@ class B200SimpleStage2InpaintPipeline(_B200DenoisingPipeline):
         latents = self._initial_latents(latents, n, h, w, generator)
         extra = torch.cat([mask, masked_latents], dim=1)
         latents = self._denoise(latents, extra, pose_cond, feature_f, None, guidance_scale, num_inference_steps, eta,
-                                generator, callback, callback_steps)
+                                generator, callback, callback_steps, guidance_rescale)
         return self._finish(latents, output_type, return_dict)
 
 
@@ -440,7 +446,7 @@ class B200PCDMsPipeline(_B200DenoisingPipeline):
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         latents = self._initial_latents(latents, n, h, w, generator)
         latents = self._denoise(latents, extra, pose_cond.contiguous(), feature_f, None, guidance_scale,
-                                num_inference_steps, eta, generator, callback, callback_steps)
+                                num_inference_steps, eta, generator, callback, callback_steps, guidance_rescale)
         return self._finish(latents, output_type, return_dict, generator)
 
 
@@ -473,5 +479,5 @@ class B200Stage3RefinedPipeline(_B200DenoisingPipeline):
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         latents = self._initial_latents(latents, n, h, w, generator)
         latents = self._denoise(latents, extra, None, feature_f, None, guidance_scale, num_inference_steps, eta,
-                                generator, callback, callback_steps)
+                                generator, callback, callback_steps, guidance_rescale)
         return self._finish(latents, output_type, return_dict)

@@ -118,12 +118,42 @@ def upsample_nearest2x(x, out=None):
     return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
 
 
-def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+def _cfg(e, n, guidance_scale, ratio, guidance_rescale):
+    """e: [2n, C, ...] fp32 -> CFG combine (+ the reference's rescale with the given per-sample std ratio)."""
+    cfg = e[:n] + guidance_scale * (e[n:] - e[:n])
+    if ratio is not None:
+        r = ratio.view(-1, *([1] * (cfg.dim() - 1)))
+        cfg = guidance_rescale * (cfg * r) + (1 - guidance_rescale) * cfg
+    return cfg
+
+
+def cfg_rescale_ratio(eps, guidance_scale, out=None, *, nhwc_channels=None):
+    e = eps.float()
+    if nhwc_channels is not None:
+        e = e[..., :nhwc_channels]
+    n = e.shape[0] // 2
+    cfg = e[:n] + guidance_scale * (e[n:] - e[:n])
+    dims = list(range(1, e.dim()))
+    ratio = e[n:].std(dim=dims) / cfg.std(dim=dims)
+    if out is not None:
+        out.copy_(ratio)
+        return out
+    return ratio
+
+
+def cfg_combine(eps, guidance_scale, guidance_rescale=0.0, out=None):
+    n = eps.shape[0] // 2
+    ratio = cfg_rescale_ratio(eps, guidance_scale) if guidance_rescale > 0.0 else None
+    return _cfg(eps.float(), n, guidance_scale, ratio, guidance_rescale).to(eps.dtype)
+
+
+def cfg_ddim_step(eps_rows, latents, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None,
+                  ratio=None, guidance_rescale=0.0):
     n = latents.shape[0]
     step = int(step_counter[0])
     c = coef_table[step]
     e = eps_rows[..., :4].float().permute(0, 3, 1, 2)
-    e = e[:n] + guidance_scale * (e[n:] - e[:n])
+    e = _cfg(e, n, guidance_scale, ratio, guidance_rescale)
     x0 = (latents - c[1] * e) * c[0]
     latents.copy_(c[2] * x0 + c[3] * e)
     x9[..., :4] = torch.cat([latents, latents]).permute(0, 2, 3, 1).to(x9.dtype)
@@ -159,11 +189,12 @@ def _unipc_update(r, e, x, last, ma, mb):
     return xn, xc, mt, ma
 
 
-def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None):
+def cfg_unipc_step(eps_rows, state, x9, coef_table, step_counter, guidance_scale, t_table=None, t_cur=None,
+                   ratio=None, guidance_rescale=0.0):
     n = state.shape[1]
     step = int(step_counter[0])
     e = eps_rows[..., :4].float().permute(0, 3, 1, 2)
-    e = e[:n] + guidance_scale * (e[n:] - e[:n])
+    e = _cfg(e, n, guidance_scale, ratio, guidance_rescale)
     xn, xc, mt, ma_old = _unipc_update(coef_table[step].tolist(), e, state[0], state[1], state[2], state[3])
     state[3].copy_(ma_old)
     state[2].copy_(mt)
@@ -242,7 +273,7 @@ def require_cuda(t, what):
 
 
 _NAMES = ["ensure_workspace", "require_cuda", "gemm", "ln_gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
-          "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "add_noise", "ddim_step", "cfg_unipc_step",
+          "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "cfg_rescale_ratio", "cfg_combine", "add_noise", "ddim_step", "cfg_unipc_step",
           "unipc_step", "softmax_rows", "gaussian_sample", "cfg_unclip_step", "unclip_step"]
 
 

@@ -233,3 +233,31 @@ def test_default_workspace_is_per_device_and_never_replaced():
         c = ops.ensure_workspace(torch.device("cuda", 0), nbytes=1)
         assert a is b is c and len(made) == 1 and made[0][0] == ops.WORKSPACE_BYTES
         assert ops.ensure_workspace("cpu") is None
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_guidance_rescale_matches_reference_formula(fast):
+    """rescale_noise_cfg (reference stage2_inpaint_pipeline.py:52-63, applied at :514-516): through the fused engine
+    (per-sample std ratio kernel + the fused step) and through the generic protocol loop (pcdm_cfg_combine)."""
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg)
+    pin = make_inputs(cfg, n=2, h=8, w=16, s_kv=6)
+    cond = prepare_conditioning(s_img_proj_f=pin["s_img_proj_f"], pred_t_img_embed=pin["pred_t_img_embed"],
+                                st_pose_f=pin["st_pose_f"], masked_latents=pin["masked_latents"], height=pin["height"],
+                                width=pin["width"], num_images_per_prompt=2, guidance_scale=2.0)
+    want = denoise_loop(o, OracleDDIMScheduler(), latents=pin["latents"], cond=cond, num_inference_steps=4,
+                        guidance_scale=2.0, guidance_rescale=0.7)
+    plain = denoise_loop(o, OracleDDIMScheduler(), latents=pin["latents"], cond=cond, num_inference_steps=4,
+                         guidance_scale=2.0)
+    assert (want - plain).abs().max() > 1e-2      # the rescale does something
+    pipe = B200Stage2InpaintPipeline(vae=None, unet=m, scheduler=B200DDIMScheduler())
+    pipe.use_cuda_graph = False
+    calls = []
+    with mock_ops.patched():
+        got = pipe(height=pin["height"], width=pin["width"], num_inference_steps=4, guidance_scale=2.0,
+                   guidance_rescale=0.7, num_images_per_prompt=2, latents=pin["latents"], output_type="latent",
+                   s_img_proj_f=pin["s_img_proj_f"], st_pose_f=pin["st_pose_f"],
+                   pred_t_img_embed=pin["pred_t_img_embed"], masked_latents=pin["masked_latents"],
+                   callback=None if fast else (lambda i, t, x: calls.append(i))).images
+    assert fast or calls == [0, 1, 2, 3]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-5)

@@ -285,6 +285,47 @@ def test_fused_step_and_schedulers_match_oracle(ops):
     torch.testing.assert_close(out.cpu(), ddpm_add_noise(s, e, ts), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_cfg_combine_and_rescale(ops, dt):
+    """a11: e_u + g (e_c - e_u) and the reference's rescale_noise_cfg (stage2_inpaint_pipeline.py:52-63) as kernels —
+    stand-alone (the generic protocol loop) and inside the fused DDIM step."""
+    from oracle.pipeline import cfg_combine, rescale_noise_cfg
+    from oracle.schedulers import OracleDDIMScheduler
+    from pcdms_b200.scheduler import B200DDIMScheduler
+    n, h, w = 3, 16, 32
+    g = torch.Generator().manual_seed(5)
+    eps = (torch.randn(2 * n, 4, h, w, generator=g) * torch.tensor([0.5, 1.0, 2.0, 1.0, 0.7, 3.0]).view(-1, 1, 1, 1)).to(dt)
+    ref = cfg_combine(eps.float(), 2.0)
+    ref_r = rescale_noise_cfg(ref, eps.float()[n:], guidance_rescale=0.7)
+    tol_ = dict(rtol=1e-5, atol=1e-5) if dt == torch.float32 else tol(dt)
+    torch.testing.assert_close(ops.cfg_combine(eps.cuda(), 2.0).float().cpu(), ref.to(dt).float(), **tol_)
+    out = ops.cfg_combine(eps.cuda(), 2.0, 0.7)
+    assert out.dtype == dt and out.shape == (n, 4, h, w)
+    torch.testing.assert_close(out.float().cpu(), ref_r, **tol_)
+    want_ratio = eps.float()[n:].std(dim=(1, 2, 3)) / ref.std(dim=(1, 2, 3))
+    torch.testing.assert_close(ops.cfg_rescale_ratio(eps.cuda(), 2.0).cpu(), want_ratio, rtol=1e-5, atol=1e-6)
+    assert torch.equal(ops.cfg_rescale_ratio(eps.cuda(), 2.0), ops.cfg_rescale_ratio(eps.cuda(), 2.0))   # reproducible
+    if dt != torch.float32:
+        return
+    # fused: NHWC fp32 rows with a leading dimension, ratio read per sample inside the step kernel
+    rows = torch.zeros(2 * n, h, w, 32)
+    rows[..., :4] = eps.permute(0, 2, 3, 1)
+    rows[..., 4:] = 99.0                      # padding columns must not enter the statistics
+    ratio = ops.cfg_rescale_ratio(rows.cuda(), 2.0, nhwc_channels=4)
+    torch.testing.assert_close(ratio.cpu(), want_ratio, rtol=1e-5, atol=1e-6)
+    sch, osch = B200DDIMScheduler(), OracleDDIMScheduler()
+    sch.set_timesteps(10)
+    osch.set_timesteps(10)
+    lat = torch.randn(n, 4, h, w, generator=g)
+    lat_d = lat.clone().cuda()
+    x9 = torch.zeros(2 * n, h, w, 64, dtype=torch.float16, device="cuda")
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ops.cfg_ddim_step(rows.cuda(), lat_d, x9, sch.coefficient_table("cuda"), counter, 2.0, ratio=ratio,
+                      guidance_rescale=0.7)
+    want = osch.step(ref_r, osch.timesteps[0], lat, return_dict=False)[0]
+    torch.testing.assert_close(lat_d.cpu(), want, rtol=1e-5, atol=1e-5)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # VAE / conditioning front-end shapes (SURVEY.md §8f): rows wider than a tile, bottom/right-padded stride 2,
 # SiLU / GELU epilogues, fp32 score softmax
