@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCDM_ABI_VERSION 2
+#define PCDM_ABI_VERSION 3
 
 #define PCDM_ERR_INVALID (-1)     /* bad argument */
 #define PCDM_ERR_CUDA (-2)        /* CUDA runtime / driver failure */
@@ -63,6 +63,24 @@ typedef struct pcdm_ext {
                               * that was given it.  pcdm_gemm_workspace_bytes() bounds what a problem can use; 64 MiB
                               * covers every BASELINE configuration.  16-byte aligned. */
   long long workspace_bytes;
+  /* ---- LayerNorm folded around GEMMs (torch.nn.LayerNorm norm1/norm2/norm3 of diffusers' BasicTransformerBlock,
+   *      SURVEY.md §8a a8): no separate normalisation pass over the hidden states.
+   * producer — the GEMM whose 16-bit output rows the LayerNorm normalises (proj_in, attn*.to_out + residual):
+   *   row_stats != NULL: the epilogue also writes, per output row, (sum, sum of squares) of the values it stores, one
+   *   fp32 pair per column slice: row_stats[slot][m][2], slot < row_stats_parts.  row_stats_parts is an OUTPUT (set at
+   *   call time: 2 per N tile); the buffer must hold row_stats_cap >= 2 * ceil(N / 64) slots of M pairs.
+   * consumer — the GEMM that multiplies the normalised rows (to_q/k/v, ff.net.0.proj), given the RAW rows as A:
+   *   ln_stats = the producer's buffer, ln_parts = its row_stats_parts, W pre-scaled by gamma (W'[n,k] = W[n,k] g[k]),
+   *   ln_colsum[n] = sum_k W'[n,k] (fp32, of the 16-bit-rounded W'), bias[n] = sum_k W[n,k] beta[k] (+ the layer's bias):
+   *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_colsum[n]) + bias[n],  mean / rstd over the K input columns
+   *   (biased variance, ln_eps inside the square root: torch.nn.LayerNorm).  Works with PCDM_FLAG_GEGLU. ---- */
+  float* row_stats;
+  int row_stats_cap;
+  int row_stats_parts;
+  const float* ln_stats;
+  int ln_parts;
+  const float* ln_colsum;
+  float ln_eps;
 } pcdm_ext;
 
 int pcdm_abi_version(void);
@@ -81,7 +99,7 @@ long long pcdm_gemm_workspace_bytes(int M, int N);
 int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w, void* out,
               long long ldo, const float* bias, const float* rowvec, long long ld_rowvec, int rows_per_image,
               const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
-              const pcdm_ext* ext, void* stream);
+              pcdm_ext* ext, void* stream);
 
 /* torch.nn.LayerNorm(K, eps) followed by torch.nn.Linear, as one call:
  *   out = act( LN(x[M, K]; gamma, beta, eps) . W[N, K]^T + bias + rowvec + residual )
@@ -93,7 +111,7 @@ int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int 
 int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
                  const void* w, void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
                  int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags,
-                 const pcdm_ext* ext, void* stream);
+                 pcdm_ext* ext, void* stream);
 
 /* torch.nn.Conv2d(Cin, Cout, 3, stride, padding=1) on NHWC activations, implicit GEMM (no im2col buffer).
  * Replaces conv_in, conv1/conv2 of ResnetBlock2D, Downsample2D.conv (stride 2), Upsample2D.conv and conv_out
@@ -105,7 +123,7 @@ int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* 
  *   of the VAE encoder's Downsample2D (diffusers: F.pad(x, (0, 1, 0, 1)) then Conv2d(stride 2, padding 0)). */
 int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                  long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride,
-                 int dtype, int flags, int bn, const pcdm_ext* ext, void* stream);
+                 int dtype, int flags, int bn, pcdm_ext* ext, void* stream);
 
 /* torch.nn.GroupNorm(groups, C, eps) (+ SiLU with PCDM_FLAG_SILU) over NHWC x = [x1 | x2] (x2 may be NULL; x1 then has
  * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out
@@ -122,6 +140,10 @@ int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float*
 /* torch.nn.LayerNorm(C, eps) over rows; replaces norm1/norm2/norm3 of BasicTransformerBlock. */
 int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
                    float eps, int M, int C, int dtype, void* stream);
+
+/* Per-row (sum, sum of squares) of x[M, C] (16-bit; ldx in elements) as stats[M][2] fp32: one statistics slot in the
+ * layout pcdm_ext.ln_stats consumes (ln_parts = 1), for rows that did not come out of a pcdm_gemm epilogue. */
+int pcdm_row_stats(const void* x, long long ldx, float* stats, int M, int C, int dtype, void* stream);
 
 /* softmax(Q K^T * scale) V per head, head_dim 64, no mask.  Replaces xformers memory_efficient_attention /
  * F.scaled_dot_product_attention behind diffusers' attention processors (stage2_batchtest_inpaint_model.py:133;

@@ -63,6 +63,13 @@ struct IGemmParams {
   int geglu;
   int out_f32;
   int silu;        // activation: 0 none, 1 SiLU, 2 GELU (erf)
+  // ---- LayerNorm around the GEMM (16-bit output paths; see pcdm_ext in include/pcdm_b200.h) ----
+  float2* stats_out;        // producer: per-row (sum, sum of squares) of the outputs, one slot per (n-tile, column-half):
+                            // [2 * n_tiles][M]; the LayerNorm statistics of the NEXT op without another pass over the rows
+  const float2* ln_stats;   // consumer: LayerNorm folded into this GEMM — W was pre-scaled by gamma, the rows arrive raw,
+  int ln_parts;             //   out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]   (bias[n] carries W . beta too)
+  const float* ln_colsum;   //   with (mean, rstd) from the producer's ln_parts partial sums over the K input columns
+  float ln_eps, ln_inv_k;
 };
 
 template <int BN, int CG>
@@ -85,6 +92,24 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 u) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+// (mean, rstd) of output row m of the PRODUCING GEMM from its per-(n-tile, half) partial sums, as the packed scalars
+// the epilogue needs: rstd and -rstd * mean.  Fixed summation order (bit-reproducible).
+__device__ __forceinline__ void ln_row_scalars(const IGemmParams& p, long long m, bool valid, float2& rstd2, float2& nm2) {
+  float sum = 0.f, sq = 0.f;
+  if (valid) {
+    for (int i = 0; i < p.ln_parts; ++i) {
+      const float2 t = __ldg(p.ln_stats + (long long)i * p.M + m);
+      sum += t.x;
+      sq += t.y;
+    }
+  }
+  const float mean = sum * p.ln_inv_k;
+  const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  rstd2 = make_float2(rstd, rstd);
+  nm2 = make_float2(-rstd * mean, -rstd * mean);
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
@@ -364,6 +389,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
         //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
         const bool use_res = p.has_res && !IG_DBG(p, 2);
+        float2 ln_rstd2 = make_float2(1.f, 1.f), ln_nm2 = make_float2(0.f, 0.f);
+        if (p.ln_stats) ln_row_scalars(p, m, valid, ln_rstd2, ln_nm2);   // global loads overlap the tile's MMAs
+        float2 st_sum = make_float2(0.f, 0.f), st_sq = make_float2(0.f, 0.f);
         if (use_res) {
           if (lane == 0) {
             bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
@@ -393,7 +421,15 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           float2 v[16];   // column pairs, packed fp32 (FFMA2 path)
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          if (p.bias && !IG_DBG(p, 4)) {
+          if (p.ln_stats) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {   // rstd * acc + (-rstd * mean) * colsum[n] + bias'[n]
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j / 2] = __ffma2_rn(ln_rstd2, v[j / 2], __ffma2_rn(ln_nm2, make_float2(cs.x, cs.y), make_float2(b.x, b.y)));
+              v[j / 2 + 1] = __ffma2_rn(ln_rstd2, v[j / 2 + 1], __ffma2_rn(ln_nm2, make_float2(cs.z, cs.w), make_float2(b.z, b.w)));
+            }
+          } else if (p.bias && !IG_DBG(p, 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
@@ -428,6 +464,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = gelu_erf2_f(v[j]);
           }
+          if (p.stats_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              st_sum = __fadd2_rn(st_sum, v[j]);
+              st_sq = __ffma2_rn(v[j], v[j], st_sq);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -445,8 +488,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           ++cnt;
         }
+        if (p.stats_out && valid)   // one slot per (n-tile, column half); a warp without chunks still writes its zeros
+          p.stats_out[(long long)(n_blk * 2 + half) * p.M + m] = make_float2(st_sum.x + st_sum.y, st_sq.x + st_sq.y);
       } else {
         // ---- GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate) ----
+        float2 ln_rstd2 = make_float2(1.f, 1.f), ln_nm2 = make_float2(0.f, 0.f);
+        if (p.ln_stats) ln_row_scalars(p, m, valid, ln_rstd2, ln_nm2);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -470,10 +517,23 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
               bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
             }
-            const float2 h0 = __fadd2_rn(make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), make_float2(bh.x, bh.y));
-            const float2 h1 = __fadd2_rn(make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
-            const float2 g0 = __fadd2_rn(make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
-            const float2 g1 = __fadd2_rn(make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
+            float2 h0 = make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1]));
+            float2 h1 = make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3]));
+            float2 g0 = make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1]));
+            float2 g1 = make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3]));
+            if (p.ln_stats) {   // LayerNorm folded into the projection: rstd * acc + (-rstd * mean) * colsum + bias'
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+              const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 32 + j));
+              h0 = __ffma2_rn(ln_rstd2, h0, __ffma2_rn(ln_nm2, make_float2(sh.x, sh.y), make_float2(bh.x, bh.y)));
+              h1 = __ffma2_rn(ln_rstd2, h1, __ffma2_rn(ln_nm2, make_float2(sh.z, sh.w), make_float2(bh.z, bh.w)));
+              g0 = __ffma2_rn(ln_rstd2, g0, __ffma2_rn(ln_nm2, make_float2(sg.x, sg.y), make_float2(bg.x, bg.y)));
+              g1 = __ffma2_rn(ln_rstd2, g1, __ffma2_rn(ln_nm2, make_float2(sg.z, sg.w), make_float2(bg.z, bg.w)));
+            } else {
+              h0 = __fadd2_rn(h0, make_float2(bh.x, bh.y));
+              h1 = __fadd2_rn(h1, make_float2(bh.z, bh.w));
+              g0 = __fadd2_rn(g0, make_float2(bg.x, bg.y));
+              g1 = __fadd2_rn(g1, make_float2(bg.z, bg.w));
+            }
             // gate activation: GELU (GEGLU, diffusers FeedForward) or SiLU (SwiGLU, DINOv2's FFN) — warp-uniform
             const float2 v0 = __fmul2_rn(h0, p.silu == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
             const float2 v1 = __fmul2_rn(h1, p.silu == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
@@ -636,9 +696,16 @@ struct ExtArgs {   // what the caller's pcdm_ext carries (all optional)
   int force_cg = 0;          // 0 = auto, 1 / 2 = force
   void* ws = nullptr;        // fp32 scratch for split-K partials; without it the launch never splits K
   long long ws_bytes = 0;
+  float* row_stats = nullptr;   // producer side of a folded LayerNorm
+  int row_stats_cap = 0;
+  const float* ln_stats = nullptr;   // consumer side
+  int ln_parts = 0;
+  const float* ln_colsum = nullptr;
+  float ln_eps = 0.f;
+  pcdm_ext* raw = nullptr;      // for the output field row_stats_parts
 };
 
-static int read_ext(const pcdm_ext* ext, ExtArgs* e) {
+static int read_ext(pcdm_ext* ext, ExtArgs* e) {
   e->force_cg = g_tune.force_cg;
   if (!ext) return 0;
   if (ext->size < (int)sizeof(pcdm_ext)) return set_error(PCDM_ERR_INVALID, "pcdm_ext: size field does not match this library's struct");
@@ -649,6 +716,23 @@ static int read_ext(const pcdm_ext* ext, ExtArgs* e) {
   if (ext->force_cta_group) e->force_cg = ext->force_cta_group;
   e->ws = ext->workspace;
   e->ws_bytes = ext->workspace_bytes;
+  ext->row_stats_parts = 0;
+  if (ext->row_stats) {
+    if (ext->row_stats_cap <= 0 || (reinterpret_cast<uintptr_t>(ext->row_stats) & 7))
+      return set_error(PCDM_ERR_INVALID, "pcdm_ext: row_stats needs row_stats_cap > 0 and an 8-byte aligned buffer");
+    e->row_stats = ext->row_stats;
+    e->row_stats_cap = ext->row_stats_cap;
+  }
+  if (ext->ln_stats) {
+    if (ext->ln_parts <= 0 || !ext->ln_colsum || !(ext->ln_eps >= 0.f) ||
+        ((reinterpret_cast<uintptr_t>(ext->ln_stats) & 7) | (reinterpret_cast<uintptr_t>(ext->ln_colsum) & 15)))
+      return set_error(PCDM_ERR_INVALID, "pcdm_ext: ln_stats needs ln_parts > 0, ln_colsum (16-byte aligned) and ln_eps >= 0");
+    e->ln_stats = ext->ln_stats;
+    e->ln_parts = ext->ln_parts;
+    e->ln_colsum = ext->ln_colsum;
+    e->ln_eps = ext->ln_eps;
+  }
+  e->raw = ext;
   return 0;
 }
 
@@ -675,7 +759,18 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   //      otherwise idle SMs into fp32 partials, then one small finishing kernel applies the epilogue ----
   EpiArgs epi = {p.bias, p.rowvec, p.ld_rowvec, p.hw, residual, ldr, p.out, p.ldo, p.silu};
   bool split = false;
-  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0) {   // K >= 4096: below, one launch wins
+  if (ext.ln_stats) {
+    if (p.out_f32 || !p.bias || p.mode != 0)
+      return set_error(PCDM_ERR_UNSUPPORTED, "gemm: a folded LayerNorm needs a 16-bit-output GEMM with the bias vector");
+    p.ln_stats = reinterpret_cast<const float2*>(ext.ln_stats);
+    p.ln_parts = ext.ln_parts;
+    p.ln_colsum = ext.ln_colsum;
+    p.ln_eps = ext.ln_eps;
+    p.ln_inv_k = 1.0f / (float)K;
+  }
+  if (ext.row_stats && (p.out_f32 || p.geglu))
+    return set_error(PCDM_ERR_UNSUPPORTED, "gemm: row statistics come with the plain 16-bit-output epilogue only");
+  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats) {   // K >= 4096: below, one launch wins
     const int sbn = (p.N % 160 == 0) ? 160 : 128;
     const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
     if (tiles * 2 <= num_sms()) {
@@ -722,6 +817,13 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     }
   }
   p.n_tiles = (p.N + bn - 1) / bn;
+  if (ext.row_stats) {
+    if (2 * p.n_tiles > ext.row_stats_cap)
+      return set_error(PCDM_ERR_INVALID, "gemm: row_stats_cap %d is below the %d slots this problem writes (2 * N / 64 always fits)",
+                       ext.row_stats_cap, 2 * p.n_tiles);
+    p.stats_out = reinterpret_cast<float2*>(ext.row_stats);
+    ext.raw->row_stats_parts = 2 * p.n_tiles;
+  }
   const int bbox = bn / cg;
   const int brows = p.N < bbox ? p.N : bbox;
   p.b_bytes = (uint32_t)brows * 128u;
@@ -772,7 +874,7 @@ using namespace pcdm;
 extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long lda2, int k1, const void* w,
                          void* out, long long ldo, const float* bias, const float* rowvec, long long ld_rowvec,
                          int rows_per_image, const void* residual, long long ldr, int M, int N, int K, int dtype, int flags, int bn,
-                         const pcdm_ext* ext_, void* stream_) {
+                         pcdm_ext* ext_, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ExtArgs ext;
   PCDM_CHECK(read_ext(ext_, &ext), "ext");
@@ -784,7 +886,7 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
   const bool geglu = flags & PCDM_FLAG_GEGLU;
   if (geglu && (N % 64)) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: GEGLU needs N % 64 == 0");
   if ((lda % 8) || (ldo % 8) || (residual && (ldr % 8))) return set_error(PCDM_ERR_UNSUPPORTED, "gemm: strides must be multiples of 8");
-  if (!a2 && bn == 0 && !(flags & PCDM_FLAG_NO_SKINNY)) {   // M <= 32 activation rows: a weight stream, not a 128-row tile problem (skinny.cu)
+  if (!a2 && bn == 0 && !(flags & PCDM_FLAG_NO_SKINNY) && !ext.ln_stats && !ext.row_stats) {   // M <= 32 activation rows: a weight stream, not a 128-row tile problem (skinny.cu)
     const int taken = skinny_gemm_try(a, lda, w, out, ldo, bias, rowvec, ld_rowvec, rows_per_image, residual, ldr, M, N,
                                       K, dtype, flags, stream, nullptr, nullptr, 0.f);
     if (taken != 0) return taken < 0 ? taken : 0;
@@ -820,7 +922,7 @@ extern "C" int pcdm_gemm(const void* a, long long lda, const void* a2, long long
 
 extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                             long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride, int dtype,
-                            int flags, int bn, const pcdm_ext* ext_, void* stream_) {
+                            int flags, int bn, pcdm_ext* ext_, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ExtArgs ext;
   PCDM_CHECK(read_ext(ext_, &ext), "ext");
@@ -888,7 +990,7 @@ extern "C" long long pcdm_gemm_workspace_bytes(int M, int N) {
 extern "C" int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* scratch,
                             const void* w, void* out, long long ldo, const float* bias, const float* rowvec,
                             long long ld_rowvec, int rows_per_image, const void* residual, long long ldr, int M, int N,
-                            int K, int dtype, int flags, const pcdm_ext* ext_, void* stream_) {
+                            int K, int dtype, int flags, pcdm_ext* ext_, void* stream_) {
   if (!x || !gamma || !beta || !w || !out) return set_error(PCDM_ERR_INVALID, "ln_gemm: null pointer");
   if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "ln_gemm: dtype must be 0 (f16) or 1 (bf16)");
   if (M <= 0 || N <= 0 || K <= 0) return set_error(PCDM_ERR_INVALID, "ln_gemm: empty problem");

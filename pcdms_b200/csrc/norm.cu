@@ -445,9 +445,52 @@ layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y
   }
 }
 
+// Per-row (sum, sum of squares) of a [M, C] 16-bit matrix: the statistics slot a GEMM with a folded LayerNorm consumes
+// (pcdm_ext.ln_stats with ln_parts = 1) when the rows were NOT produced by one of this library's GEMM epilogues (the
+// custom-attention-processor path).  One warp per row, fixed reduction order.
+template <int DT>
+__global__ void __launch_bounds__(256) row_stats_kernel(const void* __restrict__ x, long long ldx, float2* __restrict__ out,
+                                                        int M, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using T = typename TypeOf<DT>::T;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* xr = reinterpret_cast<const T*>(x) + row * ldx;
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+  for (int v = lane; v < C / 8; v += 32) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      s2 = __fadd2_rn(s2, f);
+      q2 = __ffma2_rn(f, f, q2);
+    }
+  }
+  const float s = warp_sum(s2.x + s2.y), q = warp_sum(q2.x + q2.y);
+  if (lane == 0) out[row] = make_float2(s, q);
+}
+
 }  // namespace pcdm
 
 using namespace pcdm;
+
+extern "C" int pcdm_row_stats(const void* x, long long ldx, float* stats, int M, int C, int dtype, void* stream_) {
+  if (!x || !stats) return set_error(PCDM_ERR_INVALID, "row_stats: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "row_stats: bad dtype");
+  if (M <= 0 || C <= 0) return set_error(PCDM_ERR_INVALID, "row_stats: empty problem");
+  if (C % 8 || (ldx % 8) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(PCDM_ERR_UNSUPPORTED, "row_stats: C % 8 == 0, ldx % 8 == 0, 8-byte aligned output");
+  const dim3 grid((M + 7) / 8), block(256);
+  if (dtype == DT_F16)
+    PCDM_CUDA(launch_kernel(row_stats_kernel<DT_F16>, grid, block, 0, (cudaStream_t)stream_, 1, x, ldx, reinterpret_cast<float2*>(stats), M, C));
+  else
+    PCDM_CUDA(launch_kernel(row_stats_kernel<DT_BF16>, grid, block, 0, (cudaStream_t)stream_, 1, x, ldx, reinterpret_cast<float2*>(stats), M, C));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
 
 static void gn_grid(int B, int HW, int C, int* PY_, int* pix_per_cta_, int* chunks_) {
   const int cvs = C / 8;

@@ -20,13 +20,15 @@ DT_F16, DT_BF16 = 0, 1
 FLAG_GEGLU, FLAG_OUT_F32, FLAG_SILU, FLAG_GELU, FLAG_PAD_BR, FLAG_W_STATIC = 1, 2, 4, 8, 16, 32
 FLAG_NO_SKINNY = 64                           # pcdm_gemm
 FLAG_GN_TWO_PASS, FLAG_GN_ONE_PASS = 64, 128  # pcdm_groupnorm
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Ext(C.Structure):
     """`pcdm_ext` of include/pcdm_b200.h: optional per-call extras of pcdm_gemm / pcdm_conv3x3 / pcdm_ln_gemm."""
     _fields_ = [("size", C.c_int), ("force_cta_group", C.c_int), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_longlong)]
+                ("workspace_bytes", C.c_longlong), ("row_stats", C.c_void_p), ("row_stats_cap", C.c_int),
+                ("row_stats_parts", C.c_int), ("ln_stats", C.c_void_p), ("ln_parts", C.c_int),
+                ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 class PcdmError(RuntimeError):

@@ -88,7 +88,27 @@ def _ext(t: torch.Tensor, force_cta_group: int = 0):
     ws = getattr(_tls, "ws", None)
     if ws is None or ws.device != t.device:
         ws = ensure_workspace(t.device)
-    return _l.Ext(C.sizeof(_l.Ext), int(force_cta_group), ws.data_ptr(), ws.numel())
+    e = _l.Ext()
+    e.size, e.force_cta_group, e.workspace, e.workspace_bytes = C.sizeof(_l.Ext), int(force_cta_group), ws.data_ptr(), ws.numel()
+    return e
+
+
+class RowStats:
+    """Per-row (sum, sum of squares) partials a producing GEMM wrote for the LayerNorm that follows it
+    (pcdm_ext.row_stats): `buf` [cap, M, 2] fp32, of which the first `parts` slots are live."""
+    __slots__ = ("buf", "parts")
+
+    def __init__(self, buf, parts):
+        self.buf, self.parts = buf, parts
+
+
+class FoldedLN:
+    """A LayerNorm folded into the GEMM that consumes it: the producer's RowStats, colsum[n] = sum_k W'[n, k] of the
+    gamma-scaled weight, eps.  The GEMM's `bias` must already carry W . beta."""
+    __slots__ = ("stats", "colsum", "eps")
+
+    def __init__(self, stats: RowStats, colsum, eps=1e-5):
+        self.stats, self.colsum, self.eps = stats, colsum, eps
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -111,8 +131,11 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # K1/K2
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True):
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True, row_stats=False,
+         ln: "FoldedLN | None" = None):
     """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual).
+    row_stats=True: also returns the RowStats of the output rows (-> `(out, stats)`), the LayerNorm statistics of the
+    next op for free.  ln=FoldedLN(...): `a` holds RAW rows, `w` is gamma-scaled, the LayerNorm happens in the epilogue.
     w_static: `w` holds model weights (not written by the kernel launched just before on this stream); pass False when
     `w` is an activation (the VAE's QK^T / PV products written as GEMMs)."""
     lib = _l.load()
@@ -133,12 +156,24 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
              (_l.FLAG_GELU if gelu else 0) | (_l.FLAG_W_STATIC if w_static else 0) |
              (0 if skinny else _l.FLAG_NO_SKINNY))
     ext = _ext(a, cta_group)
+    stats = None
+    if row_stats:
+        cap = 2 * ((N + 63) // 64)
+        stats = RowStats(torch.empty((cap, M, 2), device=a.device, dtype=torch.float32), 0)
+        ext.row_stats, ext.row_stats_cap = stats.buf.data_ptr(), cap
+    if ln is not None:
+        assert ln.stats.buf.shape[1] == M and ln.colsum.dtype == torch.float32 and ln.colsum.numel() == N and bias is not None
+        ext.ln_stats, ext.ln_parts = ln.stats.buf.data_ptr(), ln.stats.parts
+        ext.ln_colsum, ext.ln_eps = ln.colsum.data_ptr(), float(ln.eps)
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
         C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), C.c_int(rows_per_image), _l.ptr(residual), C.c_longlong(residual.stride(0) if residual is not None else 0),
         C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(_dt(a)), C.c_int(flags), C.c_int(bn), C.byref(ext), _stream(a))
     _l.check(rc)
+    if row_stats:
+        stats.parts = int(ext.row_stats_parts)
+        return out, stats
     return out
 
 
@@ -229,6 +264,18 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None,
                             _l.ptr(workspace), _stream(x1))
     _l.check(rc, kernels=2)
     return out
+
+
+def row_stats(x) -> RowStats:
+    """RowStats of x [M, C] computed by a stand-alone kernel (rows that did not come out of a gemm(row_stats=True))."""
+    lib = _l.load()
+    M, Cc = x.shape
+    assert x.stride(1) == 1
+    buf = torch.empty((1, M, 2), device=x.device, dtype=torch.float32)
+    rc = lib.pcdm_row_stats(_l.ptr(x), C.c_longlong(x.stride(0)), _l.ptr(buf), C.c_int(M), C.c_int(Cc), C.c_int(_dt(x)),
+                            _stream(x))
+    _l.check(rc)
+    return RowStats(buf, 1)
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out=None):

@@ -11,6 +11,8 @@ accumulation.  There is no PyTorch / CPU compute fallback: without the CUDA libr
 What is fused relative to the reference's op-by-op graph:
   * bias, time-embedding add, residual add, SiLU and GEGLU live in the GEMM/conv epilogues;
   * q/k/v of self-attention are one GEMM; all 22 resnet time_emb_proj linears are one GEMM per step;
+  * the three LayerNorms of every transformer block are folded into the GEMMs either side of them (statistics from the
+    producer's epilogue, gamma in the consumer's weights, normalisation in the consumer's epilogue): no LN launches;
   * the skip concat of the up blocks is never materialised (GroupNorm and the 1x1 shortcut read both sources);
   * cross-attention K/V depend only on encoder_hidden_states: computed once per conditioning, not once per step.
 """
@@ -119,9 +121,9 @@ class B200Attention:
         w = self._u._w
         B, S, C = hidden_states.shape
         x = hidden_states.reshape(B * S, C)
-        if encoder_hidden_states is None:
-            qkv = ops.gemm(x, w[f"{self.prefix}.to_qkv.weight"])
-            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, self.heads)
+        if encoder_hidden_states is None:   # processor protocol: already-normalised rows, the unfolded projections
+            q, k, v = (ops.gemm(x, w[f"{self.prefix}.{n}.weight"]) for n in ("to_q", "to_k", "to_v"))
+            a = ops.attention(q, k, v, B, self.heads)
         else:
             q = ops.gemm(x, w[f"{self.prefix}.to_q.weight"])
             ctx = encoder_hidden_states.reshape(-1, encoder_hidden_states.shape[-1])
@@ -509,14 +511,27 @@ class B200UNet2DConditionModel(WeightArenaMixin):
                 for a in ("attn1", "attn2"):
                     for n in ("to_q", "to_k", "to_v"):
                         w[f"{t}.{a}.{n}.weight"] = lin(f"{t}.{a}.{n}.weight")
-                w[f"{t}.attn1.to_qkv.weight"] = torch.cat(
-                    [w[f"{t}.attn1.to_q.weight"], w[f"{t}.attn1.to_k.weight"], w[f"{t}.attn1.to_v.weight"]]).contiguous()
                 w[f"{t}.attn2.to_kv.weight"] = torch.cat(
                     [w[f"{t}.attn2.to_k.weight"], w[f"{t}.attn2.to_v.weight"]]).contiguous()
+                # LayerNorm folded into the GEMM that consumes it (norm1 -> q/k/v, norm2 -> to_q, norm3 -> GEGLU proj):
+                # W' = W diag(gamma) (16-bit), colsum[n] = sum_k W'[n,k], bias'[n] = W[n,:] . beta (+ bias[n]);
+                # the GEMM runs on the RAW rows and the epilogue applies rstd * (acc - mean * colsum) + bias'
                 perm = ops.geglu_row_permutation(4 * c)
-                w[f"{t}.ff.net.0.proj.weight"] = sd[f"{t}.ff.net.0.proj.weight"].detach()[perm].to(
-                    device=dev, dtype=dt).contiguous()
-                w[f"{t}.ff.net.0.proj.bias"] = sd[f"{t}.ff.net.0.proj.bias"].detach().float()[perm].to(dev).contiguous()
+                for name, srcs, norm, bias_key, rows in (
+                        (f"{t}.attn1.to_qkv_ln", [f"{t}.attn1.to_q", f"{t}.attn1.to_k", f"{t}.attn1.to_v"], f"{t}.norm1", None, None),
+                        (f"{t}.attn2.to_q_ln", [f"{t}.attn2.to_q"], f"{t}.norm2", None, None),
+                        (f"{t}.ff.net.0.proj_ln", [f"{t}.ff.net.0.proj"], f"{t}.norm3", f"{t}.ff.net.0.proj.bias", perm)):
+                    W = torch.cat([sd[f"{k}.weight"].detach().to(dev, torch.float32) for k in srcs])
+                    gamma = sd[f"{norm}.weight"].detach().to(dev, torch.float32)
+                    beta = sd[f"{norm}.bias"].detach().to(dev, torch.float32)
+                    Wf = (W * gamma[None, :]).to(dt)
+                    cb = (W.double() @ beta.double()).float()
+                    if bias_key is not None:
+                        cb = cb + sd[bias_key].detach().to(dev, torch.float32)
+                    cs = Wf.double().sum(dim=1).float()
+                    if rows is not None:
+                        Wf, cb, cs = Wf[rows.to(Wf.device)], cb[rows.to(cb.device)], cs[rows.to(cs.device)]
+                    w[f"{name}.weight"], w[f"{name}.bias"], w[f"{name}.colsum"] = Wf.contiguous(), cb.contiguous(), cs.contiguous()
             elif op[0] in ("down", "up"):
                 w[f"{op[1]}.weight"], w[f"{op[1]}.bias"] = conv(f"{op[1]}.weight"), f32(f"{op[1]}.bias")
         self._loaded = True
@@ -692,28 +707,38 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         M = B * S
         t = f"{p}.transformer_blocks.0"
         hn = ops.groupnorm(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], 1e-6, silu=False)
-        h = ops.gemm(hn.view(M, C), w[f"{p}.proj_in.weight"], bias=w[f"{p}.proj_in.bias"])
+        # The three LayerNorms of the block never run as passes of their own: each GEMM that PRODUCES the hidden
+        # states also emits per-row (sum, sum of squares) from its epilogue, each GEMM that CONSUMES the normalised
+        # rows reads the raw rows with gamma folded into its weights and finishes the normalisation in its epilogue.
+        h, st = ops.gemm(hn.view(M, C), w[f"{p}.proj_in.weight"], bias=w[f"{p}.proj_in.bias"], row_stats=True)
         a1, a2 = self._attn[f"{t}.attn1"], self._attn[f"{t}.attn2"]
+
+        def folded(name, stats):
+            return dict(bias=w[f"{name}.bias"], ln=ops.FoldedLN(stats, w[f"{name}.colsum"], 1e-5))
+
         # self-attention
-        n = ops.layernorm(h, w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
         if isinstance(a1.processor, B200AttnProcessor):
-            qkv = ops.gemm(n, w[f"{t}.attn1.to_qkv.weight"])
+            qkv = ops.gemm(h, w[f"{t}.attn1.to_qkv_ln.weight"], **folded(f"{t}.attn1.to_qkv_ln", st))
             a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
-            h = ops.gemm(a, w[f"{t}.attn1.to_out.0.weight"], bias=w[f"{t}.attn1.to_out.0.bias"], residual=h)
-        else:
+            h, st = ops.gemm(a, w[f"{t}.attn1.to_out.0.weight"], bias=w[f"{t}.attn1.to_out.0.bias"], residual=h,
+                             row_stats=True)
+        else:   # a foreign processor gets the normalised rows, as diffusers hands them over
+            n = ops.layernorm(h, w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
             h = (a1.processor(a1, n.view(B, S, C)).reshape(M, C) + h).contiguous()
+            st = ops.row_stats(h)
         # cross-attention (K/V precomputed per conditioning)
-        n = ops.layernorm(h, w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])
         if isinstance(a2.processor, B200AttnProcessor):
-            q = ops.gemm(n, w[f"{t}.attn2.to_q.weight"])
+            q = ops.gemm(h, w[f"{t}.attn2.to_q_ln.weight"], **folded(f"{t}.attn2.to_q_ln", st))
             kvb = kv[f"{t}.attn2"]
             a = ops.attention(q, kvb[:, :C], kvb[:, C:], B, heads)
-            h = ops.gemm(a, w[f"{t}.attn2.to_out.0.weight"], bias=w[f"{t}.attn2.to_out.0.bias"], residual=h)
+            h, st = ops.gemm(a, w[f"{t}.attn2.to_out.0.weight"], bias=w[f"{t}.attn2.to_out.0.bias"], residual=h,
+                             row_stats=True)
         else:
+            n = ops.layernorm(h, w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])
             h = (a2.processor(a2, n.view(B, S, C), encoder_hidden_states=kv["_ctx3d"]).reshape(M, C) + h).contiguous()
-        # feed-forward (GEGLU fused into the first GEMM's epilogue)
-        n = ops.layernorm(h, w[f"{t}.norm3.weight"], w[f"{t}.norm3.bias"])
-        g = ops.gemm(n, w[f"{t}.ff.net.0.proj.weight"], bias=w[f"{t}.ff.net.0.proj.bias"], geglu=True)
+            st = ops.row_stats(h)
+        # feed-forward (LayerNorm + GEGLU both in the first GEMM's epilogue)
+        g = ops.gemm(h, w[f"{t}.ff.net.0.proj_ln.weight"], geglu=True, **folded(f"{t}.ff.net.0.proj_ln", st))
         h = ops.gemm(g, w[f"{t}.ff.net.2.weight"], bias=w[f"{t}.ff.net.2.bias"], residual=h)
         out = ops.gemm(h, w[f"{p}.proj_out.weight"], bias=w[f"{p}.proj_out.bias"], residual=x.view(M, C))
         return out.view(B, H, W, C)

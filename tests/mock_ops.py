@@ -18,9 +18,16 @@ def _rt(x, dtype):
 
 
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
-         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True):
+         out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True, row_stats=False,
+         ln=None):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
+    if ln is not None:   # pcdm_ext.ln_*: out = rstd * (acc - mean * colsum) + bias, (mean, rstd) from the producer's sums
+        K = x.shape[1]
+        st = ln.stats.buf[: ln.stats.parts].sum(0)
+        mean = st[:, 0] / K
+        rstd = torch.rsqrt((st[:, 1] / K - mean * mean).clamp_min(0) + ln.eps)
+        y = rstd[:, None] * (y - mean[:, None] * ln.colsum[None, :])
     if geglu:
         y = y + (bias if bias is not None else 0)
         g = y.view(y.shape[0], -1, 64)
@@ -39,7 +46,16 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     y = y if out_f32 else _rt(y, a.dtype)
     if out is not None:
         out.copy_(y)
-        return out
+        y = out
+    if row_stats:
+        from pcdms_b200.ops import RowStats
+        yf = y.float()
+        # two slots, as a real launch with one N tile would write (statistics of the values before the 16-bit store
+        # differ from these by rounding noise far below the tolerance of any consumer)
+        half = yf.shape[1] // 2
+        buf = torch.stack([torch.stack([yf[:, :half].sum(1), (yf[:, :half] ** 2).sum(1)], dim=1),
+                           torch.stack([yf[:, half:].sum(1), (yf[:, half:] ** 2).sum(1)], dim=1)])
+        return y, RowStats(buf, 2)
     return y
 
 
@@ -264,6 +280,12 @@ def gaussian_sample(moments, B, channels, HW, noise=None, scale=1.0, out=None):
     return (v * scale).contiguous()
 
 
+def row_stats(x):
+    from pcdms_b200.ops import RowStats
+    xf = x.float()
+    return RowStats(torch.stack([xf.sum(1), (xf ** 2).sum(1)], dim=1)[None], 1)
+
+
 def ensure_workspace(device, nbytes=0):
     return None
 
@@ -272,7 +294,7 @@ def require_cuda(t, what):
     return None
 
 
-_NAMES = ["ensure_workspace", "require_cuda", "gemm", "ln_gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
+_NAMES = ["ensure_workspace", "require_cuda", "row_stats", "gemm", "ln_gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
           "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "cfg_rescale_ratio", "cfg_combine", "add_noise", "ddim_step", "cfg_unipc_step",
           "unipc_step", "softmax_rows", "gaussian_sample", "cfg_unclip_step", "unclip_step"]
 

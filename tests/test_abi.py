@@ -15,7 +15,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert len(syms) >= 15 and "pcdm_conv3x3" in syms and "pcdm_attention" in syms and "pcdm_cfg_ddim_step" in syms
     for s in syms:
         assert hasattr(cdll, s), f"{s} declared in include/pcdm_b200.h but not exported"
-    assert cdll.pcdm_abi_version() == lib.ABI_VERSION == 2
+    assert cdll.pcdm_abi_version() == lib.ABI_VERSION == 3
     assert isinstance(cdll.pcdm_last_error(), bytes)
 
 
@@ -77,7 +77,7 @@ def test_new_entry_points_validate_before_touching_the_device():
     rc = cdll.pcdm_cfg_unclip_step(p, ll(8), p, p, i(0), ll(4), p, p, p, f(2.0), i(1), i(2), i(8), None, None, None)
     assert rc == lib.ERR_INVALID            # ld_xin < E
     # pcdm_ext is validated before any CUDA call: size, cta group, workspace alignment
-    bad = lib.Ext(4, 0, None, 0)
+    bad = lib.Ext(4, 0, None, 0)   # a caller compiled against a shorter struct
     rc = cdll.pcdm_gemm(p, ll(64), None, ll(0), i(0), p, p, ll(64), None, None, ll(0), i(1), None, ll(0), i(128), i(64),
                         i(64), i(0), i(0), i(0), ctypes.byref(bad), None)
     assert rc == lib.ERR_INVALID and b"pcdm_ext" in cdll.pcdm_last_error()

@@ -285,6 +285,53 @@ def test_fused_step_and_schedulers_match_oracle(ops):
     torch.testing.assert_close(out.cpu(), ddpm_add_noise(s, e, ts), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,C,N,geglu,res", [(1000, 320, 960, False, True), (4096, 640, 640, False, False),
+                                            (300, 1280, 2560, True, True), (2048, 320, 2560, True, False),
+                                            (16, 128, 256, False, True), (32768, 320, 320, False, True)])
+def test_layernorm_folded_into_gemms(ops, dt, M, C, N, geglu, res):
+    """LayerNorm without a pass of its own (BasicTransformerBlock norm1/2/3): the PRODUCING GEMM emits
+    per-row (sum, sum of squares) from its epilogue (pcdm_ext.row_stats), the CONSUMING GEMM takes the raw rows, a
+    gamma-scaled weight and finishes the normalisation in its epilogue (pcdm_ext.ln_*).  Checked against
+    torch LayerNorm -> Linear (-> GEGLU) in fp32 on the same 16-bit tensors, and against the stand-alone statistics
+    kernel."""
+    g = torch.Generator().manual_seed(M + C + N)
+    a = torch.randn(M, C, generator=g).to(dt)
+    w0 = (torch.randn(C, C, generator=g) / C ** 0.5).to(dt)
+    b0 = torch.randn(C, generator=g)
+    r = (2.0 * torch.randn(M, C, generator=g) + 1.5).to(dt) if res else None     # rows with a non-zero mean
+    gamma, beta = 1.0 + 0.2 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    W = torch.randn(N, C, generator=g) / C ** 0.5
+    bias = torch.randn(N, generator=g)
+    # producer: h = a @ w0^T + b0 (+ r), with row statistics
+    h, st = ops.gemm(a.cuda(), w0.cuda(), bias=b0.cuda(), residual=r.cuda() if res else None, row_stats=True)
+    h_ref = a.float() @ w0.float().t() + b0 + (r.float() if res else 0)
+    close(h, h_ref, dt)
+    assert 1 <= st.parts <= st.buf.shape[0]
+    sums = st.buf[: st.parts].sum(0).cpu()
+    hf = h.float().cpu()
+    torch.testing.assert_close(sums[:, 0], hf.sum(1), rtol=2e-3, atol=2e-2 * C ** 0.5)
+    torch.testing.assert_close(sums[:, 1], (hf ** 2).sum(1), rtol=4e-3, atol=1e-2)
+    alone = ops.row_stats(h)
+    assert alone.parts == 1
+    torch.testing.assert_close(alone.buf[0].cpu(), torch.stack([hf.sum(1), (hf ** 2).sum(1)], dim=1), rtol=1e-4, atol=1e-3)
+    # consumer: LN(h) @ W^T + bias (-> GEGLU)
+    ref = F.layer_norm(hf, (C,), gamma, beta, 1e-5) @ W.to(dt).float().t() + bias
+    Wf = (W * gamma[None, :]).to(dt)
+    cb = (W.to(dt).double() @ beta.double()).float() + bias
+    cs = Wf.double().sum(1).float()
+    if geglu:
+        hh, gate = ref.chunk(2, dim=1)
+        ref = hh * F.gelu(gate)
+        perm = ops.geglu_row_permutation(N // 2)
+        Wf, cb, cs = Wf[perm].contiguous(), cb[perm].contiguous(), cs[perm].contiguous()
+    for stats in (st, alone):
+        out = ops.gemm(h, Wf.cuda(), bias=cb.cuda(), geglu=geglu, ln=ops.FoldedLN(stats, cs.cuda(), 1e-5))
+        # the weight rounding differs from the unfused form (round(W g) vs round(W)): twice the single-op tolerance
+        close(out, ref, dt, mult=2.0)
+    assert torch.equal(out, ops.gemm(h, Wf.cuda(), bias=cb.cuda(), geglu=geglu, ln=ops.FoldedLN(alone, cs.cuda(), 1e-5)))
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
 def test_cfg_combine_and_rescale(ops, dt):
     """a11: e_u + g (e_c - e_u) and the reference's rescale_noise_cfg (stage2_inpaint_pipeline.py:52-63) as kernels —
