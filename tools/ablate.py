@@ -36,7 +36,10 @@ def _empty_like_result(name, args, kw):
     if name == "gemm":
         a, wgt = args[0], args[1]
         n = wgt.shape[0] // 2 if kw.get("geglu") else wgt.shape[0]
-        return torch.empty((a.shape[0], n), device=a.device, dtype=torch.float32 if kw.get("out_f32") else a.dtype)
+        out = torch.empty((a.shape[0], n), device=a.device, dtype=torch.float32 if kw.get("out_f32") else a.dtype)
+        if kw.get("row_stats"):
+            return out, ops.RowStats(torch.ones((2, a.shape[0], 2), device=a.device, dtype=torch.float32), 2)
+        return out
     if name == "conv3x3":
         x, wgt = args[0], args[1]
         s = kw.get("stride", 1)
