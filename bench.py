@@ -227,16 +227,21 @@ def roofline_probe(unet, pipe_state, peaks):
         real_cout = unet.config.out_channels if k.get("out_f32") else w.shape[0]
         return 2.0 * B * (H // s) * (W // s) * real_cout * 9 * real_cin
 
+    def up_flops(x, w, *a, **k):   # algorithmic = the reference's op (nearest-2x, then a 9-tap conv at 2H x 2W)
+        B, H, W, cin = x.shape
+        return 2.0 * B * (2 * H) * (2 * W) * w.shape[1] * 9 * cin
+
     def gemm_flops(a_, w, *a, **k):
         return 2.0 * a_.shape[0] * w.shape[0] * w.shape[1]
 
     def attn_flops(q, k_, v, B, heads, *a, **k):
         return 4.0 * B * heads * (q.shape[0] // B) * (k_.shape[0] // B) * 64
 
-    saved = (ops.conv3x3, ops.gemm, ops.attention)
+    saved = (ops.conv3x3, ops.gemm, ops.attention, ops.conv3x3_up2x)
     ops.conv3x3 = wrap("conv3x3_igemm", saved[0], conv_flops)
     ops.gemm = wrap("linear_gemm", saved[1], gemm_flops)
     ops.attention = wrap("attention", saved[2], attn_flops)
+    ops.conv3x3_up2x = wrap("conv3x3_igemm", saved[3], up_flops)   # Upsample2D's conv: same kernel, same class
     try:
         for _ in range(2):
             pending.clear()
@@ -246,7 +251,7 @@ def roofline_probe(unet, pipe_state, peaks):
             unet.forward_nhwc(pipe_state.x9, pipe_state.t_cur, pipe_state.kv, pipe_state.cls, pipe_state.pose)
         torch.cuda.synchronize()
     finally:
-        ops.conv3x3, ops.gemm, ops.attention = saved
+        ops.conv3x3, ops.gemm, ops.attention, ops.conv3x3_up2x = saved
     for name, fl, e0, e1 in pending:
         s = stats.setdefault(name, dict(flops=0.0, ms=0.0, launches=0))
         s["flops"] += fl
@@ -412,6 +417,8 @@ def run_b200(args):
         "frac": (conv.get("tflops") / peaks["burst"]) if conv.get("tflops") else None, "traffic": traffic,
         "peak_source": peaks["source"] + "; burst bf16 figure (kernels timed one launch at a time)",
         "launches_per_unet_step": conv.get("launches"),
+        "note": "algorithmic FLOPs = the reference's ops (SURVEY.md §8d); the 3 Upsample2D convs execute 16/36 of theirs "
+                "(four per-parity 2x2 convolutions over the low-resolution input instead of 9 taps at 2H x 2W)",
         "algorithmic_flops_per_unet_step": conv.get("flops"),
         "avg_launch_ms": (conv.get("ms") / conv.get("launches")) if conv.get("launches") else None,
         "other_kernels": {k: {kk: v[kk] for kk in ("tflops", "frac_of_burst_peak", "launches", "ms")}

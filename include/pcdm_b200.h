@@ -70,16 +70,16 @@ typedef struct pcdm_ext {
    *   fp32 pair per column slice: row_stats[slot][m][2], slot < row_stats_parts.  row_stats_parts is an OUTPUT (set at
    *   call time: 2 per N tile); the buffer must hold row_stats_cap >= 2 * ceil(N / 64) slots of M pairs.
    * consumer — the GEMM that multiplies the normalised rows (to_q/k/v, ff.net.0.proj), given the RAW rows as A:
-   *   ln_stats = the producer's buffer, ln_parts = its row_stats_parts, W pre-scaled by gamma (W'[n,k] = W[n,k] g[k]),
-   *   ln_colsum[n] = sum_k W'[n,k] (fp32, of the 16-bit-rounded W'), bias[n] = sum_k W[n,k] beta[k] (+ the layer's bias):
-   *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_colsum[n]) + bias[n],  mean / rstd over the K input columns
-   *   (biased variance, ln_eps inside the square root: torch.nn.LayerNorm).  Works with PCDM_FLAG_GEGLU. ---- */
+   *   ln_stats = the producer's buffer, ln_parts = its row_stats_parts.  The caller prepares the weight once:
+   *   W'[n,k] = W[n,k] g[k] - mean_k(W[n,:] g) (gamma-scaled, then every ROW centred: sum_k W'[n,k] = 0, so the
+   *   row mean of A cancels inside the accumulation) and bias[n] = sum_k W[n,k] beta[k] (+ the layer's own bias).  Then
+   *   out[m,n] = rstd[m] * acc[m,n] + bias[n],  rstd over the K input columns (biased variance, ln_eps inside the
+   *   square root: torch.nn.LayerNorm) — the epilogue costs what a plain bias add costs.  Works with PCDM_FLAG_GEGLU. ---- */
   float* row_stats;
   int row_stats_cap;
   int row_stats_parts;
   const float* ln_stats;
   int ln_parts;
-  const float* ln_colsum;
   float ln_eps;
 } pcdm_ext;
 
@@ -124,6 +124,19 @@ int pcdm_ln_gemm(const void* x, long long ldx, const float* gamma, const float* 
 int pcdm_conv3x3(const void* x, const void* w_packed, void* out, const float* bias, const float* rowvec,
                  long long ld_rowvec, const void* residual, int B, int H, int W, int Cin, int Cout, int stride,
                  int dtype, int flags, int bn, pcdm_ext* ext, void* stream);
+
+/* diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest") followed by Conv2d(Cin, Cout, 3, padding=1), as ONE
+ * launch that never materialises the upsampled tensor (reference blocks
+ * src/models/stage2_inpaint_unet_2d_condition.py:407-429).  An output pixel (2i + py, 2j + px) only sees source rows
+ * {i - 1, i} (py = 0) or {i, i + 1} (py = 1), and columns alike: the layer is four 2x2 convolutions over the
+ * LOW-resolution input, one per output parity, with the 3x3 taps pre-summed per parity — 16 Cin instead of 36 Cin MACs per
+ * output value.  x: [B, H, W, Cin]; out: [B, 2H, 2W, Cout];
+ * w_up: [4][Cout][2][2][Cin] 16-bit, plane p = 2 py + px, tap (ty, tx) = the sum of W[:, :, r, s] over the rows r / columns s
+ * that collapse onto source offset (ty - 1 + py, tx - 1 + px)  (pcdms_b200.ops.pack_upsample_conv_weight).
+ * Cin % 64 == 0, Cout % 64 == 0; W | 128 and H*W a multiple or divisor of 128 (as pcdm_conv3x3 at H x W), W and H*W
+ * multiples or divisors of 32.  flags: PCDM_FLAG_SILU / PCDM_FLAG_GELU. */
+int pcdm_conv3x3_up2x(const void* x, const void* w_up, void* out, const float* bias, int B, int H, int W, int Cin,
+                      int Cout, int dtype, int flags, int bn, pcdm_ext* ext, void* stream);
 
 /* torch.nn.GroupNorm(groups, C, eps) (+ SiLU with PCDM_FLAG_SILU) over NHWC x = [x1 | x2] (x2 may be NULL; x1 then has
  * C channels).  Replaces norm1/norm2(+nonlinearity) of ResnetBlock2D, Transformer2DModel.norm and conv_norm_out

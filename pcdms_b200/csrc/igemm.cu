@@ -41,7 +41,11 @@ struct IGemmParams {
   int num_kb;      // K / 64
   int m_tiles, n_tiles;
   int mode;        // 0 = plain GEMM (A row-major [M, K], up to two K-segments), 1 = conv3x3 s1, 2 = conv3x3 s2 (pad 1),
-                   // 3 = conv3x3 s2 with bottom/right padding only
+                   // 3 = conv3x3 s2 with bottom/right padding only, 4 = nearest-2x upsample + conv3x3 as four 2x2
+                   // convolutions over the LOW-resolution input, one per output-pixel parity ("plane": the tile index
+                   // enumerates it through `splits` = 4; H / W / M are low-resolution; see pcdm_conv3x3_up2x)
+  CUtensorMap tmOutP[4];   // mode 4: the output pixels of parity (py, px) as a 4-D strided view [Cout, W, H, B]
+  int obox_w, obox_h;      // mode 4: the 32 pixels a warp stores at once as a (obox_w x obox_h x 32/(w*h)) box
   int H, W;        // conv: output height / width
   int cblocks;     // conv: Cin / 64
   int kb_split;    // plain: k-blocks taken from tmA[0]; the rest come from tmA[1]
@@ -66,10 +70,9 @@ struct IGemmParams {
   // ---- LayerNorm around the GEMM (16-bit output paths; see pcdm_ext in include/pcdm_b200.h) ----
   float2* stats_out;        // producer: per-row (sum, sum of squares) of the outputs, one slot per (n-tile, column-half):
                             // [2 * n_tiles][M]; the LayerNorm statistics of the NEXT op without another pass over the rows
-  const float2* ln_stats;   // consumer: LayerNorm folded into this GEMM — W was pre-scaled by gamma, the rows arrive raw,
-  int ln_parts;             //   out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]   (bias[n] carries W . beta too)
-  const float* ln_colsum;   //   with (mean, rstd) from the producer's ln_parts partial sums over the K input columns
-  float ln_eps, ln_inv_k;
+  const float2* ln_stats;   // consumer: LayerNorm folded into this GEMM — the rows arrive raw, W was pre-scaled by gamma
+  int ln_parts;             //   AND row-centred (sum_k W'[n,k] = 0, so the mean cancels inside the accumulation):
+  float ln_eps, ln_inv_k;   //   out = rstd[m] * acc + bias[n]   (bias[n] carries W . beta), rstd from the producer's sums
 };
 
 template <int BN, int CG>
@@ -94,9 +97,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 u) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
-// (mean, rstd) of output row m of the PRODUCING GEMM from its per-(n-tile, half) partial sums, as the packed scalars
-// the epilogue needs: rstd and -rstd * mean.  Fixed summation order (bit-reproducible).
-__device__ __forceinline__ void ln_row_scalars(const IGemmParams& p, long long m, bool valid, float2& rstd2, float2& nm2) {
+// rstd of row m of the LayerNorm input from the PRODUCING GEMM's per-(n-tile, half) partial sums.  Fixed summation
+// order (bit-reproducible).
+__device__ __forceinline__ float2 ln_row_rstd(const IGemmParams& p, long long m, bool valid) {
   float sum = 0.f, sq = 0.f;
   if (valid) {
     for (int i = 0; i < p.ln_parts; ++i) {
@@ -108,8 +111,7 @@ __device__ __forceinline__ void ln_row_scalars(const IGemmParams& p, long long m
   const float mean = sum * p.ln_inv_k;
   const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
   const float rstd = rsqrtf(var + p.ln_eps);
-  rstd2 = make_float2(rstd, rstd);
-  nm2 = make_float2(-rstd * mean, -rstd * mean);
+  return make_float2(rstd, rstd);
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA[0]);
-    if (!p.out_f32) tma_prefetch_desc(&p.tmOut);
+    if (!p.out_f32) tma_prefetch_desc(p.mode == 4 ? &p.tmOutP[0] : &p.tmOut);
     if (p.has_res) tma_prefetch_desc(&p.tmRes);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 2);   // the activation producer's and the weight producer's expect_tx arrivals
@@ -183,7 +185,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         y0 = rem / p.W;
         x0 = rem - y0 * p.W;
       }
-      const int kb_begin = split * p.kb_per_split;
+      const int plane = p.mode == 4 ? split : 0;
+      const int kb_begin = (p.mode == 4 ? 0 : split) * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
       // The K range is walked segment by segment — one filter tap of a conv, or one of the (up to two) concatenated
       // A matrices of a GEMM — so that inside a segment only the channel coordinate moves and the per-k-block loop is
@@ -203,7 +206,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           c0 = (kb - tap * p.cblocks) * 64;
           seg_end = min(kb_end, (tap + 1) * p.cblocks);
           c3 = b0;
-          if (p.mode == 1) {
+          if (p.mode == 4) {
+            // output row 2i + py reads upsampled rows 2i + py - 1 .. + 1 = source rows {i - 1, i} (py = 0) or {i, i + 1}
+            // (py = 1): a 2-tap filter whose taps were pre-summed on the host; columns alike
+            c1 = x0 + (tap & 1) - 1 + (plane & 1);
+            c2 = y0 + (tap >> 1) - 1 + (plane >> 1);
+          } else if (p.mode == 1) {
             c1 = x0 + s - 1;
             c2 = y0 + r - 1;
           } else if (p.mode == 2) {
@@ -252,8 +260,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int n_blk = mn % p.n_tiles;
-      const int n0 = n_blk * BN + ((CG == 2) ? (int)rank * (BN / 2) : 0);
-      const int kb_begin = split * p.kb_per_split;
+      // mode 4: the four parity planes' weights are stacked along N ([4 * Cout, 4 * Cin])
+      const int n0 = n_blk * BN + ((CG == 2) ? (int)rank * (BN / 2) : 0) + (p.mode == 4 ? split * p.N : 0);
+      const int kb_begin = (p.mode == 4 ? 0 : split) * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-      const int split = tile / mn_tiles;
+      const int split = p.mode == 4 ? 0 : tile / mn_tiles;
       const int nkb = min(p.num_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -389,8 +398,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
         //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
         const bool use_res = p.has_res && !IG_DBG(p, 2);
-        float2 ln_rstd2 = make_float2(1.f, 1.f), ln_nm2 = make_float2(0.f, 0.f);
-        if (p.ln_stats) ln_row_scalars(p, m, valid, ln_rstd2, ln_nm2);   // global loads overlap the tile's MMAs
+        float2 ln_rstd2 = make_float2(1.f, 1.f);
+        if (p.ln_stats) ln_rstd2 = ln_row_rstd(p, m, valid);   // global loads overlap the tile's MMAs
         float2 st_sum = make_float2(0.f, 0.f), st_sq = make_float2(0.f, 0.f);
         if (use_res) {
           if (lane == 0) {
@@ -423,11 +432,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           if (p.ln_stats) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {   // rstd * acc + (-rstd * mean) * colsum[n] + bias'[n]
-              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+            for (int j = 0; j < 32; j += 4) {   // rstd * acc + bias'[n]: the same issue slots as a plain bias add
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j / 2] = __ffma2_rn(ln_rstd2, v[j / 2], __ffma2_rn(ln_nm2, make_float2(cs.x, cs.y), make_float2(b.x, b.y)));
-              v[j / 2 + 1] = __ffma2_rn(ln_rstd2, v[j / 2 + 1], __ffma2_rn(ln_nm2, make_float2(cs.z, cs.w), make_float2(b.z, b.w)));
+              v[j / 2] = __ffma2_rn(ln_rstd2, v[j / 2], make_float2(b.x, b.y));
+              v[j / 2 + 1] = __ffma2_rn(ln_rstd2, v[j / 2 + 1], make_float2(b.z, b.w));
             }
           } else if (p.bias && !IG_DBG(p, 4)) {
 #pragma unroll
@@ -483,7 +491,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && !IG_DBG(p, 1)) {
-            tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
+            if (p.mode == 4) {   // the warp's 32 low-resolution pixels land on every second pixel of every second row
+              const int hw = p.H * p.W;
+              const int bw = m_warp0 / hw, rem = m_warp0 - bw * hw;
+              tma_store_4d(&p.tmOutP[split], sl, n0, rem % p.W, rem / p.W, bw);
+            } else {
+              tma_store_2d(&p.tmOut, sl, n0, m_warp0);   // rows >= M / columns >= N are clipped by the tensor map
+            }
             bulk_commit();
           }
           ++cnt;
@@ -492,8 +506,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           p.stats_out[(long long)(n_blk * 2 + half) * p.M + m] = make_float2(st_sum.x + st_sum.y, st_sq.x + st_sq.y);
       } else {
         // ---- GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate) ----
-        float2 ln_rstd2 = make_float2(1.f, 1.f), ln_nm2 = make_float2(0.f, 0.f);
-        if (p.ln_stats) ln_row_scalars(p, m, valid, ln_rstd2, ln_nm2);
+        float2 ln_rstd2 = make_float2(1.f, 1.f);   // stays 1 without a folded LayerNorm: rstd * acc + bias == acc + bias
+        if (p.ln_stats) ln_rstd2 = ln_row_rstd(p, m, valid);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -517,23 +531,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
               bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
             }
-            float2 h0 = make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1]));
-            float2 h1 = make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3]));
-            float2 g0 = make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1]));
-            float2 g1 = make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3]));
-            if (p.ln_stats) {   // LayerNorm folded into the projection: rstd * acc + (-rstd * mean) * colsum + bias'
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
-              const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 32 + j));
-              h0 = __ffma2_rn(ln_rstd2, h0, __ffma2_rn(ln_nm2, make_float2(sh.x, sh.y), make_float2(bh.x, bh.y)));
-              h1 = __ffma2_rn(ln_rstd2, h1, __ffma2_rn(ln_nm2, make_float2(sh.z, sh.w), make_float2(bh.z, bh.w)));
-              g0 = __ffma2_rn(ln_rstd2, g0, __ffma2_rn(ln_nm2, make_float2(sg.x, sg.y), make_float2(bg.x, bg.y)));
-              g1 = __ffma2_rn(ln_rstd2, g1, __ffma2_rn(ln_nm2, make_float2(sg.z, sg.w), make_float2(bg.z, bg.w)));
-            } else {
-              h0 = __fadd2_rn(h0, make_float2(bh.x, bh.y));
-              h1 = __fadd2_rn(h1, make_float2(bh.z, bh.w));
-              g0 = __fadd2_rn(g0, make_float2(bg.x, bg.y));
-              g1 = __fadd2_rn(g1, make_float2(bg.z, bg.w));
-            }
+            // (+ folded LayerNorm: rstd * acc + bias'; rstd == 1 otherwise)
+            const float2 h0 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), make_float2(bh.x, bh.y));
+            const float2 h1 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
+            const float2 g0 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
+            const float2 g1 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
             // gate activation: GELU (GEGLU, diffusers FeedForward) or SiLU (SwiGLU, DINOv2's FFN) — warp-uniform
             const float2 v0 = __fmul2_rn(h0, p.silu == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
             const float2 v1 = __fmul2_rn(h1, p.silu == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
@@ -667,7 +669,7 @@ static int kb_cycles(int bn, int cg) {
   return bn == 64 ? 446 : (bn == 128 ? 479 : (bn == 160 ? 549 : 619));
 }
 
-static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int force_cg, int* bn_out, int* cg_out) {
+static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int force_cg, int planes, int* bn_out, int* cg_out) {
   const int cand[4] = {160, 256, 128, 64};
   long long best = 1LL << 62;
   *bn_out = 128;
@@ -680,7 +682,8 @@ static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int forc
       if (geglu && (bn % 64)) continue;
       if (bn == 160 && (N % 160)) continue;
       if (cg == 2 && bn < 128) continue;
-      const long long tiles = (long long)((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+      if (planes > 1 && (N % bn)) continue;   // stacked per-plane weights: an N tile must not straddle two planes
+      const long long tiles = (long long)((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn) * planes;
       const long long slots = num_sms() / cg;
       const long long waves = (tiles + slots - 1) / slots;
       // per tile: the k loop, plus the part of the epilogue / pipeline turn-around that is not hidden
@@ -700,7 +703,6 @@ struct ExtArgs {   // what the caller's pcdm_ext carries (all optional)
   int row_stats_cap = 0;
   const float* ln_stats = nullptr;   // consumer side
   int ln_parts = 0;
-  const float* ln_colsum = nullptr;
   float ln_eps = 0.f;
   pcdm_ext* raw = nullptr;      // for the output field row_stats_parts
 };
@@ -724,12 +726,10 @@ static int read_ext(pcdm_ext* ext, ExtArgs* e) {
     e->row_stats_cap = ext->row_stats_cap;
   }
   if (ext->ln_stats) {
-    if (ext->ln_parts <= 0 || !ext->ln_colsum || !(ext->ln_eps >= 0.f) ||
-        ((reinterpret_cast<uintptr_t>(ext->ln_stats) & 7) | (reinterpret_cast<uintptr_t>(ext->ln_colsum) & 15)))
-      return set_error(PCDM_ERR_INVALID, "pcdm_ext: ln_stats needs ln_parts > 0, ln_colsum (16-byte aligned) and ln_eps >= 0");
+    if (ext->ln_parts <= 0 || !(ext->ln_eps >= 0.f) || (reinterpret_cast<uintptr_t>(ext->ln_stats) & 7))
+      return set_error(PCDM_ERR_INVALID, "pcdm_ext: ln_stats needs ln_parts > 0, ln_eps >= 0 and an 8-byte aligned buffer");
     e->ln_stats = ext->ln_stats;
     e->ln_parts = ext->ln_parts;
-    e->ln_colsum = ext->ln_colsum;
     e->ln_eps = ext->ln_eps;
   }
   e->raw = ext;
@@ -749,7 +749,7 @@ struct EpiArgs {   // the fused-epilogue operands as the caller gave them
 };
 
 static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, const void* residual, long long ldr,
-                          const ExtArgs& ext, cudaStream_t stream) {
+                          const ExtArgs& ext, cudaStream_t stream, int planes = 1) {
   void* const g_ws = ext.ws;
   const long long g_ws_bytes = ext.ws_bytes;
   const int g_force_cg = ext.force_cg;
@@ -764,13 +764,12 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
       return set_error(PCDM_ERR_UNSUPPORTED, "gemm: a folded LayerNorm needs a 16-bit-output GEMM with the bias vector");
     p.ln_stats = reinterpret_cast<const float2*>(ext.ln_stats);
     p.ln_parts = ext.ln_parts;
-    p.ln_colsum = ext.ln_colsum;
     p.ln_eps = ext.ln_eps;
     p.ln_inv_k = 1.0f / (float)K;
   }
   if (ext.row_stats && (p.out_f32 || p.geglu))
     return set_error(PCDM_ERR_UNSUPPORTED, "gemm: row statistics come with the plain 16-bit-output epilogue only");
-  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats) {   // K >= 4096: below, one launch wins
+  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats && planes == 1) {   // K >= 4096: below, one launch wins
     const int sbn = (p.N % 160 == 0) ? 160 : 128;
     const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
     if (tiles * 2 <= num_sms()) {
@@ -792,19 +791,21 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   }
   int cg = 1;
   if (bn == 0) {
-    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, &bn, &cg);
+    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, planes, &bn, &cg);
   } else {
     // explicit tile width (tests / tuning): CTA pairs (256-row tiles) when forced, or by the same model
     int bn_model;
-    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, &bn_model, &cg);
+    pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, planes, &bn_model, &cg);
+    if (planes > 1 && (p.N % bn)) return set_error(PCDM_ERR_INVALID, "conv3x3_up2x: the forced N tile must divide Cout");
     if (g_force_cg == 0) cg = (p.M > 128 && bn >= 128 && !split && kb_cycles(bn, 2) < kb_cycles(bn, 1)) ? 2 : 1;
     if (bn < 128 || p.M <= 128 || split) cg = 1;
   }
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
+  if (planes > 1) { p.splits = planes; p.kb_per_split = p.num_kb; }
   p.has_res = residual ? 1 : 0;
   if (p.has_res && (p.geglu || p.out_f32))
     return set_error(PCDM_ERR_UNSUPPORTED, "igemm: residual cannot be combined with GEGLU or fp32 output");
-  if (!p.out_f32) {
+  if (!p.out_f32 && planes == 1) {
     const uint64_t n_out = p.geglu ? (uint64_t)p.N / 2 : (uint64_t)p.N;
     const uint64_t dims[2] = {n_out, (uint64_t)p.M};
     const uint64_t strides[1] = {(uint64_t)p.ldo * 2};
@@ -828,7 +829,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   const int brows = p.N < bbox ? p.N : bbox;
   p.b_bytes = (uint32_t)brows * 128u;
   {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)p.N};
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)p.N * planes};
     const uint64_t strides[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {64, (uint32_t)brows};
     PCDM_CHECK(make_tmap(&p.tmB, w, 2, dims, strides, box), "weight tensor map");
@@ -976,6 +977,63 @@ extern "C" int pcdm_conv3x3(const void* x, const void* w_packed, void* out, cons
   p.geglu = 0; p.out_f32 = (flags & PCDM_FLAG_OUT_F32) ? 1 : 0; p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
   if (rowvec && (ld_rowvec % 4)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3: rowvec stride must be a multiple of 4");
   return dispatch_igemm(p, dtype, bn, w_packed, 9 * Cin, residual, Cout, ext, stream);
+}
+
+extern "C" int pcdm_conv3x3_up2x(const void* x, const void* w_up, void* out, const float* bias, int B, int H, int W, int Cin,
+                                 int Cout, int dtype, int flags, int bn, pcdm_ext* ext_, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ExtArgs ext;
+  PCDM_CHECK(read_ext(ext_, &ext), "ext");
+  if (!x || !w_up || !out) return set_error(PCDM_ERR_INVALID, "conv3x3_up2x: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "conv3x3_up2x: dtype must be 0 (f16) or 1 (bf16)");
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(PCDM_ERR_INVALID, "conv3x3_up2x: empty problem");
+  if (Cin % 64 || Cout % 64) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: Cin and Cout must be multiples of 64");
+  if (flags & ~(PCDM_FLAG_SILU | PCDM_FLAG_GELU)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: only activation flags");
+  if (ext.row_stats || ext.ln_stats) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: no LayerNorm extras");
+  // tiles are 128 consecutive LOW-resolution pixels (the same geometry as pcdm_conv3x3 at H x W)
+  if (W > 128 || (128 % W)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: input width must divide 128");
+  const int hw = H * W;
+  int tile_h, tile_b;
+  if (hw >= 128) {
+    if (hw % 128) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: H*W must be a multiple of 128 (or divide it)");
+    tile_h = 128 / W; tile_b = 1;
+  } else {
+    if (128 % hw) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: H*W must divide 128");
+    tile_h = H; tile_b = 128 / hw;
+  }
+  if (tile_b > B) tile_b = B;
+  if ((long long)B * hw > 0x7fffffffLL / 4 - 256) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: B*H*W too large");
+  // a warp stores 32 consecutive low-resolution pixels per TMA box: (obox_w x obox_h x images)
+  int obw, obh, obb;
+  if (W >= 32) { if (W % 32) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: W must be a multiple or divisor of 32"); obw = 32; obh = 1; obb = 1; }
+  else if (hw >= 32) { if ((32 % W) || (hw % 32)) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: W | 32 and 32 | H*W"); obw = W; obh = 32 / W; obb = 1; }
+  else { if (32 % hw) return set_error(PCDM_ERR_UNSUPPORTED, "conv3x3_up2x: H*W must divide 32"); obw = W; obh = H; obb = 32 / hw; }
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = B * hw; p.N = Cout; p.num_kb = 4 * (Cin / 64);
+  p.m_tiles = (p.M + 127) / 128;
+  p.mode = 4; p.H = H; p.W = W; p.cblocks = Cin / 64; p.kb_split = p.num_kb;
+  p.obox_w = obw; p.obox_h = obh;
+  p.a_bytes = 128u * (uint32_t)(W * tile_h * tile_b);
+  {
+    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)tile_h, (uint32_t)tile_b};
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)hw * Cin * 2};
+    PCDM_CHECK(make_tmap(&p.tmA[0], x, 4, dims, strides, box), "conv input tensor map");
+  }
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      // output pixel (2i + py, 2j + px) of the [B, 2H, 2W, Cout] result, viewed per parity as [Cout, W, H, B]
+      char* base = reinterpret_cast<char*>(out) + ((size_t)py * 2 * W + px) * Cout * 2;
+      const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)2 * Cout * 2, (uint64_t)2 * 2 * W * Cout * 2, (uint64_t)4 * hw * Cout * 2};
+      const uint32_t box[4] = {32, (uint32_t)obw, (uint32_t)obh, (uint32_t)obb};
+      PCDM_CHECK(make_tmap(&p.tmOutP[py * 2 + px], base, 4, dims, strides, box, 64), "parity output tensor map");
+    }
+  p.bias = bias; p.hw = hw;
+  p.out = out; p.ldo = Cout;
+  p.silu = (flags & PCDM_FLAG_SILU) ? 1 : ((flags & PCDM_FLAG_GELU) ? 2 : 0);
+  return dispatch_igemm(p, dtype, bn, w_up, 4 * Cin, nullptr, Cout, ext, stream, 4);
 }
 
 extern "C" long long pcdm_gemm_workspace_bytes(int M, int N) {

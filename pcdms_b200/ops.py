@@ -103,12 +103,25 @@ class RowStats:
 
 
 class FoldedLN:
-    """A LayerNorm folded into the GEMM that consumes it: the producer's RowStats, colsum[n] = sum_k W'[n, k] of the
-    gamma-scaled weight, eps.  The GEMM's `bias` must already carry W . beta."""
-    __slots__ = ("stats", "colsum", "eps")
+    """A LayerNorm folded into the GEMM that consumes it: the producer's RowStats and eps.  The GEMM's weight must be
+    `fold_layernorm_weight(...)` (gamma-scaled, rows centred) and its `bias` must carry W . beta."""
+    __slots__ = ("stats", "eps")
 
-    def __init__(self, stats: RowStats, colsum, eps=1e-5):
-        self.stats, self.colsum, self.eps = stats, colsum, eps
+    def __init__(self, stats: RowStats, eps=1e-5):
+        self.stats, self.eps = stats, eps
+
+
+def fold_layernorm_weight(W: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias, dtype):
+    """Weight / bias of Linear(LayerNorm(x; gamma, beta)) for the folded form `rstd[m] * (x[m] . W'^T) + bias'`:
+    W'[n, k] = W[n, k] gamma[k] - mean_k(W[n, :] gamma) — with centred rows the row mean of x cancels inside the
+    accumulation, only rstd is left for the epilogue — and bias'[n] = W[n, :] . beta (+ bias[n]).  fp64 arithmetic,
+    W' rounded once to `dtype`."""
+    Wg = W.double() * gamma.double()[None, :]
+    Wc = (Wg - Wg.mean(dim=1, keepdim=True)).to(dtype)
+    cb = W.double() @ beta.double()
+    if bias is not None:
+        cb = cb + bias.double()
+    return Wc.contiguous(), cb.float().contiguous()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -118,6 +131,23 @@ def pack_conv3x3_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """[Cout, Cin, 3, 3] (torch Conv2d layout) -> [Cout, 3, 3, Cin] flattened to [Cout, 9*Cin] (tap-major K)."""
     assert w.dim() == 4 and w.shape[2:] == (3, 3)
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
+
+
+def pack_upsample_conv_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] of the conv that follows a nearest-2x upsample -> [4, Cout, 4*Cin]: per output parity
+    p = 2*py + px a 2x2 filter over the LOW-resolution input whose tap (ty, tx) is the sum of the 3x3 taps that read
+    the same source pixel (py = 0: rows {0} | {1, 2}; py = 1: rows {0, 1} | {2}; columns alike).  Summed in fp64,
+    rounded once."""
+    assert w.dim() == 4 and w.shape[2:] == (3, 3)
+    w = w.double()
+    collapse = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    planes = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = [w[:, :, collapse[py][ty]][:, :, :, collapse[px][tx]].sum(dim=(2, 3))
+                    for ty in (0, 1) for tx in (0, 1)]
+            planes.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))
+    return torch.stack(planes).to(dtype).contiguous()
 
 
 def geglu_row_permutation(n_out: int) -> torch.Tensor:
@@ -162,9 +192,8 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
         stats = RowStats(torch.empty((cap, M, 2), device=a.device, dtype=torch.float32), 0)
         ext.row_stats, ext.row_stats_cap = stats.buf.data_ptr(), cap
     if ln is not None:
-        assert ln.stats.buf.shape[1] == M and ln.colsum.dtype == torch.float32 and ln.colsum.numel() == N and bias is not None
-        ext.ln_stats, ext.ln_parts = ln.stats.buf.data_ptr(), ln.stats.parts
-        ext.ln_colsum, ext.ln_eps = ln.colsum.data_ptr(), float(ln.eps)
+        assert ln.stats.buf.shape[1] == M and bias is not None
+        ext.ln_stats, ext.ln_parts, ext.ln_eps = ln.stats.buf.data_ptr(), ln.stats.parts, float(ln.eps)
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
@@ -221,6 +250,24 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
     rc = lib.pcdm_conv3x3(_l.ptr(x), _l.ptr(w_packed), _l.ptr(out), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
                           C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
                           C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), C.byref(ext), _stream(x))
+    _l.check(rc)
+    return out
+
+
+def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0):
+    """Upsample2D: nearest-2x + conv3x3 in one launch.  x: [B, H, W, Cin]; w_up: pack_upsample_conv_weight(...)
+    [4, Cout, 4*Cin]; returns [B, 2H, 2W, Cout]."""
+    lib = _l.load()
+    B, H, W, Cin = x.shape
+    Cout = w_up.shape[1]
+    assert w_up.shape == (4, Cout, 4 * Cin) and x.is_contiguous() and w_up.is_contiguous()
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=x.dtype)
+    assert out.is_contiguous() and tuple(out.shape) == (B, 2 * H, 2 * W, Cout)
+    ext = _ext(x, cta_group)
+    rc = lib.pcdm_conv3x3_up2x(_l.ptr(x), _l.ptr(w_up), _l.ptr(out), _l.ptr(_f32(bias)), C.c_int(B), C.c_int(H),
+                               C.c_int(W), C.c_int(Cin), C.c_int(Cout), C.c_int(_dt(x)),
+                               C.c_int(_l.FLAG_SILU if silu else 0), C.c_int(bn), C.byref(ext), _stream(x))
     _l.check(rc)
     return out
 

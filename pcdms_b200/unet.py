@@ -13,6 +13,8 @@ What is fused relative to the reference's op-by-op graph:
   * q/k/v of self-attention are one GEMM; all 22 resnet time_emb_proj linears are one GEMM per step;
   * the three LayerNorms of every transformer block are folded into the GEMMs either side of them (statistics from the
     producer's epilogue, gamma in the consumer's weights, normalisation in the consumer's epilogue): no LN launches;
+  * Upsample2D (nearest-2x + conv3x3) is one launch of four per-parity 2x2 convolutions over the low-resolution
+    tensor: the 4x tensor is never written and the layer costs 16/36 of the MACs;
   * the skip concat of the up blocks is never materialised (GroupNorm and the 1x1 shortcut read both sources);
   * cross-attention K/V depend only on encoder_hidden_states: computed once per conditioning, not once per step.
 """
@@ -514,26 +516,25 @@ class B200UNet2DConditionModel(WeightArenaMixin):
                 w[f"{t}.attn2.to_kv.weight"] = torch.cat(
                     [w[f"{t}.attn2.to_k.weight"], w[f"{t}.attn2.to_v.weight"]]).contiguous()
                 # LayerNorm folded into the GEMM that consumes it (norm1 -> q/k/v, norm2 -> to_q, norm3 -> GEGLU proj):
-                # W' = W diag(gamma) (16-bit), colsum[n] = sum_k W'[n,k], bias'[n] = W[n,:] . beta (+ bias[n]);
-                # the GEMM runs on the RAW rows and the epilogue applies rstd * (acc - mean * colsum) + bias'
+                # gamma-scaled, row-centred weight + bias' = W . beta (+ bias) (ops.fold_layernorm_weight); the GEMM runs
+                # on the RAW rows and its epilogue applies rstd[m] * acc + bias'
                 perm = ops.geglu_row_permutation(4 * c)
                 for name, srcs, norm, bias_key, rows in (
                         (f"{t}.attn1.to_qkv_ln", [f"{t}.attn1.to_q", f"{t}.attn1.to_k", f"{t}.attn1.to_v"], f"{t}.norm1", None, None),
                         (f"{t}.attn2.to_q_ln", [f"{t}.attn2.to_q"], f"{t}.norm2", None, None),
                         (f"{t}.ff.net.0.proj_ln", [f"{t}.ff.net.0.proj"], f"{t}.norm3", f"{t}.ff.net.0.proj.bias", perm)):
                     W = torch.cat([sd[f"{k}.weight"].detach().to(dev, torch.float32) for k in srcs])
-                    gamma = sd[f"{norm}.weight"].detach().to(dev, torch.float32)
-                    beta = sd[f"{norm}.bias"].detach().to(dev, torch.float32)
-                    Wf = (W * gamma[None, :]).to(dt)
-                    cb = (W.double() @ beta.double()).float()
-                    if bias_key is not None:
-                        cb = cb + sd[bias_key].detach().to(dev, torch.float32)
-                    cs = Wf.double().sum(dim=1).float()
+                    Wf, cb = ops.fold_layernorm_weight(
+                        W, sd[f"{norm}.weight"].detach().to(dev), sd[f"{norm}.bias"].detach().to(dev),
+                        sd[bias_key].detach().to(dev) if bias_key is not None else None, dt)
                     if rows is not None:
-                        Wf, cb, cs = Wf[rows.to(Wf.device)], cb[rows.to(cb.device)], cs[rows.to(cs.device)]
-                    w[f"{name}.weight"], w[f"{name}.bias"], w[f"{name}.colsum"] = Wf.contiguous(), cb.contiguous(), cs.contiguous()
-            elif op[0] in ("down", "up"):
+                        Wf, cb = Wf[rows.to(Wf.device)].contiguous(), cb[rows.to(cb.device)].contiguous()
+                    w[f"{name}.weight"], w[f"{name}.bias"] = Wf, cb
+            elif op[0] == "down":
                 w[f"{op[1]}.weight"], w[f"{op[1]}.bias"] = conv(f"{op[1]}.weight"), f32(f"{op[1]}.bias")
+            elif op[0] == "up":   # nearest-2x + conv3x3 as four per-parity 2x2 convs over the low-resolution input
+                w[f"{op[1]}.weight"] = ops.pack_upsample_conv_weight(sd[f"{op[1]}.weight"].detach().float(), dt).to(dev)
+                w[f"{op[1]}.bias"] = f32(f"{op[1]}.bias")
         self._loaded = True
         self._arena = None       # a consolidated arena of earlier weights is stale now
         self._ctx_cache = None
@@ -681,7 +682,7 @@ class B200UNet2DConditionModel(WeightArenaMixin):
             elif kind == "down":
                 x = ops.conv3x3(x, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], stride=2)
             elif kind == "up":
-                x = ops.conv3x3(ops.upsample_nearest2x(x), w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"])
+                x = ops.conv3x3_up2x(x, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"])
         hn = ops.groupnorm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], cfg.norm_eps, silu=True)
         return ops.conv3x3(hn, w["conv_out.weight"], bias=w["conv_out.bias"], out_f32=True)
 
@@ -714,7 +715,7 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         a1, a2 = self._attn[f"{t}.attn1"], self._attn[f"{t}.attn2"]
 
         def folded(name, stats):
-            return dict(bias=w[f"{name}.bias"], ln=ops.FoldedLN(stats, w[f"{name}.colsum"], 1e-5))
+            return dict(bias=w[f"{name}.bias"], ln=ops.FoldedLN(stats, 1e-5))
 
         # self-attention
         if isinstance(a1.processor, B200AttnProcessor):

@@ -22,12 +22,12 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
          ln=None):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
-    if ln is not None:   # pcdm_ext.ln_*: out = rstd * (acc - mean * colsum) + bias, (mean, rstd) from the producer's sums
+    if ln is not None:   # pcdm_ext.ln_*: out = rstd * acc + bias (row-centred weight), rstd from the producer's sums
         K = x.shape[1]
         st = ln.stats.buf[: ln.stats.parts].sum(0)
         mean = st[:, 0] / K
         rstd = torch.rsqrt((st[:, 1] / K - mean * mean).clamp_min(0) + ln.eps)
-        y = rstd[:, None] * (y - mean[:, None] * ln.colsum[None, :])
+        y = rstd[:, None] * y
     if geglu:
         y = y + (bias if bias is not None else 0)
         g = y.view(y.shape[0], -1, 64)
@@ -85,6 +85,23 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
         y = F.silu(y)
     y = y.contiguous()
     return y if out_f32 else _rt(y, x.dtype)
+
+
+def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0):
+    """Four 2x2 convolutions over the low-resolution input, one per output parity (the documented semantics of
+    pcdm_conv3x3_up2x): plane p = 2 py + px, tap (ty, tx) reads source pixel (i + ty - 1 + py, j + tx - 1 + px)."""
+    B, H, W, Cin = x.shape
+    Cout = w_up.shape[1]
+    xin = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))            # source rows / columns -1 .. H / W
+    y = x.new_zeros((B, 2 * H, 2 * W, Cout), dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            wk = w_up[2 * py + px].float().view(Cout, 2, 2, Cin).permute(0, 3, 1, 2)
+            o = F.conv2d(xin[:, :, py:py + H + 1, px:px + W + 1], wk, bias)
+            y[:, py::2, px::2] = o.permute(0, 2, 3, 1)
+    if silu:
+        y = F.silu(y)
+    return _rt(y.contiguous(), x.dtype)
 
 
 def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None):
@@ -294,7 +311,7 @@ def require_cuda(t, what):
     return None
 
 
-_NAMES = ["ensure_workspace", "require_cuda", "row_stats", "gemm", "ln_gemm", "conv3x3", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
+_NAMES = ["ensure_workspace", "require_cuda", "row_stats", "gemm", "ln_gemm", "conv3x3", "conv3x3_up2x", "groupnorm", "layernorm", "attention", "nchw_to_nhwc_pad", "nhwc_to_nchw",
           "timestep_embedding", "upsample_nearest2x", "cfg_ddim_step", "cfg_rescale_ratio", "cfg_combine", "add_noise", "ddim_step", "cfg_unipc_step",
           "unipc_step", "softmax_rows", "gaussian_sample", "cfg_unclip_step", "unclip_step"]
 
