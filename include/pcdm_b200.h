@@ -81,6 +81,16 @@ typedef struct pcdm_ext {
   const float* ln_stats;
   int ln_parts;
   float ln_eps;
+  /* ---- GroupNorm statistics out of the producing conv / GEMM epilogue (the "conv3x3 + bias + GroupNorm" fusion of the
+   *      north star: diffusers ResnetBlock2D norm1/norm2, Transformer2DModel.norm, conv_norm_out).
+   *   chan_stats != NULL (pcdm_gemm / pcdm_conv3x3 / pcdm_conv3x3_up2x, 16-bit output, no GEGLU): the epilogue also
+   *   writes, for every 32-row slab of the output and every channel, (sum, sum of squares) of the 16-bit values AS
+   *   STORED: chan_stats[slab][N][2] fp32, slab = row / 32, ceil(M / 32) slabs (pcdm_conv3x3_up2x: an image's slabs are
+   *   [parity plane][32 low-resolution pixels], still contiguous per image).  The rows of a slab must belong to one
+   *   image: rows_per_image (pcdm_gemm) / H*W % 32 == 0.  Deterministic (fixed reduction order); also produced on the
+   *   split-K route.  pcdm_groupnorm_apply consumes it: GroupNorm then costs one read + one write of the activation
+   *   and no pass for the statistics. ---- */
+  float* chan_stats;
 } pcdm_ext;
 
 int pcdm_abi_version(void);
@@ -149,6 +159,15 @@ int pcdm_conv3x3_up2x(const void* x, const void* w_up, void* out, const float* b
 long long pcdm_groupnorm_workspace_bytes(int B, int groups);
 int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, const float* gamma, const float* beta, float eps,
                    int B, int HW, int C, int groups, int dtype, int flags, void* workspace, void* stream);
+
+/* GroupNorm (+ SiLU) of x = [x1 | x2] whose statistics were already emitted by the producers of x1 / x2
+ * (pcdm_ext.chan_stats): y = (x - mean[b, g]) * rstd[b, g] * gamma + beta, one streaming read + write; each CTA first
+ * folds the per-slab partial sums of its channel groups (fp64, fixed order).  stats1 / stats2: [B * HW / 32][C1 or C - C1][2]
+ * fp32 (stats2 NULL when x2 is NULL).  HW % 32 == 0, C % groups == 0, C % 8 == 0, C1 % 8 == 0.  workspace: as
+ * pcdm_groupnorm (its first B * groups * 8 bytes hold the folded (mean, rstd)).  flags: PCDM_FLAG_SILU. */
+int pcdm_groupnorm_apply(const void* x1, const float* stats1, const void* x2, const float* stats2, int C1, void* y,
+                         const float* gamma, const float* beta, float eps, int B, int HW, int C, int groups, int dtype,
+                         int flags, void* workspace, void* stream);
 
 /* torch.nn.LayerNorm(C, eps) over rows; replaces norm1/norm2/norm3 of BasicTransformerBlock. */
 int pcdm_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,

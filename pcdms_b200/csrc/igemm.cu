@@ -73,6 +73,9 @@ struct IGemmParams {
   const float2* ln_stats;   // consumer: LayerNorm folded into this GEMM — the rows arrive raw, W was pre-scaled by gamma
   int ln_parts;             //   AND row-centred (sum_k W'[n,k] = 0, so the mean cancels inside the accumulation):
   float ln_eps, ln_inv_k;   //   out = rstd[m] * acc + bias[n]   (bias[n] carries W . beta), rstd from the producer's sums
+  // ---- GroupNorm statistics of the output (pcdm_ext.chan_stats): per 32-row slab and per channel, (sum, sum of
+  //      squares) of the 16-bit values as stored: [slabs][N][2] fp32.  Rows of a slab belong to one image (H*W % 32 == 0).
+  float* chan_stats;
 };
 
 template <int BN, int CG>
@@ -490,6 +493,38 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           fence_proxy_async();
           __syncwarp();
+          if (p.chan_stats) {
+            // column sums over the warp's 32 rows, read back from the staged (rounded) tile: lane (w, par) takes the two
+            // columns of 32-bit word w from rows par, par + 2, ... — even rows sit in banks 0-15, odd rows in 16-31, so
+            // the 16 loads are conflict-free; one xor-16 shuffle folds the two row parities (fixed order)
+            const int w = lane & 15, par = lane >> 4;
+            const int rows_ok = p.M - m_warp0;   // rows of this slab that exist (>= 32: all)
+            float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = 2 * i + par;
+              uint32_t word;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sl_s + sw64(r, w >> 2) + (uint32_t)(w & 3) * 4u));
+              if (r < rows_ok) {
+                const float2 f = unpack2<DT>(word);
+                cs = __fadd2_rn(cs, f);
+                cq = __ffma2_rn(f, f, cq);
+              }
+            }
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16);
+            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cq.x += __shfl_xor_sync(0xffffffffu, cq.x, 16);
+            cq.y += __shfl_xor_sync(0xffffffffu, cq.y, 16);
+            if (par == 0 && rows_ok > 0) {
+              long long slab = m_warp0 >> 5;
+              if (p.mode == 4) {   // an image's slabs stay contiguous: [image][parity plane][32-pixel slab of the plane]
+                const int hw = p.H * p.W;
+                const int bw = m_warp0 / hw;
+                slab = (long long)bw * (hw >> 3) + (long long)split * (hw >> 5) + ((m_warp0 - bw * hw) >> 5);
+              }
+              *reinterpret_cast<float4*>(p.chan_stats + (slab * p.N + n0 + 2 * w) * 2) = make_float4(cs.x, cq.x, cs.y, cq.y);
+            }
+          }
           if (lane == 0 && !IG_DBG(p, 1)) {
             if (p.mode == 4) {   // the warp's 32 low-resolution pixels land on every second pixel of every second row
               const int hw = p.H * p.W;
@@ -577,20 +612,27 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 }
 
 // Split-K finish: out[m, n] = act( sum_s part[s][m][n] + bias[n] + rowvec[m / hw][n] + residual[m][n] ), fixed
-// summation order (bit-reproducible); 8 columns per thread.
+// summation order (bit-reproducible).  One CTA per (32-row slab, 256-column block): thread (cx, ry) owns 8 columns of
+// rows ry, ry + 8, ry + 16, ry + 24 of the slab, so the slab's per-channel (sum, sum of squares) — the GroupNorm
+// statistics of the next op, pcdm_ext.chan_stats — fall out of a fixed-order fold over the 8 row lanes.
 template <int DT>
-__global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      const float* __restrict__ bias, const float* __restrict__ rowvec,
                                      long long ld_rowvec, int hw, const void* __restrict__ residual, long long ldr,
-                                     void* __restrict__ out, long long ldo, int silu) {
+                                     void* __restrict__ out, long long ldo, int silu, float* __restrict__ chan_stats) {
   using T = typename TypeOf<DT>::T;
+  __shared__ float red[8][32][16];
   pdl_launch_dependents();
   pdl_wait();
-  const int nv = N / 8;
-  const long long total = (long long)M * nv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n0 = (int)(i % nv) * 8;
-    const long long m = i / nv;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int n0 = (blockIdx.y * 32 + cx) * 8;
+  const bool col_ok = n0 < N;
+  float cs[8], cq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  for (int k = 0; k < 4 && col_ok; ++k) {
+    const long long m = (long long)blockIdx.x * 32 + ry + 8 * k;
+    if (m >= M) break;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -626,6 +668,30 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
     uint4 o;
     o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
     *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
+    if (chan_stats) {   // statistics of the values as stored (rounded)
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2<DT>(ow[j]);
+        cs[2 * j] += f.x; cs[2 * j + 1] += f.y;
+        cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]); cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]);
+      }
+    }
+  }
+  if (!chan_stats) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[ry][cx][2 * j] = cs[j]; red[ry][cx][2 * j + 1] = cq[j]; }
+  __syncthreads();
+  if (ry == 0 && col_ok) {
+    float t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = red[0][cx][j];
+    for (int r = 1; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] += red[r][cx][j];
+    float4* dst = reinterpret_cast<float4*>(chan_stats + ((long long)blockIdx.x * N + n0) * 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
   }
 }
 
@@ -704,6 +770,7 @@ struct ExtArgs {   // what the caller's pcdm_ext carries (all optional)
   const float* ln_stats = nullptr;   // consumer side
   int ln_parts = 0;
   float ln_eps = 0.f;
+  float* chan_stats = nullptr;  // GroupNorm statistics of the output, per 32-row slab and channel
   pcdm_ext* raw = nullptr;      // for the output field row_stats_parts
 };
 
@@ -731,6 +798,10 @@ static int read_ext(pcdm_ext* ext, ExtArgs* e) {
     e->ln_stats = ext->ln_stats;
     e->ln_parts = ext->ln_parts;
     e->ln_eps = ext->ln_eps;
+  }
+  if (ext->chan_stats) {
+    if (reinterpret_cast<uintptr_t>(ext->chan_stats) & 15) return set_error(PCDM_ERR_INVALID, "pcdm_ext: chan_stats must be 16-byte aligned");
+    e->chan_stats = ext->chan_stats;
   }
   e->raw = ext;
   return 0;
@@ -769,6 +840,11 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   }
   if (ext.row_stats && (p.out_f32 || p.geglu))
     return set_error(PCDM_ERR_UNSUPPORTED, "gemm: row statistics come with the plain 16-bit-output epilogue only");
+  if (ext.chan_stats) {
+    if (p.out_f32 || p.geglu) return set_error(PCDM_ERR_UNSUPPORTED, "channel statistics come with the plain 16-bit-output epilogue only");
+    if (p.hw % 32) return set_error(PCDM_ERR_UNSUPPORTED, "channel statistics need rows-per-image (H*W) to be a multiple of 32");
+    p.chan_stats = ext.chan_stats;   // cleared again below when split-K hands the epilogue to the finishing kernel
+  }
   if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats && planes == 1) {   // K >= 4096: below, one launch wins
     const int sbn = (p.N % 160 == 0) ? 160 : 128;
     const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
@@ -783,7 +859,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
         bn = sbn;
         p.splits = splits;
         p.kb_per_split = kbps;
-        p.bias = nullptr; p.rowvec = nullptr; p.silu = 0;
+        p.bias = nullptr; p.rowvec = nullptr; p.silu = 0; p.chan_stats = nullptr;
         p.out = g_ws; p.ldo = p.N; p.out_f32 = 1;
         residual = nullptr;
       }
@@ -846,17 +922,15 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   }
 #undef PCDM_LAUNCH
   if (rc != 0 || !split) return rc;
-  const long long total = (long long)p.M * (p.N / 8);
-  long long grid = (total + 255) / 256;
-  if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
+  const dim3 fgrid((p.M + 31) / 32, (p.N / 8 + 31) / 32);
   if (dt == DT_F16)
-    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, dim3((int)grid), dim3(256), 0, stream, 1,
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, fgrid, dim3(256), 0, stream, 1,
                             reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
-                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu, ext.chan_stats));
   else
-    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_BF16>, dim3((int)grid), dim3(256), 0, stream, 1,
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_BF16>, fgrid, dim3(256), 0, stream, 1,
                             reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
-                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu, ext.chan_stats));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -445,6 +445,42 @@ layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics from the PRODUCER's epilogue (pcdm_ext.chan_stats: per 32-row slab and channel, (sum, sum of
+// squares) of the stored values) -> (mean, rstd) per (image, group).  One warp per (image, group): lanes stride over
+// the group's (slab, channel) partials in a fixed order, fp64 accumulation, xor-shuffle tree.  The activation itself is
+// not read: the statistics pass of GroupNorm has disappeared into the conv / GEMM that wrote the tensor.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gn_fold_kernel(const float2* __restrict__ st1, const float2* __restrict__ st2,
+                                                      int C1, int C, int slabs_per_image, int groups, int B, int HW,
+                                                      float eps, float2* __restrict__ final_stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= B * groups) return;
+  const int b = item / groups, g = item - b * groups;
+  const int cpg = C / groups, C2 = C - C1;
+  const int total = slabs_per_image * cpg;
+  double a = 0.0, q = 0.0;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int sl = idx / cpg, c = g * cpg + (idx - sl * cpg);
+    const long long slab = (long long)b * slabs_per_image + sl;
+    const float2 v = c < C1 ? __ldg(st1 + slab * C1 + c) : __ldg(st2 + slab * C2 + (c - C1));
+    a += (double)v.x;
+    q += (double)v.y;
+  }
+  a = warp_sum(a);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const double inv_n = 1.0 / ((double)cpg * (double)HW);
+    const double mean = a * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    final_stats[item] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
 // Per-row (sum, sum of squares) of a [M, C] 16-bit matrix: the statistics slot a GEMM with a folded LayerNorm consumes
 // (pcdm_ext.ln_stats with ln_parts = 1) when the rows were NOT produced by one of this library's GEMM epilogues (the
 // custom-attention-processor path).  One warp per row, fixed reduction order.
@@ -629,6 +665,37 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
     PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
                             (const float2*)ws.final_stats, gamma, beta, silu, y));
   }
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_groupnorm_apply(const void* x1, const float* stats1, const void* x2, const float* stats2, int C1,
+                                    void* y, const float* gamma, const float* beta, float eps, int B, int HW, int C,
+                                    int groups, int dtype, int flags, void* workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x1 || !stats1 || !y || !gamma || !beta || !workspace) return set_error(PCDM_ERR_INVALID, "groupnorm_apply: null pointer");
+  if (dtype != DT_F16 && dtype != DT_BF16) return set_error(PCDM_ERR_INVALID, "groupnorm_apply: bad dtype");
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0) return set_error(PCDM_ERR_INVALID, "groupnorm_apply: empty problem");
+  if (C % groups || C % 8 || C > 4096) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm_apply: C must be a multiple of groups and 8, <= 4096");
+  if (HW % 32) return set_error(PCDM_ERR_UNSUPPORTED, "groupnorm_apply: H*W must be a multiple of 32 (statistics come per 32-row slab)");
+  if (!x2) C1 = C;
+  if (C1 % 8 || C1 <= 0 || C1 > C || (x2 && !stats2)) return set_error(PCDM_ERR_INVALID, "groupnorm_apply: bad channel split");
+  if ((reinterpret_cast<uintptr_t>(stats1) | reinterpret_cast<uintptr_t>(stats2)) & 7)
+    return set_error(PCDM_ERR_INVALID, "groupnorm_apply: statistics must be 8-byte aligned");
+  float2* final_stats = reinterpret_cast<float2*>(workspace);   // the first region of a pcdm_groupnorm workspace
+  PCDM_CUDA(launch_kernel(gn_fold_kernel, dim3((B * groups + 3) / 4), dim3(128), 0, stream, 1,
+                          reinterpret_cast<const float2*>(stats1), reinterpret_cast<const float2*>(stats2), C1, C, HW / 32,
+                          groups, B, HW, eps, final_stats));
+  int PY, pix_per_cta, chunks;
+  gn_grid(B, HW, C, &PY, &pix_per_cta, &chunks);
+  const dim3 grid(chunks, B), block(C / 8, PY);
+  const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
+  if (dtype == DT_F16)
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)final_stats, gamma, beta, silu, y));
+  else
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)final_stats, gamma, beta, silu, y));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

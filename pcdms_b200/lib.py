@@ -28,7 +28,7 @@ class Ext(C.Structure):
     _fields_ = [("size", C.c_int), ("force_cta_group", C.c_int), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_longlong), ("row_stats", C.c_void_p), ("row_stats_cap", C.c_int),
                 ("row_stats_parts", C.c_int), ("ln_stats", C.c_void_p), ("ln_parts", C.c_int),
-                ("ln_eps", C.c_float)]
+                ("ln_eps", C.c_float), ("chan_stats", C.c_void_p)]
 
 
 class PcdmError(RuntimeError):

@@ -102,6 +102,23 @@ class RowStats:
         self.buf, self.parts = buf, parts
 
 
+class ChanStats:
+    """Per 32-row slab and per channel (sum, sum of squares) a producing conv / GEMM wrote for the GroupNorm that
+    follows it (pcdm_ext.chan_stats): `buf` [rows / 32, N, 2] fp32; `hw` = rows per image."""
+    __slots__ = ("buf", "hw")
+
+    def __init__(self, buf, hw):
+        self.buf, self.hw = buf, hw
+
+
+def _chan_stats_buf(t, M, N, hw):
+    """The buffer a launch with pcdm_ext.chan_stats fills, or None when the shape cannot carry slab statistics (the
+    rows of a 32-row slab must belong to one image) — the consumer then runs the stand-alone GroupNorm."""
+    if hw % 32 or M % 32:
+        return None
+    return ChanStats(torch.empty((M // 32, N, 2), device=t.device, dtype=torch.float32), hw)
+
+
 class FoldedLN:
     """A LayerNorm folded into the GEMM that consumes it: the producer's RowStats and eps.  The GEMM's weight must be
     `fold_layernorm_weight(...)` (gamma-scaled, rows centred) and its `bias` must carry W . beta."""
@@ -162,10 +179,12 @@ def geglu_row_permutation(n_out: int) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
          out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True, row_stats=False,
-         ln: "FoldedLN | None" = None):
+         ln: "FoldedLN | None" = None, chan_stats=False):
     """out[M, N] = [a | a2][M, K] @ w[N, K]^T (+bias) (+rowvec[m // rows_per_image]) (+residual).
     row_stats=True: also returns the RowStats of the output rows (-> `(out, stats)`), the LayerNorm statistics of the
     next op for free.  ln=FoldedLN(...): `a` holds RAW rows, `w` is gamma-scaled, the LayerNorm happens in the epilogue.
+    chan_stats=True (with rows_per_image = H*W): also returns the ChanStats of the output (-> `(out, stats)`, stats None
+    when the shape cannot carry them), the GroupNorm statistics of the next op for free.
     w_static: `w` holds model weights (not written by the kernel launched just before on this stream); pass False when
     `w` is an activation (the VAE's QK^T / PV products written as GEMMs)."""
     lib = _l.load()
@@ -194,6 +213,12 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     if ln is not None:
         assert ln.stats.buf.shape[1] == M and bias is not None
         ext.ln_stats, ext.ln_parts, ext.ln_eps = ln.stats.buf.data_ptr(), ln.stats.parts, float(ln.eps)
+    cstats = None
+    if chan_stats:
+        assert not row_stats
+        cstats = _chan_stats_buf(a, M, N, rows_per_image)
+        if cstats is not None:
+            ext.chan_stats = cstats.buf.data_ptr()
     rc = lib.pcdm_gemm(
         _l.ptr(a), C.c_longlong(a.stride(0)), _l.ptr(a2), C.c_longlong(a2.stride(0) if a2 is not None else 0),
         C.c_int(k1), _l.ptr(w), _l.ptr(out), C.c_longlong(out.stride(0)), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
@@ -203,6 +228,8 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
     if row_stats:
         stats.parts = int(ext.row_stats_parts)
         return out, stats
+    if chan_stats:
+        return out, cstats
     return out
 
 
@@ -232,9 +259,10 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
 
 
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
-            pad_br=False, bn=0, cta_group=0):
+            pad_br=False, bn=0, cta_group=0, chan_stats=False):
     """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout].
-    pad_br (stride 2 only): zero padding on the bottom/right instead of all round (the VAE encoder's downsampler)."""
+    pad_br (stride 2 only): zero padding on the bottom/right instead of all round (the VAE encoder's downsampler).
+    chan_stats=True: -> `(out, ChanStats | None)`, the GroupNorm statistics of the output from the epilogue."""
     lib = _l.load()
     B, Hin, Win, Cin = x.shape
     Cout = w_packed.shape[0]
@@ -247,14 +275,19 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
         assert residual.is_contiguous() and residual.shape == out.shape
     flags = (_l.FLAG_OUT_F32 if out_f32 else 0) | (_l.FLAG_SILU if silu else 0) | (_l.FLAG_PAD_BR if pad_br else 0)
     ext = _ext(x, cta_group)
+    cstats = None
+    if chan_stats and not out_f32:
+        cstats = _chan_stats_buf(x, B * H * W, Cout, H * W)
+        if cstats is not None:
+            ext.chan_stats = cstats.buf.data_ptr()
     rc = lib.pcdm_conv3x3(_l.ptr(x), _l.ptr(w_packed), _l.ptr(out), _l.ptr(_f32(bias)), _l.ptr(_f32(rowvec)),
                           C.c_longlong(rowvec.stride(0) if rowvec is not None else 0), _l.ptr(residual), C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
                           C.c_int(stride), C.c_int(_dt(x)), C.c_int(flags), C.c_int(bn), C.byref(ext), _stream(x))
     _l.check(rc)
-    return out
+    return (out, cstats) if chan_stats else out
 
 
-def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0):
+def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0, chan_stats=False):
     """Upsample2D: nearest-2x + conv3x3 in one launch.  x: [B, H, W, Cin]; w_up: pack_upsample_conv_weight(...)
     [4, Cout, 4*Cin]; returns [B, 2H, 2W, Cout]."""
     lib = _l.load()
@@ -265,11 +298,16 @@ def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0)
         out = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=x.dtype)
     assert out.is_contiguous() and tuple(out.shape) == (B, 2 * H, 2 * W, Cout)
     ext = _ext(x, cta_group)
+    cstats = None
+    if chan_stats:   # slabs: [image][parity plane][32 low-resolution pixels] — contiguous per image, as the consumer needs
+        if (H * W) % 32 == 0:
+            cstats = ChanStats(torch.empty((4 * B * H * W // 32, Cout, 2), device=x.device, dtype=torch.float32), 4 * H * W)
+            ext.chan_stats = cstats.buf.data_ptr()
     rc = lib.pcdm_conv3x3_up2x(_l.ptr(x), _l.ptr(w_up), _l.ptr(out), _l.ptr(_f32(bias)), C.c_int(B), C.c_int(H),
                                C.c_int(W), C.c_int(Cin), C.c_int(Cout), C.c_int(_dt(x)),
                                C.c_int(_l.FLAG_SILU if silu else 0), C.c_int(bn), C.byref(ext), _stream(x))
     _l.check(rc)
-    return out
+    return (out, cstats) if chan_stats else out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -290,9 +328,12 @@ def _gn_workspace(device, B, groups):
     return ws
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None):
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None,
+              stats=None):
     """x1: [B, ..., C1] NHWC (x2 optional second channel segment); returns [B, ..., C1+C2].
-    path: None (automatic), "two_pass" or "one_pass" (tests)."""
+    path: None (automatic), "two_pass" or "one_pass" (tests).
+    stats=(ChanStats of x1, ChanStats of x2 | None): the statistics came out of the producers' epilogues — no pass over
+    the activation for them (pcdm_groupnorm_apply); ignored (stand-alone kernels) when either is None."""
     lib = _l.load()
     lib.pcdm_groupnorm_workspace_bytes.restype = C.c_longlong
     B = x1.shape[0]
@@ -304,6 +345,16 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None,
         out = torch.empty((*x1.shape[:-1], Ct), device=x1.device, dtype=x1.dtype)
     if workspace is None:
         workspace = _gn_workspace(x1.device, B, groups)
+    if stats is not None and stats[0] is not None and (x2 is None or stats[1] is not None) and HW % 32 == 0:
+        s1, s2 = stats[0], (stats[1] if x2 is not None else None)
+        assert s1.hw == HW and s1.buf.shape == (B * HW // 32, C1, 2)
+        assert s2 is None or (s2.hw == HW and s2.buf.shape == (B * HW // 32, Ct - C1, 2))
+        rc = lib.pcdm_groupnorm_apply(_l.ptr(x1), _l.ptr(s1.buf), _l.ptr(x2), _l.ptr(s2.buf if s2 is not None else None),
+                                      C.c_int(C1), _l.ptr(out), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)), C.c_float(eps),
+                                      C.c_int(B), C.c_int(HW), C.c_int(Ct), C.c_int(groups), C.c_int(_dt(x1)),
+                                      C.c_int(_l.FLAG_SILU if silu else 0), _l.ptr(workspace), _stream(x1))
+        _l.check(rc, kernels=2)
+        return out
     rc = lib.pcdm_groupnorm(_l.ptr(x1), _l.ptr(x2), C.c_int(C1), _l.ptr(out), _l.ptr(_f32(gamma)), _l.ptr(_f32(beta)),
                             C.c_float(eps), C.c_int(B), C.c_int(HW), C.c_int(Ct), C.c_int(groups), C.c_int(_dt(x1)),
                             C.c_int((_l.FLAG_SILU if silu else 0) | {None: 0, "two_pass": _l.FLAG_GN_TWO_PASS,

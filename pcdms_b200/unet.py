@@ -15,6 +15,8 @@ What is fused relative to the reference's op-by-op graph:
     producer's epilogue, gamma in the consumer's weights, normalisation in the consumer's epilogue): no LN launches;
   * Upsample2D (nearest-2x + conv3x3) is one launch of four per-parity 2x2 convolutions over the low-resolution
     tensor: the 4x tensor is never written and the layer costs 16/36 of the MACs;
+  * GroupNorm statistics come out of the epilogue of the conv / GEMM that PRODUCES the tensor (per-channel sums per
+    32-row slab, folded per (image, group) by a one-warp-per-group kernel): GroupNorm is one read + one write pass;
   * the skip concat of the up blocks is never materialised (GroupNorm and the 1x1 shortcut read both sources);
   * cross-attention K/V depend only on encoder_hidden_states: computed once per conditioning, not once per step.
 """
@@ -662,8 +664,11 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         for p, _, cout in self._resnets:
             temb_off[p] = (off, cout)
             off += cout
+        # Every producer of a GroupNorm input (conv_in, conv1 / conv2 of the resnets, the transformers' proj_out, the
+        # down / up sampler convs) also emits per-channel (sum, sum of squares) from its epilogue; activations travel as
+        # (tensor, ChanStats) pairs — skips included — and GroupNorm never reads a tensor for its statistics.
         # conv_in (+ pose) (reference :742)
-        x = ops.conv3x3(x_in, w["conv_in.weight"], bias=w["conv_in.bias"], residual=pose)
+        x = ops.conv3x3(x_in, w["conv_in.weight"], bias=w["conv_in.bias"], residual=pose, chan_stats=True)
         skips = [x]
         x_skip = None
         for op in self._plan:
@@ -680,34 +685,40 @@ class B200UNet2DConditionModel(WeightArenaMixin):
             elif kind == "pop":
                 x_skip = skips.pop()
             elif kind == "down":
-                x = ops.conv3x3(x, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], stride=2)
+                x = ops.conv3x3(x[0], w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], stride=2, chan_stats=True)
             elif kind == "up":
-                x = ops.conv3x3_up2x(x, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"])
-        hn = ops.groupnorm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], cfg.norm_eps, silu=True)
+                x = ops.conv3x3_up2x(x[0], w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], chan_stats=True)
+        hn = ops.groupnorm(x[0], w["conv_norm_out.weight"], w["conv_norm_out.bias"], cfg.norm_eps, silu=True,
+                           stats=(x[1], None))
         return ops.conv3x3(hn, w["conv_out.weight"], bias=w["conv_out.bias"], out_f32=True)
 
-    def _resnet(self, p, x, x_skip, temb, cin, cout):
+    def _resnet(self, p, xs, skip, temb, cin, cout):
+        """xs / skip: (tensor, ChanStats) pairs; returns one."""
         w, eps = self._w, self.config.norm_eps
+        x, x_st = xs
+        x_skip, skip_st = skip if skip is not None else (None, None)
         B, H, W, c1 = x.shape
         M = B * H * W
-        h = ops.groupnorm(x, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], eps, x2=x_skip, silu=True)
-        h = ops.conv3x3(h, w[f"{p}.conv1.weight"], bias=w[f"{p}.conv1.bias"], rowvec=temb)
-        h = ops.groupnorm(h, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], eps, silu=True)
+        h = ops.groupnorm(x, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], eps, x2=x_skip, silu=True,
+                          stats=(x_st, skip_st))
+        h, h_st = ops.conv3x3(h, w[f"{p}.conv1.weight"], bias=w[f"{p}.conv1.bias"], rowvec=temb, chan_stats=True)
+        h = ops.groupnorm(h, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], eps, silu=True, stats=(h_st, None))
         if cin != cout:
             res = ops.gemm(x.view(M, c1), w[f"{p}.conv_shortcut.weight"],
                            a2=x_skip.view(M, -1) if x_skip is not None else None, bias=w[f"{p}.conv_shortcut.bias"])
             res = res.view(B, H, W, cout)
         else:
             res = x
-        return ops.conv3x3(h, w[f"{p}.conv2.weight"], bias=w[f"{p}.conv2.bias"], residual=res)
+        return ops.conv3x3(h, w[f"{p}.conv2.weight"], bias=w[f"{p}.conv2.bias"], residual=res, chan_stats=True)
 
-    def _transformer(self, p, x, kv, C, heads):
+    def _transformer(self, p, xs, kv, C, heads):
         w = self._w
+        x, x_st = xs
         B, H, W, _ = x.shape
         S = H * W
         M = B * S
         t = f"{p}.transformer_blocks.0"
-        hn = ops.groupnorm(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], 1e-6, silu=False)
+        hn = ops.groupnorm(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], 1e-6, silu=False, stats=(x_st, None))
         # The three LayerNorms of the block never run as passes of their own: each GEMM that PRODUCES the hidden
         # states also emits per-row (sum, sum of squares) from its epilogue, each GEMM that CONSUMES the normalised
         # rows reads the raw rows with gamma folded into its weights and finishes the normalisation in its epilogue.
@@ -741,5 +752,6 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         # feed-forward (LayerNorm + GEGLU both in the first GEMM's epilogue)
         g = ops.gemm(h, w[f"{t}.ff.net.0.proj_ln.weight"], geglu=True, **folded(f"{t}.ff.net.0.proj_ln", st))
         h = ops.gemm(g, w[f"{t}.ff.net.2.weight"], bias=w[f"{t}.ff.net.2.bias"], residual=h)
-        out = ops.gemm(h, w[f"{p}.proj_out.weight"], bias=w[f"{p}.proj_out.bias"], residual=x.view(M, C))
-        return out.view(B, H, W, C)
+        out, o_st = ops.gemm(h, w[f"{p}.proj_out.weight"], bias=w[f"{p}.proj_out.bias"], residual=x.view(M, C),
+                             rows_per_image=S, chan_stats=True)
+        return out.view(B, H, W, C), o_st

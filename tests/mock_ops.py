@@ -17,9 +17,23 @@ def _rt(x, dtype):
     return x.to(dtype)
 
 
+def _chan_stats_of(y_rows, hw, order=None):
+    """pcdm_ext.chan_stats of stored rows y [M, N]: [M / 32, N, 2] (sum, sum of squares) per 32-row slab, or None when
+    the shape cannot carry them; `order` permutes the rows first (the slab order of pcdm_conv3x3_up2x)."""
+    from pcdms_b200.ops import ChanStats
+    M, N = y_rows.shape
+    if hw % 32 or M % 32:
+        return None
+    yf = y_rows.float()
+    if order is not None:
+        yf = yf[order]
+    yf = yf.view(M // 32, 32, N)
+    return ChanStats(torch.stack([yf.sum(1), (yf ** 2).sum(1)], dim=-1).contiguous(), hw)
+
+
 def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, residual=None, geglu=False,
          out_f32=False, silu=False, gelu=False, bn=0, w_static=True, cta_group=0, skinny=True, row_stats=False,
-         ln=None):
+         ln=None, chan_stats=False):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().t()
     if ln is not None:   # pcdm_ext.ln_*: out = rstd * acc + bias (row-centred weight), rstd from the producer's sums
@@ -56,6 +70,8 @@ def gemm(a, w, out=None, *, a2=None, bias=None, rowvec=None, rows_per_image=1, r
         buf = torch.stack([torch.stack([yf[:, :half].sum(1), (yf[:, :half] ** 2).sum(1)], dim=1),
                            torch.stack([yf[:, half:].sum(1), (yf[:, half:] ** 2).sum(1)], dim=1)])
         return y, RowStats(buf, 2)
+    if chan_stats:
+        return y, _chan_stats_of(y, rows_per_image)
     return y
 
 
@@ -67,7 +83,7 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
 
 
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
-            pad_br=False, bn=0, cta_group=0):
+            pad_br=False, bn=0, cta_group=0, chan_stats=False):
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     w = w_packed.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
@@ -84,10 +100,13 @@ def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, str
     if silu:
         y = F.silu(y)
     y = y.contiguous()
-    return y if out_f32 else _rt(y, x.dtype)
+    y = y if out_f32 else _rt(y, x.dtype)
+    if chan_stats:
+        return y, (None if out_f32 else _chan_stats_of(y.reshape(-1, Cout), y.shape[1] * y.shape[2]))
+    return y
 
 
-def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0):
+def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0, chan_stats=False):
     """Four 2x2 convolutions over the low-resolution input, one per output parity (the documented semantics of
     pcdm_conv3x3_up2x): plane p = 2 py + px, tap (ty, tx) reads source pixel (i + ty - 1 + py, j + tx - 1 + px)."""
     B, H, W, Cin = x.shape
@@ -101,12 +120,39 @@ def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0)
             y[:, py::2, px::2] = o.permute(0, 2, 3, 1)
     if silu:
         y = F.silu(y)
-    return _rt(y.contiguous(), x.dtype)
+    y = _rt(y.contiguous(), x.dtype)
+    if chan_stats:
+        if (H * W) % 32:
+            return y, None
+        # slab order of the kernel: [image][parity plane 2 py + px][32 low-resolution pixels]
+        planes = torch.stack([y[:, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=1)   # [B, 4, H, W, Cout]
+        return y, _chan_stats_of(planes.reshape(-1, Cout), 4 * H * W)
+    return y
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None):
+def groupnorm(x1, gamma, beta, eps, *, x2=None, groups=32, silu=False, out=None, workspace=None, path=None,
+              stats=None):
     x = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
     shp = x.shape
+    B, Ct = shp[0], shp[-1]
+    HW = x.numel() // (B * Ct)
+    if stats is not None and stats[0] is not None and (x2 is None or stats[1] is not None) and HW % 32 == 0:
+        # pcdm_groupnorm_apply: (mean, rstd) per (image, group) folded from the PRODUCERS' slab statistics — the mock
+        # really uses them, so a host-side mix-up (stale or foreign statistics) shows up in the CPU tests
+        srcs = [stats[0]] + ([stats[1]] if x2 is not None else [])
+        assert all(s_.hw == HW and s_.buf.shape[0] == B * HW // 32 for s_ in srcs)
+        per_img = torch.cat([s_.buf.view(B, HW // 32, -1, 2).double().sum(1) for s_ in srcs], dim=1)   # [B, Ct, 2]
+        g = per_img.view(B, groups, Ct // groups, 2).sum(2)
+        n = (Ct // groups) * HW
+        mean = g[..., 0] / n
+        rstd = torch.rsqrt((g[..., 1] / n - mean * mean).clamp_min(0) + eps)
+        cpg = Ct // groups
+        xf = x.float().reshape(B, HW, groups, cpg)
+        y = (xf - mean.float()[:, None, :, None]) * rstd.float()[:, None, :, None]
+        y = y.reshape(B, HW, Ct) * gamma + beta
+        if silu:
+            y = F.silu(y)
+        return _rt(y.reshape(shp).contiguous(), x1.dtype)
     y = F.group_norm(x.float().reshape(shp[0], -1, shp[-1]).transpose(1, 2), groups, gamma, beta, eps)
     if silu:
         y = F.silu(y)

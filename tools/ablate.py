@@ -27,7 +27,14 @@ ctx = torch.randn(B, 258, 1024, device=dev).to(dt)
 cls = torch.randn(B, 1024, device=dev).to(dt)
 pose = (0.1 * torch.randn(B, h, w, 320, device=dev)).to(dt)
 kv = m.context_kv(ctx)
-real = {n: getattr(ops, n) for n in ["gemm", "conv3x3", "groupnorm", "layernorm", "attention", "upsample_nearest2x"]}
+real = {n: getattr(ops, n) for n in ["gemm", "conv3x3", "conv3x3_up2x", "groupnorm", "layernorm", "attention"]}
+
+
+def _fake_chan_stats(out, hw):
+    M, N = out.numel() // out.shape[-1], out.shape[-1]
+    if hw % 32:
+        return None
+    return ops.ChanStats(torch.ones((M // 32, N, 2), device=out.device, dtype=torch.float32), hw)
 
 
 def _empty_like_result(name, args, kw):
@@ -39,12 +46,19 @@ def _empty_like_result(name, args, kw):
         out = torch.empty((a.shape[0], n), device=a.device, dtype=torch.float32 if kw.get("out_f32") else a.dtype)
         if kw.get("row_stats"):
             return out, ops.RowStats(torch.ones((2, a.shape[0], 2), device=a.device, dtype=torch.float32), 2)
+        if kw.get("chan_stats"):
+            return out, _fake_chan_stats(out, kw.get("rows_per_image", 1))
         return out
     if name == "conv3x3":
         x, wgt = args[0], args[1]
         s = kw.get("stride", 1)
-        return torch.empty((x.shape[0], x.shape[1] // s, x.shape[2] // s, wgt.shape[0]), device=x.device,
-                           dtype=torch.float32 if kw.get("out_f32") else x.dtype)
+        out = torch.empty((x.shape[0], x.shape[1] // s, x.shape[2] // s, wgt.shape[0]), device=x.device,
+                          dtype=torch.float32 if kw.get("out_f32") else x.dtype)
+        return (out, _fake_chan_stats(out, out.shape[1] * out.shape[2])) if kw.get("chan_stats") else out
+    if name == "conv3x3_up2x":
+        x, wgt = args[0], args[1]
+        out = torch.empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], wgt.shape[1]), device=x.device, dtype=x.dtype)
+        return (out, _fake_chan_stats(out, out.shape[1] * out.shape[2])) if kw.get("chan_stats") else out
     if name == "groupnorm":
         x1, x2 = args[0], kw.get("x2")
         c = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
@@ -98,7 +112,8 @@ cases = [
     ("no layernorm", {"layernorm": skipper("layernorm")}),
     ("no attention", {"attention": skipper("attention")}),
     ("no self-attention 2048", {"attention": skipper("attention", lambda a, k: a[0].shape[0] // a[3] == 2048 and a[1].shape[0] // a[3] == 2048)}),
-    ("no conv3x3", {"conv3x3": skipper("conv3x3")}),
+    ("no conv3x3", {"conv3x3": skipper("conv3x3"), "conv3x3_up2x": skipper("conv3x3_up2x")}),
+    ("no Upsample2D convs", {"conv3x3_up2x": skipper("conv3x3_up2x")}),
     ("no conv3x3 at 32x64", {"conv3x3": skipper("conv3x3", lambda a, k: a[0].shape[1] == 32)}),
     ("no conv3x3 at 16x32", {"conv3x3": skipper("conv3x3", lambda a, k: a[0].shape[1] == 16)}),
     ("no conv3x3 at 8x16", {"conv3x3": skipper("conv3x3", lambda a, k: a[0].shape[1] == 8)}),
@@ -110,7 +125,7 @@ cases = [
     ("no gemm with M = 8192", {"gemm": skipper("gemm", lambda a, k: a[0].shape[0] == 8192)}),
     ("no gemm with M = 2048", {"gemm": skipper("gemm", lambda a, k: a[0].shape[0] == 2048)}),
     ("no gemm with M <= 512", {"gemm": skipper("gemm", lambda a, k: a[0].shape[0] <= 512)}),
-    ("nothing but launches skipped: all", {n: skipper(n) for n in ["gemm", "conv3x3", "groupnorm", "layernorm", "attention"]}),
+    ("nothing but launches skipped: all", {n: skipper(n) for n in ["gemm", "conv3x3", "conv3x3_up2x", "groupnorm", "layernorm", "attention"]}),
 ]
 res = {}
 full = None
