@@ -105,16 +105,25 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 u) {
 __device__ __forceinline__ float2 ln_row_rstd(const IGemmParams& p, long long m, bool valid) {
   float sum = 0.f, sq = 0.f;
   if (valid) {
-    for (int i = 0; i < p.ln_parts; ++i) {
-      const float2 t = __ldg(p.ln_stats + (long long)i * p.M + m);
-      sum += t.x;
-      sq += t.y;
+    for (int i0 = 0; i0 < p.ln_parts; i0 += 4) {   // four independent loads in flight (a dependent chain of L2
+      float2 t[4];                                 // latencies per tile sat on the epilogue's critical path otherwise)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        t[j] = (i0 + j < p.ln_parts) ? __ldg(p.ln_stats + (long long)(i0 + j) * p.M + m) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sum += t[j].x; sq += t[j].y; }
     }
   }
   const float mean = sum * p.ln_inv_k;
   const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
   const float rstd = rsqrtf(var + p.ln_eps);
   return make_float2(rstd, rstd);
+}
+// ... and the NEXT tile's statistics are pulled into L1 while this tile's epilogue runs (no registers held)
+__device__ __forceinline__ void ln_prefetch(const IGemmParams& p, long long m) {
+  if (m < p.M)
+    for (int i = 0; i < p.ln_parts; ++i)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_stats + (long long)i * p.M + m));
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
@@ -343,6 +352,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     uint32_t acc_phase = 0;
     const int nbuf = p.nbuf;
     const uint32_t tempty_addr[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+    auto next_tile_row = [&](int t) -> long long {   // this thread's output row in tile t (>= M when there is none)
+      if (t >= total_tiles) return (long long)p.M;
+      const int mn_ = t % mn_tiles;
+      return (long long)((mn_ / p.n_tiles) * CG + (int)rank) * 128 + row;
+    };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int m_blk = mn / p.n_tiles, n_blk = mn % p.n_tiles;
@@ -402,7 +416,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         //      GEMM — K = 320..1280, ~1 us of MMAs per tile — was bound by exactly that latency chain). ----
         const bool use_res = p.has_res && !IG_DBG(p, 2);
         float2 ln_rstd2 = make_float2(1.f, 1.f);
-        if (p.ln_stats) ln_rstd2 = ln_row_rstd(p, m, valid);   // global loads overlap the tile's MMAs
+        if (p.ln_stats) {
+          ln_rstd2 = ln_row_rstd(p, m, valid);
+          ln_prefetch(p, next_tile_row(tile + tile_step));
+        }
         float2 st_sum = make_float2(0.f, 0.f), st_sq = make_float2(0.f, 0.f);
         if (use_res) {
           if (lane == 0) {
@@ -542,7 +559,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       } else {
         // ---- GEGLU: weight rows were packed as groups of [32 value | 32 gate]; out[:, g*32 + j] = val * gelu(gate) ----
         float2 ln_rstd2 = make_float2(1.f, 1.f);   // stays 1 without a folded LayerNorm: rstd * acc + bias == acc + bias
-        if (p.ln_stats) ln_rstd2 = ln_row_rstd(p, m, valid);
+        if (p.ln_stats) {
+          ln_rstd2 = ln_row_rstd(p, m, valid);
+          ln_prefetch(p, next_tile_row(tile + tile_step));
+        }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -630,17 +650,40 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   float cs[8], cq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  for (int k = 0; k < 4 && col_ok; ++k) {
-    const long long m = (long long)blockIdx.x * 32 + ry + 8 * k;
-    if (m >= M) break;
+  // the four rows' partial sums first, with all their loads independent (8 x 32-byte loads in flight per split step)
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const long long m_first = (long long)blockIdx.x * 32 + ry;
+  if (col_ok) {
+    for (int sidx = 0; sidx < splits; ++sidx) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long m = m_first + 8 * k;
+        a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M) {
+          const float4* pp = reinterpret_cast<const float4*>(part + ((long long)sidx * M + m) * N + n0);
+          a[k] = __ldg(pp);
+          b[k] = __ldg(pp + 1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[k][0] += a[k].x; acc[k][1] += a[k].y; acc[k][2] += a[k].z; acc[k][3] += a[k].w;
+        acc[k][4] += b[k].x; acc[k][5] += b[k].y; acc[k][6] += b[k].z; acc[k][7] += b[k].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long m = m_first + 8 * k;
+    if (!col_ok || m >= M) continue;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    for (int sidx = 0; sidx < splits; ++sidx) {
-      const float4* pp = reinterpret_cast<const float4*>(part + ((long long)sidx * M + m) * N + n0);
-      const float4 a = __ldg(pp), b = __ldg(pp + 1);
-      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = acc[k][j];
     if (bias) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n0)), b = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;

@@ -447,8 +447,8 @@ layernorm_kernel(const void* __restrict__ x, long long ldx, void* __restrict__ y
 
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics from the PRODUCER's epilogue (pcdm_ext.chan_stats: per 32-row slab and channel, (sum, sum of
-// squares) of the stored values) -> (mean, rstd) per (image, group).  One warp per (image, group): lanes stride over
-// the group's (slab, channel) partials in a fixed order, fp64 accumulation, xor-shuffle tree.  The activation itself is
+// squares) of the stored values) -> (mean, rstd) per (image, group).  One 128-thread CTA per (image, group): threads
+// stride over the group's (slab, channel) partials in a fixed order, fp64 accumulation, fixed tree.  The activation itself is
 // not read: the statistics pass of GroupNorm has disappeared into the conv / GEMM that wrote the tensor.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gn_fold_kernel(const float2* __restrict__ st1, const float2* __restrict__ st2,
@@ -456,26 +456,38 @@ __global__ void __launch_bounds__(128) gn_fold_kernel(const float2* __restrict__
                                                       float eps, float2* __restrict__ final_stats) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ double red[2][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * 4 + warp;
-  if (item >= B * groups) return;
+  const int item = blockIdx.x;                 // one CTA per (image, group): the fold is latency-, not bandwidth-bound
   const int b = item / groups, g = item - b * groups;
   const int cpg = C / groups, C2 = C - C1;
   const int total = slabs_per_image * cpg;
   double a = 0.0, q = 0.0;
-  for (int idx = lane; idx < total; idx += 32) {
-    const int sl = idx / cpg, c = g * cpg + (idx - sl * cpg);
-    const long long slab = (long long)b * slabs_per_image + sl;
-    const float2 v = c < C1 ? __ldg(st1 + slab * C1 + c) : __ldg(st2 + slab * C2 + (c - C1));
-    a += (double)v.x;
-    q += (double)v.y;
+  for (int base = 0; base < total; base += 4 * 128) {   // four independent loads in flight per thread
+    float2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * 128 + (int)threadIdx.x;
+      v[j] = make_float2(0.f, 0.f);
+      if (idx < total) {
+        const int sl = idx / cpg, c = g * cpg + (idx - sl * cpg);
+        const long long slab = (long long)b * slabs_per_image + sl;
+        v[j] = c < C1 ? __ldg(st1 + slab * C1 + c) : __ldg(st2 + slab * C2 + (c - C1));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a += (double)v[j].x; q += (double)v[j].y; }
   }
   a = warp_sum(a);
   q = warp_sum(q);
-  if (lane == 0) {
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double sa = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
+    const double sq = ((red[1][0] + red[1][1]) + red[1][2]) + red[1][3];
     const double inv_n = 1.0 / ((double)cpg * (double)HW);
-    const double mean = a * inv_n;
-    double var = q * inv_n - mean * mean;
+    const double mean = sa * inv_n;
+    double var = sq * inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     final_stats[item] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
@@ -683,7 +695,7 @@ extern "C" int pcdm_groupnorm_apply(const void* x1, const float* stats1, const v
   if ((reinterpret_cast<uintptr_t>(stats1) | reinterpret_cast<uintptr_t>(stats2)) & 7)
     return set_error(PCDM_ERR_INVALID, "groupnorm_apply: statistics must be 8-byte aligned");
   float2* final_stats = reinterpret_cast<float2*>(workspace);   // the first region of a pcdm_groupnorm workspace
-  PCDM_CUDA(launch_kernel(gn_fold_kernel, dim3((B * groups + 3) / 4), dim3(128), 0, stream, 1,
+  PCDM_CUDA(launch_kernel(gn_fold_kernel, dim3(B * groups), dim3(128), 0, stream, 1,
                           reinterpret_cast<const float2*>(stats1), reinterpret_cast<const float2*>(stats2), C1, C, HW / 32,
                           groups, B, HW, eps, final_stats));
   int PY, pix_per_cta, chunks;

@@ -204,7 +204,7 @@ def test_groupnorm_statistics_from_producer_epilogues(ops, dt):
     got = ops.groupnorm(xa, gamma.cuda(), beta.cuda(), 1e-5, x2=xb, silu=True, stats=(s1, s5))
     ref = F.silu(F.group_norm(torch.cat([xa, xb], -1).float().cpu().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
     close(got.permute(0, 3, 1, 2), ref, dt)
-    close(got, ops.groupnorm(xa, gamma.cuda(), beta.cuda(), 1e-5, x2=xb, silu=True), dt)      # the stand-alone path
+    close(got, ops.groupnorm(xa, gamma.cuda(), beta.cuda(), 1e-5, x2=xb, silu=True).cpu(), dt)   # the stand-alone path
     y6, s6 = ops.conv3x3(x.cuda(), rnd(128, 9 * Cin, scale=(9 * Cin) ** -0.5).cuda(), chan_stats=True)
     g2, b2 = 1 + 0.1 * torch.randn(448, generator=g), 0.1 * torch.randn(448, generator=g)
     got = ops.groupnorm(y1, g2.cuda(), b2.cuda(), 1e-6, x2=y6, stats=(s1, s6))
