@@ -632,58 +632,44 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 }
 
 // Split-K finish: out[m, n] = act( sum_s part[s][m][n] + bias[n] + rowvec[m / hw][n] + residual[m][n] ), fixed
-// summation order (bit-reproducible).  One CTA per (32-row slab, 256-column block): thread (cx, ry) owns 8 columns of
-// rows ry, ry + 8, ry + 16, ry + 24 of the slab, so the slab's per-channel (sum, sum of squares) — the GroupNorm
-// statistics of the next op, pcdm_ext.chan_stats — fall out of a fixed-order fold over the 8 row lanes.
+// summation order (bit-reproducible).  One CTA per (32-row slab, 64-column block): lane = row of the slab, warp = an
+// 8-column vector — every thread finishes one row's 8 values with its split loads four deep in flight, and the slab's
+// per-channel (sum, sum of squares) — the GroupNorm statistics of the next op, pcdm_ext.chan_stats — are a shuffle
+// tree over the warp's 32 rows.
 template <int DT>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      const float* __restrict__ bias, const float* __restrict__ rowvec,
                                      long long ld_rowvec, int hw, const void* __restrict__ residual, long long ldr,
                                      void* __restrict__ out, long long ldo, int silu, float* __restrict__ chan_stats) {
   using T = typename TypeOf<DT>::T;
-  __shared__ float red[8][32][16];
   pdl_launch_dependents();
   pdl_wait();
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int n0 = (blockIdx.y * 32 + cx) * 8;
-  const bool col_ok = n0 < N;
-  float cs[8], cq[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.y * 8 + warp) * 8;
+  if (n0 >= N) return;   // whole warp
+  const long long m = (long long)blockIdx.x * 32 + lane;
+  const bool row_ok = m < M;
+  float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  // the four rows' partial sums first, with all their loads independent (8 x 32-byte loads in flight per split step)
-  float acc[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-  const long long m_first = (long long)blockIdx.x * 32 + ry;
-  if (col_ok) {
-    for (int sidx = 0; sidx < splits; ++sidx) {
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (row_ok) {
+    for (int s0 = 0; s0 < splits; s0 += 4) {
       float4 a[4], b[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const long long m = m_first + 8 * k;
         a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M) {
-          const float4* pp = reinterpret_cast<const float4*>(part + ((long long)sidx * M + m) * N + n0);
+        if (s0 + k < splits) {
+          const float4* pp = reinterpret_cast<const float4*>(part + ((long long)(s0 + k) * M + m) * N + n0);
           a[k] = __ldg(pp);
           b[k] = __ldg(pp + 1);
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[k][0] += a[k].x; acc[k][1] += a[k].y; acc[k][2] += a[k].z; acc[k][3] += a[k].w;
-        acc[k][4] += b[k].x; acc[k][5] += b[k].y; acc[k][6] += b[k].z; acc[k][7] += b[k].w;
+      for (int k = 0; k < 4; ++k) {   // split index order: fixed
+        v[0] += a[k].x; v[1] += a[k].y; v[2] += a[k].z; v[3] += a[k].w;
+        v[4] += b[k].x; v[5] += b[k].y; v[6] += b[k].z; v[7] += b[k].w;
       }
     }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long m = m_first + 8 * k;
-    if (!col_ok || m >= M) continue;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = acc[k][j];
     if (bias) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n0)), b = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
@@ -708,30 +694,26 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
     }
-    uint4 o;
-    o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
-    if (chan_stats) {   // statistics of the values as stored (rounded)
-      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+  }
+  uint4 o;
+  o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
+  if (row_ok) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
+  if (!chan_stats) return;
+  // statistics of the values as stored (rounded); rows past M contribute zeros
+  float t[16];
+  {
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack2<DT>(ow[j]);
-        cs[2 * j] += f.x; cs[2 * j + 1] += f.y;
-        cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]); cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = row_ok ? unpack2<DT>(ow[j]) : make_float2(0.f, 0.f);
+      t[4 * j] = f.x; t[4 * j + 1] = f.x * f.x; t[4 * j + 2] = f.y; t[4 * j + 3] = f.y * f.y;
     }
   }
-  if (!chan_stats) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { red[ry][cx][2 * j] = cs[j]; red[ry][cx][2 * j + 1] = cq[j]; }
-  __syncthreads();
-  if (ry == 0 && col_ok) {
-    float t[16];
+  for (int o_ = 16; o_ > 0; o_ >>= 1)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = red[0][cx][j];
-    for (int r = 1; r < 8; ++r)
-#pragma unroll
-      for (int j = 0; j < 16; ++j) t[j] += red[r][cx][j];
+    for (int j = 0; j < 16; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], o_);
+  if (lane == 0) {
     float4* dst = reinterpret_cast<float4*>(chan_stats + ((long long)blockIdx.x * N + n0) * 2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) dst[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
@@ -965,7 +947,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   }
 #undef PCDM_LAUNCH
   if (rc != 0 || !split) return rc;
-  const dim3 fgrid((p.M + 31) / 32, (p.N / 8 + 31) / 32);
+  const dim3 fgrid((p.M + 31) / 32, (p.N / 8 + 7) / 8);
   if (dt == DT_F16)
     PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, fgrid, dim3(256), 0, stream, 1,
                             reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
