@@ -87,8 +87,8 @@ typedef struct pcdm_ext {
    *   writes, for every 32-row slab of the output and every channel, (sum, sum of squares) of the 16-bit values AS
    *   STORED: chan_stats[slab][N][2] fp32, slab = row / 32, ceil(M / 32) slabs (pcdm_conv3x3_up2x: an image's slabs are
    *   [parity plane][32 low-resolution pixels], still contiguous per image).  The rows of a slab must belong to one
-   *   image: rows_per_image (pcdm_gemm) / H*W % 32 == 0.  Deterministic (fixed reduction order); also produced on the
-   *   split-K route.  pcdm_groupnorm_apply consumes it: GroupNorm then costs one read + one write of the activation
+   *   image: rows_per_image (pcdm_gemm) / H*W % 32 == 0.  Deterministic (fixed reduction order); a launch that emits
+   *   them never takes the split-K route.  pcdm_groupnorm_apply consumes it: GroupNorm then costs one read + one write of the activation
    *   and no pass for the statistics. ---- */
   float* chan_stats;
 } pcdm_ext;

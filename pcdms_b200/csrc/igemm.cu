@@ -632,43 +632,27 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 }
 
 // Split-K finish: out[m, n] = act( sum_s part[s][m][n] + bias[n] + rowvec[m / hw][n] + residual[m][n] ), fixed
-// summation order (bit-reproducible).  One CTA per (32-row slab, 64-column block): lane = row of the slab, warp = an
-// 8-column vector — every thread finishes one row's 8 values with its split loads four deep in flight, and the slab's
-// per-channel (sum, sum of squares) — the GroupNorm statistics of the next op, pcdm_ext.chan_stats — are a shuffle
-// tree over the warp's 32 rows.
+// summation order (bit-reproducible); 8 columns per thread.
 template <int DT>
-__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
+__global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      const float* __restrict__ bias, const float* __restrict__ rowvec,
                                      long long ld_rowvec, int hw, const void* __restrict__ residual, long long ldr,
-                                     void* __restrict__ out, long long ldo, int silu, float* __restrict__ chan_stats) {
+                                     void* __restrict__ out, long long ldo, int silu) {
   using T = typename TypeOf<DT>::T;
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n0 = (blockIdx.y * 8 + warp) * 8;
-  if (n0 >= N) return;   // whole warp
-  const long long m = (long long)blockIdx.x * 32 + lane;
-  const bool row_ok = m < M;
-  float v[8];
+  const int nv = N / 8;
+  const long long total = (long long)M * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n0 = (int)(i % nv) * 8;
+    const long long m = i / nv;
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (row_ok) {
-    for (int s0 = 0; s0 < splits; s0 += 4) {
-      float4 a[4], b[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s0 + k < splits) {
-          const float4* pp = reinterpret_cast<const float4*>(part + ((long long)(s0 + k) * M + m) * N + n0);
-          a[k] = __ldg(pp);
-          b[k] = __ldg(pp + 1);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {   // split index order: fixed
-        v[0] += a[k].x; v[1] += a[k].y; v[2] += a[k].z; v[3] += a[k].w;
-        v[4] += b[k].x; v[5] += b[k].y; v[6] += b[k].z; v[7] += b[k].w;
-      }
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) {
+      const float4* pp = reinterpret_cast<const float4*>(part + ((long long)sidx * M + m) * N + n0);
+      const float4 a = __ldg(pp), b = __ldg(pp + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
     }
     if (bias) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n0)), b = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
@@ -694,29 +678,9 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
     }
-  }
-  uint4 o;
-  o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
-  if (row_ok) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
-  if (!chan_stats) return;
-  // statistics of the values as stored (rounded); rows past M contribute zeros
-  float t[16];
-  {
-    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = row_ok ? unpack2<DT>(ow[j]) : make_float2(0.f, 0.f);
-      t[4 * j] = f.x; t[4 * j + 1] = f.x * f.x; t[4 * j + 2] = f.y; t[4 * j + 3] = f.y * f.y;
-    }
-  }
-#pragma unroll
-  for (int o_ = 16; o_ > 0; o_ >>= 1)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], o_);
-  if (lane == 0) {
-    float4* dst = reinterpret_cast<float4*>(chan_stats + ((long long)blockIdx.x * N + n0) * 2);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+    uint4 o;
+    o.x = pack2<DT>(v[0], v[1]); o.y = pack2<DT>(v[2], v[3]); o.z = pack2<DT>(v[4], v[5]); o.w = pack2<DT>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + m * ldo + n0) = o;
   }
 }
 
@@ -868,9 +832,9 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   if (ext.chan_stats) {
     if (p.out_f32 || p.geglu) return set_error(PCDM_ERR_UNSUPPORTED, "channel statistics come with the plain 16-bit-output epilogue only");
     if (p.hw % 32) return set_error(PCDM_ERR_UNSUPPORTED, "channel statistics need rows-per-image (H*W) to be a multiple of 32");
-    p.chan_stats = ext.chan_stats;   // cleared again below when split-K hands the epilogue to the finishing kernel
+    p.chan_stats = ext.chan_stats;   // (a launch that emits statistics never takes the split-K route)
   }
-  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats && planes == 1) {   // K >= 4096: below, one launch wins
+  if (bn == 0 && g_ws && !p.out_f32 && !p.geglu && p.num_kb >= 64 && (p.N % 8) == 0 && !ext.ln_stats && !ext.row_stats && !ext.chan_stats && planes == 1) {   // K >= 4096: below, one launch wins
     const int sbn = (p.N % 160 == 0) ? 160 : 128;
     const int tiles = p.m_tiles * ((p.N + sbn - 1) / sbn);
     if (tiles * 2 <= num_sms()) {
@@ -884,7 +848,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
         bn = sbn;
         p.splits = splits;
         p.kb_per_split = kbps;
-        p.bias = nullptr; p.rowvec = nullptr; p.silu = 0; p.chan_stats = nullptr;
+        p.bias = nullptr; p.rowvec = nullptr; p.silu = 0;
         p.out = g_ws; p.ldo = p.N; p.out_f32 = 1;
         residual = nullptr;
       }
@@ -947,15 +911,17 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
   }
 #undef PCDM_LAUNCH
   if (rc != 0 || !split) return rc;
-  const dim3 fgrid((p.M + 31) / 32, (p.N / 8 + 7) / 8);
+  const long long total = (long long)p.M * (p.N / 8);
+  long long grid = (total + 255) / 256;
+  if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
   if (dt == DT_F16)
-    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, fgrid, dim3(256), 0, stream, 1,
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_F16>, dim3((int)grid), dim3(256), 0, stream, 1,
                             reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
-                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu, ext.chan_stats));
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
   else
-    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_BF16>, fgrid, dim3(256), 0, stream, 1,
+    PCDM_CUDA(launch_kernel(splitk_finish_kernel<DT_BF16>, dim3((int)grid), dim3(256), 0, stream, 1,
                             reinterpret_cast<const float*>(g_ws), p.splits, p.M, p.N, epi.bias, epi.rowvec,
-                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu, ext.chan_stats));
+                            epi.ld_rowvec, epi.hw, epi.residual, epi.ldr, epi.out, epi.ldo, epi.silu));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

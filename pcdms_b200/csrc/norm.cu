@@ -141,11 +141,9 @@ template <int DT>
 __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int C1, int C, int HW,
                                 int groups, int pix_per_cta, const float2* __restrict__ final_stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                void* __restrict__ y, const float2* __restrict__ st1, const float2* __restrict__ st2,
-                                int slabs_per_image, float eps) {
+                                void* __restrict__ y) {
   pdl_launch_dependents();
   using T = typename TypeOf<DT>::T;
-  extern __shared__ float2 gstat[];   // [groups] (mean, rstd) of this CTA's image when it folds the producers' slab sums
   const int b = blockIdx.y;
   const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
   const int c0 = cv * 8;
@@ -157,44 +155,6 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
   const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   pdl_wait();
   const float2* stats_b = final_stats + (size_t)b * groups;
-  if (st1) {
-    // Small images (<= 16 slabs): every CTA of the image folds the producers' per-slab channel sums itself — one warp
-    // per group, four loads in flight per lane, fp64, fixed order — instead of waiting for a separate fold launch
-    // (the redundant reads are a few tens of KB of L2 per CTA; a dependent launch costs more than that).
-    const int tid = py * blockDim.x + cv, nwarps = (blockDim.x * blockDim.y) >> 5, warp = tid >> 5, lane = tid & 31;
-    const int total = slabs_per_image * cpg, C2 = C - C1;
-    if (warp < nwarps) {
-      for (int g = warp; g < groups; g += nwarps) {
-        double a = 0.0, q = 0.0;
-        for (int base = 0; base < total; base += 128) {
-          float2 v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int idx = base + j * 32 + lane;
-            v[j] = make_float2(0.f, 0.f);
-            if (idx < total) {
-              const int sl = idx / cpg, c = g * cpg + (idx - sl * cpg);
-              const long long slab = (long long)b * slabs_per_image + sl;
-              v[j] = c < C1 ? __ldg(st1 + slab * C1 + c) : __ldg(st2 + slab * C2 + (c - C1));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { a += (double)v[j].x; q += (double)v[j].y; }
-        }
-        a = warp_sum(a);
-        q = warp_sum(q);
-        if (lane == 0) {
-          const double inv_n = 1.0 / ((double)cpg * (double)HW);
-          const double mean = a * inv_n;
-          double var = q * inv_n - mean * mean;
-          if (var < 0.0) var = 0.0;
-          gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-        }
-      }
-    }
-    __syncthreads();
-    stats_b = gstat;
-  }
   float2 sc2[4], sh2[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -711,14 +671,12 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
     PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_F16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
                             pix_per_cta, eps, ws));
     PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
-                            (const float2*)ws.final_stats, gamma, beta, silu, y, (const float2*)nullptr,
-                            (const float2*)nullptr, 0, 0.f));
+                            (const float2*)ws.final_stats, gamma, beta, silu, y));
   } else {
     PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_BF16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
                             pix_per_cta, eps, ws));
     PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
-                            (const float2*)ws.final_stats, gamma, beta, silu, y, (const float2*)nullptr,
-                            (const float2*)nullptr, 0, 0.f));
+                            (const float2*)ws.final_stats, gamma, beta, silu, y));
   }
   PCDM_CUDA(cudaGetLastError());
   return 0;
@@ -738,34 +696,19 @@ extern "C" int pcdm_groupnorm_apply(const void* x1, const float* stats1, const v
   if ((reinterpret_cast<uintptr_t>(stats1) | reinterpret_cast<uintptr_t>(stats2)) & 7)
     return set_error(PCDM_ERR_INVALID, "groupnorm_apply: statistics must be 8-byte aligned");
   float2* final_stats = reinterpret_cast<float2*>(workspace);   // the first region of a pcdm_groupnorm workspace
-  const int slabs = HW / 32;
-  const bool merged = slabs <= 16 && groups <= 64;   // small images: the apply CTAs fold the statistics themselves
-  const float2* s1 = reinterpret_cast<const float2*>(stats1);
-  const float2* s2 = reinterpret_cast<const float2*>(stats2);
-  if (!merged)
-    PCDM_CUDA(launch_kernel(gn_fold_kernel, dim3(B * groups), dim3(128), 0, stream, 1, s1, s2, C1, C, slabs, groups, B, HW,
-                            eps, final_stats));
+  PCDM_CUDA(launch_kernel(gn_fold_kernel, dim3(B * groups), dim3(128), 0, stream, 1,
+                          reinterpret_cast<const float2*>(stats1), reinterpret_cast<const float2*>(stats2), C1, C, HW / 32,
+                          groups, B, HW, eps, final_stats));
   int PY, pix_per_cta, chunks;
   gn_grid(B, HW, C, &PY, &pix_per_cta, &chunks);
-  if (merged) {   // fewer, larger CTAs: every CTA of an image re-reads that image's slab sums
-    const int max_chunks = slabs <= 4 ? 2 : 8;
-    if (chunks > max_chunks) {
-      chunks = max_chunks;
-      pix_per_cta = (HW + chunks - 1) / chunks;
-      chunks = (HW + pix_per_cta - 1) / pix_per_cta;
-    }
-  }
   const dim3 grid(chunks, B), block(C / 8, PY);
   const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
-  const size_t smem = merged ? (size_t)groups * sizeof(float2) : 0;
   if (dtype == DT_F16)
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
-                            (const float2*)final_stats, gamma, beta, silu, y, merged ? s1 : (const float2*)nullptr,
-                            merged ? s2 : (const float2*)nullptr, slabs, eps));
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)final_stats, gamma, beta, silu, y));
   else
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
-                            (const float2*)final_stats, gamma, beta, silu, y, merged ? s1 : (const float2*)nullptr,
-                            merged ? s2 : (const float2*)nullptr, slabs, eps));
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+                            (const float2*)final_stats, gamma, beta, silu, y));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -664,11 +664,17 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         for p, _, cout in self._resnets:
             temb_off[p] = (off, cout)
             off += cout
-        # Every producer of a GroupNorm input (conv_in, conv1 / conv2 of the resnets, the transformers' proj_out, the
-        # down / up sampler convs) also emits per-channel (sum, sum of squares) from its epilogue; activations travel as
-        # (tensor, ChanStats) pairs — skips included — and GroupNorm never reads a tensor for its statistics.
+        # Producers of LARGE GroupNorm inputs (conv_in, conv1 / conv2 of the resnets, the transformers' proj_out, the
+        # down / up sampler convs — whenever the tensor exceeds what the single-pass GroupNorm kernel keeps in
+        # registers, i.e. the 32x64 level at batch 16) also emit per-channel (sum, sum of squares) from their epilogue;
+        # activations travel as (tensor, ChanStats | None) pairs — skips included — and GroupNorm does not read such a
+        # tensor for its statistics.  Small tensors keep the one-launch register-resident GroupNorm: measured, a second
+        # dependent launch costs them more than the statistics read it saves (profiles/r2_groupnorm_stats.md).
         # conv_in (+ pose) (reference :742)
-        x = ops.conv3x3(x_in, w["conv_in.weight"], bias=w["conv_in.bias"], residual=pose, chan_stats=True)
+        big = self._emit_gn_stats
+        x = ops.conv3x3(x_in, w["conv_in.weight"], bias=w["conv_in.bias"], residual=pose,
+                        chan_stats=big(B * H * W, cfg.block_out_channels[0]))
+        x = x if isinstance(x, tuple) else (x, None)
         skips = [x]
         x_skip = None
         for op in self._plan:
@@ -685,12 +691,24 @@ class B200UNet2DConditionModel(WeightArenaMixin):
             elif kind == "pop":
                 x_skip = skips.pop()
             elif kind == "down":
-                x = ops.conv3x3(x[0], w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], stride=2, chan_stats=True)
+                xin = x[0]
+                x = ops.conv3x3(xin, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], stride=2,
+                                chan_stats=big(xin.shape[0] * xin.shape[1] * xin.shape[2] // 4, op[2]))
+                x = x if isinstance(x, tuple) else (x, None)
             elif kind == "up":
-                x = ops.conv3x3_up2x(x[0], w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"], chan_stats=True)
+                xin = x[0]
+                x = ops.conv3x3_up2x(xin, w[f"{op[1]}.weight"], bias=w[f"{op[1]}.bias"],
+                                     chan_stats=big(xin.shape[0] * xin.shape[1] * xin.shape[2] * 4, op[2]))
+                x = x if isinstance(x, tuple) else (x, None)
         hn = ops.groupnorm(x[0], w["conv_norm_out.weight"], w["conv_norm_out.bias"], cfg.norm_eps, silu=True,
                            stats=(x[1], None))
         return ops.conv3x3(hn, w["conv_out.weight"], bias=w["conv_out.bias"], out_f32=True)
+
+    GN_STATS_MIN_BYTES = 16 << 20   # = the size up to which pcdm_groupnorm runs its one-launch register-resident pass
+
+    def _emit_gn_stats(self, rows, channels):
+        """Should the producer of a [rows, channels] 16-bit tensor emit GroupNorm statistics from its epilogue?"""
+        return rows * channels * 2 > self.GN_STATS_MIN_BYTES
 
     def _resnet(self, p, xs, skip, temb, cin, cout):
         """xs / skip: (tensor, ChanStats) pairs; returns one."""
@@ -701,7 +719,9 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         M = B * H * W
         h = ops.groupnorm(x, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], eps, x2=x_skip, silu=True,
                           stats=(x_st, skip_st))
-        h, h_st = ops.conv3x3(h, w[f"{p}.conv1.weight"], bias=w[f"{p}.conv1.bias"], rowvec=temb, chan_stats=True)
+        emit = self._emit_gn_stats(M, cout)
+        h = ops.conv3x3(h, w[f"{p}.conv1.weight"], bias=w[f"{p}.conv1.bias"], rowvec=temb, chan_stats=emit)
+        h, h_st = h if emit else (h, None)
         h = ops.groupnorm(h, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], eps, silu=True, stats=(h_st, None))
         if cin != cout:
             res = ops.gemm(x.view(M, c1), w[f"{p}.conv_shortcut.weight"],
@@ -709,7 +729,8 @@ class B200UNet2DConditionModel(WeightArenaMixin):
             res = res.view(B, H, W, cout)
         else:
             res = x
-        return ops.conv3x3(h, w[f"{p}.conv2.weight"], bias=w[f"{p}.conv2.bias"], residual=res, chan_stats=True)
+        out = ops.conv3x3(h, w[f"{p}.conv2.weight"], bias=w[f"{p}.conv2.bias"], residual=res, chan_stats=emit)
+        return out if emit else (out, None)
 
     def _transformer(self, p, xs, kv, C, heads):
         w = self._w
@@ -752,6 +773,8 @@ class B200UNet2DConditionModel(WeightArenaMixin):
         # feed-forward (LayerNorm + GEGLU both in the first GEMM's epilogue)
         g = ops.gemm(h, w[f"{t}.ff.net.0.proj_ln.weight"], geglu=True, **folded(f"{t}.ff.net.0.proj_ln", st))
         h = ops.gemm(g, w[f"{t}.ff.net.2.weight"], bias=w[f"{t}.ff.net.2.bias"], residual=h)
-        out, o_st = ops.gemm(h, w[f"{p}.proj_out.weight"], bias=w[f"{p}.proj_out.bias"], residual=x.view(M, C),
-                             rows_per_image=S, chan_stats=True)
+        emit = self._emit_gn_stats(M, C)
+        out = ops.gemm(h, w[f"{p}.proj_out.weight"], bias=w[f"{p}.proj_out.bias"], residual=x.view(M, C),
+                       rows_per_image=S, chan_stats=emit)
+        out, o_st = out if emit else (out, None)
         return out.view(B, H, W, C), o_st

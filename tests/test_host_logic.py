@@ -33,10 +33,12 @@ def _forward(m, cfg, i, t):
     return mock_ops.nhwc_to_nchw(rows, cfg.out_channels, torch.float32)
 
 
-@pytest.mark.parametrize("stage2", [True, False])
-def test_unet_orchestration_matches_oracle(stage2):
+@pytest.mark.parametrize("stage2,gn_stats_everywhere", [(True, False), (False, False), (True, True), (False, True)])
+def test_unet_orchestration_matches_oracle(stage2, gn_stats_everywhere):
     cfg = UNetConfig.tiny() if stage2 else UNetConfig.tiny(in_channels=8, stage2=False)
     o, m = _models(cfg)
+    if gn_stats_everywhere:   # producer-epilogue GroupNorm statistics are normally reserved for > 16 MB tensors
+        m.GN_STATS_MIN_BYTES = 0
     i = make_unet_inputs(cfg, batch=2, h=16, w=32, s_kv=9)
     want = o(i["sample"], 981, i["encoder_hidden_states"], class_labels=i.get("class_labels"),
              my_pose_cond=i.get("my_pose_cond"))[0]

@@ -179,10 +179,10 @@ def test_groupnorm_statistics_from_producer_epilogues(ops, dt):
     # stride 2
     y2, s2 = ops.conv3x3(rnd(2, 16, 32, 64).cuda(), rnd(64, 9 * 64, scale=1 / 24).cuda(), stride=2, chan_stats=True)
     check_stats(s2, y2.view(-1, 64))
-    # split-K route (tile-starved: 16 images of 4 x 8, K = 9 * 1280)
+    # a tile-starved shape (16 images of 4 x 8, K = 9 * 1280): with statistics the launch stays off the split-K route
     xs, ws, bs = _splitk_problem("cuda", 5)
     y3, s3 = ops.conv3x3(xs, ws, bias=bs, chan_stats=True)
-    assert torch.equal(y3, ops.conv3x3(xs, ws, bias=bs))
+    close(y3, ops.conv3x3(xs, ws, bias=bs).cpu(), dt if dt == torch.float16 else torch.float16, mult=2.0)
     check_stats(s3, y3.view(-1, 1280))
     # one-launch Upsample2D: slabs ordered [image][parity plane][32 low-resolution pixels]
     xu = rnd(2, 8, 16, 64)

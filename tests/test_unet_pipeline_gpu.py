@@ -77,6 +77,20 @@ def test_unet_tiny_stage2(dt, mult):
            dtype=dt)
 
 
+def test_unet_tiny_with_producer_groupnorm_statistics_everywhere():
+    """The producer-epilogue GroupNorm statistics path (normally taken by > 16 MB tensors only: the 32x64 level at the
+    bench batch) forced on at every level of the tiny net, incl. the skip concats and the one-launch Upsample2D."""
+    from oracle.factory import make_unet_inputs
+    from oracle.unet import UNetConfig
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg, torch.float16)
+    m.GN_STATS_MIN_BYTES = 0
+    i = make_unet_inputs(cfg, batch=2, h=16, w=32, s_kv=9)
+    out, ref = _run_unet(o, m, i, 981)
+    _check(out, ref, 3e-3, 5e-4, "tiny stage-2 UNet fp16, GroupNorm statistics from producer epilogues at every level",
+           config="tiny UNet B2 16x32 s_kv9", dtype=torch.float16)
+
+
 def test_unet_tiny_stage3_topology():
     from oracle.factory import make_unet_inputs
     from oracle.unet import UNetConfig
