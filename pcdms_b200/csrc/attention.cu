@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
       float mx = -INFINITY;
       if (kv_left >= 64) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int i = 0; i < 64; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i)

@@ -409,6 +409,13 @@ __device__ __forceinline__ float2 gelu_erf2_f(float2 x) {
   return __ffma2_rn(h, erf, h);
 }
 
+// max of three in ONE instruction (FMNMX3, sm_100): halves the row-maximum pass of the attention softmax
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

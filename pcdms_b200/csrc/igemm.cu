@@ -29,7 +29,7 @@ namespace pcdm {
 constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
 constexpr int IG_EPI_WARPS = 8;
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
-constexpr int IG_RES_SLOTS = 4;        // residual slots per epilogue warp: the chunks one warp owns in a <= 256-wide tile
+constexpr int IG_RES_SLOTS = 5;        // residual slots per epilogue warp: the chunks one warp owns in a <= 320-wide tile
 constexpr int IG_MAX_STAGES = 8;
 
 struct IGemmParams {
@@ -83,8 +83,13 @@ struct IGemmCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = (BN / CG) * 128;   // a CTA pair splits the weight tile: each CTA stages BN/2 rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  // accumulators: double-buffered in TMEM (the epilogue of tile i overlaps the MMAs of tile i + 1) up to 256 columns;
+  // the 320-wide pair tile (two 160-column MMAs fed from ONE activation stage) takes 320 of the 512 columns once
+  static constexpr int NACC = BN <= 256 ? 2 : 1;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : (BN <= 256 ? 256 : 512);
+  static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
+  static constexpr int NSUB = BN <= 256 ? 1 : 2;          // MMAs per k16 step (N <= 256 per tcgen05.mma)
+  static constexpr int SUB_N = BN / NSUB;
 };
 
 // byte offset of 16-byte chunk j of row r inside a [rows x 64 B] tile written with the TMA 64-byte swizzle
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int n_blk = mn % p.n_tiles;
       // mode 4: the four parity planes' weights are stacked along N ([4 * Cout, 4 * Cin])
-      const int n0 = n_blk * BN + ((CG == 2) ? (int)rank * (BN / 2) : 0) + (p.mode == 4 ? split * p.N : 0);
+      const int n0 = n_blk * BN + ((CG == 2) ? (int)rank * (Cfg::SUB_N / 2) : 0) + (p.mode == 4 ? split * p.N : 0);
       const int kb_begin = (p.mode == 4 ? 0 : split) * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -285,7 +290,14 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             tma_load_2d(sb, &p.tmB, &full[stage], kb * 64, n0);
           } else {
             if (rank == 0) mbar_expect_tx(&full[stage], 2u * b_bytes);
-            tma_load_2d_cg2(sb, &p.tmB, mapa_u32(smem_u32(&full[stage]), 0), kb * 64, n0);
+            const uint32_t fbar = mapa_u32(smem_u32(&full[stage]), 0);
+            if (Cfg::NSUB == 1) {
+              tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n0);
+            } else {
+              // 320-wide tile = two 160-column MMAs; of each, this CTA supplies 80 weight rows (box = 80 rows)
+              tma_load_2d_cg2(sb, &p.tmB, fbar, kb * 64, n0);
+              tma_load_2d_cg2(sb + (Cfg::SUB_N / 2) * 128, &p.tmB, fbar, kb * 64, n0 + Cfg::SUB_N);
+            }
           }
         }
         __syncwarp();
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     }
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA of a pair; whole warp, one elected lane issues) =====================
-    constexpr uint32_t idesc = make_idesc(DT, 128 * CG, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc(DT, 128 * CG, Cfg::SUB_N, 0, 0);
     // SW128 K-major descriptor: high word constant (SBO 1024 B, version 1, 128-byte swizzle); low word = addr >> 4 |
     // LBO(16 B) << 16, advanced by plain adds (shared addresses < 256 KB never carry out of the 14-bit field)
     constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -318,9 +330,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 4 && !IG_DBG(p, 16); ++k) {
             const uint64_t da = ((uint64_t)kDescHi << 32) | (a_lo + 2u * k);   // +32 B per k16 inside the swizzle atom
-            const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + 2u * k);
-            if (CG == 2) umma_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int h = 0; h < Cfg::NSUB; ++h) {   // 320-wide pair tile: two N = 160 MMAs share the activation operand
+              const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + 2u * k + (uint32_t)h * ((Cfg::SUB_N / CG) * 128 >> 4));
+              if (CG == 2) umma_ss_cg2(d_tmem + h * Cfg::SUB_N, da, db, idesc, (kb | k) != 0);
+              else umma_ss(d_tmem + h * Cfg::SUB_N, da, db, idesc, (kb | k) != 0);
+            }
           }
           // commits come from the SAME lane as the MMAs they track
           if (CG == 2) tc_commit_cg2(&empty[stage]);   // frees the stage in both CTAs
@@ -333,8 +348,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps: TMEM quadrant q, column-chunk parity `half`) =====================
@@ -615,8 +629,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         if (CG == 2) mbar_arrive_cluster(tempty_addr[acc]);   // the MMA issuer lives in the leader CTA
         else mbar_arrive(&tempty[acc]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait<0>();   // all TMA stores have landed before the CTA (and its shared memory) goes away
   }
@@ -693,7 +706,7 @@ template <int BN, int DT, int CG>
 static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, CG>;
   PCDM_ENSURE_SMEM(IG_SMEM_LIMIT, igemm_kernel<BN, DT, CG>);
-  p.nbuf = p.has_res ? IG_RES_SLOTS : 2;
+  p.nbuf = p.has_res ? (BN > 256 ? 5 : 4) : 2;   // residual: one slot per 32-column chunk a warp owns in the tile
   p.dbg = g_tune.gemm_dbg;
   const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
@@ -719,31 +732,35 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
 // cycles per 64-deep k-block of one CTA in steady state.  Once the issue chains were shortened the loop is bound by
 // L2 -> shared-memory delivery (~70 B/clk/SM: (128 + BN / cta_group) x 128 B per k-block) or by the MMAs (2 BN
 // cycles), which makes 160-wide tiles on CTA pairs the best shape for this UNet (every N is a multiple of 160).
+static bool g_tune_bn320() { return true; }
+
 static int kb_cycles(int bn, int cg) {
-  if (cg == 2) return bn == 128 ? 361 : (bn == 160 ? 398 : 629);
+  if (cg == 2) return bn == 128 ? 361 : (bn == 160 ? 398 : (bn == 320 ? 680 : 629));
   return bn == 64 ? 446 : (bn == 128 ? 479 : (bn == 160 ? 549 : 619));
 }
 
 static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int force_cg, int planes, int* bn_out, int* cg_out) {
-  const int cand[4] = {160, 256, 128, 64};
+  const int cand[5] = {160, 256, 128, 64, 320};
   long long best = 1LL << 62;
   *bn_out = 128;
   *cg_out = 1;
   for (int cg = 1; cg <= 2; ++cg) {
     if (force_cg && cg != force_cg) continue;
     if (cg == 2 && M <= 128) continue;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
       const int bn = cand[i];
       if (geglu && (bn % 64)) continue;
       if (bn == 160 && (N % 160)) continue;
+      if (bn == 320 && (cg != 2 || (N % 320) || !g_tune_bn320())) continue;
       if (cg == 2 && bn < 128) continue;
       if (planes > 1 && (N % bn)) continue;   // stacked per-plane weights: an N tile must not straddle two planes
       const long long tiles = (long long)((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn) * planes;
       const long long slots = num_sms() / cg;
       const long long waves = (tiles + slots - 1) / slots;
       // per tile: the k loop, plus the part of the epilogue / pipeline turn-around that is not hidden
+      // (the 320-wide tile's accumulator is single-buffered: its epilogue is not hidden behind the next tile's MMAs)
       const long long tile_cycles = (long long)num_kb * kb_cycles(bn, cg) + 1500 + (geglu ? 1500 : 0) + (has_res ? 300 : 0) +
-                                    (cg == 2 ? 400 : 0);
+                                    (cg == 2 ? 400 : 0) + (bn == 320 ? 2500 : 0);
       const long long cost = waves * tile_cycles;
       if (cost < best) { best = cost; *bn_out = bn; *cg_out = cg; }
     }
@@ -862,7 +879,7 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     int bn_model;
     pick_tile(p.M, p.N, p.kb_per_split, p.geglu, residual != nullptr, split ? 1 : g_force_cg, planes, &bn_model, &cg);
     if (planes > 1 && (p.N % bn)) return set_error(PCDM_ERR_INVALID, "conv3x3_up2x: the forced N tile must divide Cout");
-    if (g_force_cg == 0) cg = (p.M > 128 && bn >= 128 && !split && kb_cycles(bn, 2) < kb_cycles(bn, 1)) ? 2 : 1;
+    if (g_force_cg == 0) cg = (p.M > 128 && bn >= 128 && !split && (bn == 320 || kb_cycles(bn, 2) < kb_cycles(bn, 1))) ? 2 : 1;
     if (bn < 128 || p.M <= 128 || split) cg = 1;
   }
   if (cg == 2) p.m_tiles = (p.M + 255) / 256;
@@ -890,9 +907,9 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     p.stats_out = reinterpret_cast<float2*>(ext.row_stats);
     ext.raw->row_stats_parts = 2 * p.n_tiles;
   }
-  const int bbox = bn / cg;
+  const int bbox = bn == 320 ? 80 : bn / cg;    // 320-wide pair tile: two boxes of 80 rows per CTA and k-block
   const int brows = p.N < bbox ? p.N : bbox;
-  p.b_bytes = (uint32_t)brows * 128u;
+  p.b_bytes = (uint32_t)brows * 128u * (bn == 320 ? 2u : 1u);
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)p.N * planes};
     const uint64_t strides[1] = {(uint64_t)K * 2};
@@ -907,7 +924,11 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     case 128: rc = cg == 2 ? PCDM_LAUNCH(128, 2) : PCDM_LAUNCH(128, 1); break;
     case 160: rc = cg == 2 ? PCDM_LAUNCH(160, 2) : PCDM_LAUNCH(160, 1); break;
     case 256: rc = cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1); break;
-    default: return set_error(PCDM_ERR_INVALID, "igemm: BN must be 0, 64, 128, 160 or 256");
+    case 320:
+      if (cg != 2 || (p.N % 320)) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: the 320-wide tile needs a CTA pair (M > 128) and N % 320 == 0");
+      rc = PCDM_LAUNCH(320, 2);
+      break;
+    default: return set_error(PCDM_ERR_INVALID, "igemm: BN must be 0, 64, 128, 160, 256 or 320");
   }
 #undef PCDM_LAUNCH
   if (rc != 0 || !split) return rc;
