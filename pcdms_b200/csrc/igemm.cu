@@ -131,6 +131,32 @@ __device__ __forceinline__ void ln_prefetch(const IGemmParams& p, long long m) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_stats + (long long)i * p.M + m));
 }
 
+// One GEGLU chunk of a row: 32 value + 32 gate accumulators -> 32 outputs  value * act(gate)  (+ bias, + folded LayerNorm:
+// rstd * acc + bias', rstd == 1 otherwise).  ACT: 1 = SiLU (SwiGLU, DINOv2's FFN), 2 = GELU erf (GEGLU, diffusers).
+// Straight-line code: the eight iterations are independent and the compiler interleaves their MUFU / FFMA2 chains.
+template <int DT, int ACT>
+__device__ __forceinline__ void geglu_math(const uint32_t (&rh)[32], const uint32_t (&rg)[32], const float* __restrict__ bias,
+                                           int n0, float2 rstd2, uint32_t (&o)[16]) {
+  const bool has_bias = bias != nullptr;
+  const float* bp = has_bias ? bias + n0 : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+    if (has_bias) {
+      bh = __ldg(reinterpret_cast<const float4*>(bp + j));
+      bg = __ldg(reinterpret_cast<const float4*>(bp + 32 + j));
+    }
+    const float2 h0 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), make_float2(bh.x, bh.y));
+    const float2 h1 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
+    const float2 g0 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
+    const float2 g1 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
+    const float2 v0 = __fmul2_rn(h0, ACT == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
+    const float2 v1 = __fmul2_rn(h1, ACT == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
+    o[j / 2] = pack2<DT>(v0.x, v0.y);
+    o[j / 2 + 1] = pack2<DT>(v1.x, v1.y);
+  }
+}
+
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA loads its own 128 activation rows and HALF of the weight tile, the leader CTA issues the M = 256 MMAs, each
 // CTA's TMEM receives (and each CTA's epilogue stores) its own 128 rows.
@@ -591,26 +617,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           tmem_ld32(t_row + c * 64, rh);
           tmem_ld32(t_row + c * 64 + 32, rg);
           tc_wait_ld();
-          // packed fp32 (FFMA2) arithmetic: this epilogue is issue-bound at K = 320..1280
+          // packed fp32 (FFMA2) arithmetic.  The gate activation is chosen OUTSIDE the unrolled loop: a warp-uniform
+          // `silu ? a : b` inside it compiled to a branch per element pair, which fenced the eight independent GELU
+          // chains off from each other (no instruction-level parallelism: the K = 320 GEGLU GEMM ran at 0.4 of its bound).
           uint32_t o[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
-            if (p.bias) {
-              bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32 + j));
-            }
-            // (+ folded LayerNorm: rstd * acc + bias'; rstd == 1 otherwise)
-            const float2 h0 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), make_float2(bh.x, bh.y));
-            const float2 h1 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
-            const float2 g0 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
-            const float2 g1 = __ffma2_rn(ln_rstd2, make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
-            // gate activation: GELU (GEGLU, diffusers FeedForward) or SiLU (SwiGLU, DINOv2's FFN) — warp-uniform
-            const float2 v0 = __fmul2_rn(h0, p.silu == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
-            const float2 v1 = __fmul2_rn(h1, p.silu == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
-            o[j / 2] = pack2<DT>(v0.x, v0.y);
-            o[j / 2 + 1] = pack2<DT>(v1.x, v1.y);
-          }
+          if (p.silu == 1) geglu_math<DT, 1>(rh, rg, p.bias, n0, ln_rstd2, o);
+          else geglu_math<DT, 2>(rh, rg, p.bias, n0, ln_rstd2, o);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
@@ -732,7 +744,7 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
 // cycles per 64-deep k-block of one CTA in steady state.  Once the issue chains were shortened the loop is bound by
 // L2 -> shared-memory delivery (~70 B/clk/SM: (128 + BN / cta_group) x 128 B per k-block) or by the MMAs (2 BN
 // cycles), which makes 160-wide tiles on CTA pairs the best shape for this UNet (every N is a multiple of 160).
-static bool g_tune_bn320() { return true; }
+static bool g_tune_bn320() { return false; }   // measured (tools/dev_bn320.py): never faster than 160 / 256; kept for explicit bn = 320
 
 static int kb_cycles(int bn, int cg) {
   if (cg == 2) return bn == 128 ? 361 : (bn == 160 ? 398 : (bn == 320 ? 680 : 629));
