@@ -329,6 +329,325 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Round 2: head_dim 64 attention restructured (VERDICT r1 "next" item 3).  One PERSISTENT CTA per SM works through
+// (batch, head, q-tile pair) items; inside an item TWO 128-row query tiles ping-pong through the tensor pipe and share
+// every K/V block that TMA brings in (half the K/V traffic per query row).  320 threads: warp 0 = TMA producer (Q
+// double-buffered across items, 3-deep K/V ring running ahead across item boundaries), warp 1 = tcgen05.mma issuer,
+// warps 2-5 = softmax of tile 0, warps 6-9 = softmax of tile 1.  A softmax thread owns ONE FULL score row (128 columns
+// in registers, read from TMEM once): no half-row exchange through shared memory, no pair barrier, the lazy rescale
+// of O is a per-warp decision, and the row maximum is 64 FMNMX3.  ~3 issue slots per score instead of 5.5.
+//
+// TMEM (512 columns): S0 [0,128) S1 [128,256) fp32 scores | O0 [256,320) O1 [320,384) fp32 accumulators |
+//                     P0 [384,448) P1 [448,512) 16-bit probabilities (A operand of the PV MMA, never in shared memory)
+// Barriers (phases by use counters; "^1" waits pass on a fresh barrier):
+//   q_full[2]/q_empty[2] per Q buffer, kv_full[3]/kv_empty[3] per ring stage, and per tile t:
+//   s_full[t] (MMA->softmax: S landed), s_free[t] (softmax->MMA: S is in registers), p_full[t] (softmax->MMA: P written,
+//   O rescaled), pv_done[t] (MMA->softmax: PV retired, P / O may be touched), o_free[t] (softmax->MMA: O read out).
+// Tail balance: the items of the last partial round are issued as SINGLE tiles (a lone tile gets the SM's whole SFU).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int A2_THREADS = 320;
+constexpr int A2_KV_STAGES = 3;
+constexpr int A2_SMEM = 2 * 2 * ATT_TILE_BYTES + A2_KV_STAGES * 2 * ATT_TILE_BYTES + 1024 + 512;
+constexpr int A2_S = 0, A2_O = 256, A2_P = 384;   // TMEM column bases (tile t: + t * 128 / 64 / 64)
+
+struct A2Item { int b, h, qt, nt; };   // nt = 1 or 2 query tiles (qt, qt + 1) of head (b, h); nt = 0: nothing
+
+// item k of this CTA -> its tiles.  `pairs` = ceil(q_tiles / 2) pair slots per (b, h); items [0, full) are pairs, the
+// remaining pair slots are issued as two single-tile items each.
+__device__ __forceinline__ A2Item a2_item(const AttnParams& p, int item, int pairs, int full, int total_items) {
+  A2Item it;
+  it.nt = 0; it.b = it.h = it.qt = 0;
+  if (item >= total_items) return it;
+  int slot, want;   // slot = tile slot index (2 per pair)
+  if (item < full) { slot = 2 * item; want = 2; }
+  else { slot = 2 * full + (item - full); want = 1; }
+  const int bh = slot / (2 * pairs), qt = slot - bh * 2 * pairs;
+  it.h = bh % p.heads; it.b = bh / p.heads; it.qt = qt;
+  it.nt = qt >= p.q_tiles ? 0 : ((want == 2 && qt + 1 < p.q_tiles) ? 2 : 1);
+  return it;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [buf][tile][16 KB]
+  uint8_t* sKV = smem + 4 * ATT_TILE_BYTES;             // [stage][K 16 KB | V 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + A2_KV_STAGES * 2 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;              // [2]
+  uint64_t* q_empty = bars + 2;         // [2]
+  uint64_t* kv_full = bars + 4;         // [3]
+  uint64_t* kv_empty = bars + 7;        // [3]
+  uint64_t* s_full = bars + 10;         // [2]
+  uint64_t* s_free = bars + 12;         // [2]
+  uint64_t* p_full = bars + 14;         // [2]
+  uint64_t* pv_done = bars + 16;        // [2]
+  uint64_t* o_free = bars + 18;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv = (p.Skv + 127) / 128;
+  const int pairs = (p.q_tiles + 1) / 2;
+  const int pair_slots = p.B * p.heads * pairs;
+  const int G = gridDim.x;
+  const int full = (pair_slots / G) * G;                         // pair slots issued as pairs
+  const int total_items = full + 2 * (pair_slots - full);        // the rest as single tiles
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < A2_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int item_it = 0, kv_it = 0;   // item_it counts the items actually processed (every role skips the same empty ones)
+    for (int item = blockIdx.x; item < total_items; item += G) {
+      const A2Item it = a2_item(p, item, pairs, full, total_items);
+      if (it.nt == 0) continue;
+      const int qb = item_it & 1;
+      mbar_wait(&q_empty[qb], (uint32_t)(((item_it >> 1) & 1) ^ 1));
+      if (elect_one()) {
+        mbar_expect_tx(&q_full[qb], (uint32_t)it.nt * ATT_TILE_BYTES);
+        for (int t = 0; t < it.nt; ++t)
+          tma_load_4d(sQ + (qb * 2 + t) * ATT_TILE_BYTES, &p.tmQ, &q_full[qb], 0, (it.qt + t) * 128, it.h, it.b);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j, ++kv_it) {
+        const int stage = kv_it % A2_KV_STAGES;
+        mbar_wait(&kv_empty[stage], (uint32_t)(((kv_it / A2_KV_STAGES) & 1) ^ 1));
+        if (elect_one()) {
+          uint8_t* sk = sKV + stage * 2 * ATT_TILE_BYTES;
+          mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+          tma_load_4d(sk, &p.tmK, &kv_full[stage], 0, j * 128, it.h, it.b);
+          tma_load_4d(sk + ATT_TILE_BYTES, &p.tmV, &kv_full[stage], 0, j * 128, it.h, it.b);
+        }
+        __syncwarp();
+      }
+      ++item_it;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk0 = make_idesc(DT, 128, 0, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);
+    constexpr uint64_t kDescHi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
+    const uint32_t kv_lo0 = (smem_u32(sKV) >> 4) & 0x3FFFu;
+    int item_it = 0, kv_it = 0;
+    int blk[2] = {0, 0}, items_done[2] = {0, 0};
+    auto n16_of = [&](int j) { return (min(128, p.Skv - j * 128) + 15) >> 4; };
+    auto issue_pv = [&](int t, int j, int stage) {   // O_t (+)= P_t(j) V(j)
+      const int n = blk[t] + j;
+      mbar_wait(&p_full[t], (uint32_t)(n & 1));
+      if (j == 0) mbar_wait(&o_free[t], (uint32_t)((items_done[t] & 1) ^ 1));   // O of the previous item was read out
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_lo = (kv_lo0 + (uint32_t)(stage * (2 * ATT_TILE_BYTES >> 4) + (ATT_TILE_BYTES >> 4))) |
+                              ((1024u >> 4) << 16);
+        const int n16 = n16_of(j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < n16)
+            umma_ts(tmem + A2_O + t * 64, tmem + A2_P + t * 64 + k * 8, kDescHi | (v_lo + (2048u >> 4) * k), idesc_pv,
+                    (j | k) != 0);
+        tc_commit(&pv_done[t]);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < total_items; item += G) {
+      const A2Item it = a2_item(p, item, pairs, full, total_items);
+      if (it.nt == 0) continue;
+      const int qb = item_it & 1;
+      mbar_wait(&q_full[qb], (uint32_t)((item_it >> 1) & 1));
+      for (int j = 0; j < n_kv; ++j) {
+        const int stage = (kv_it + j) % A2_KV_STAGES;
+        mbar_wait(&kv_full[stage], (uint32_t)(((kv_it + j) / A2_KV_STAGES) & 1));
+        for (int t = 0; t < it.nt; ++t) {   // S_t = Q_t K(j)^T
+          const int n = blk[t] + j;
+          mbar_wait(&s_free[t], (uint32_t)((n & 1) ^ 1));   // the softmax warps hold S_t(n - 1) in registers
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t q_lo = q_lo0 + (uint32_t)(qb * 2 + t) * (ATT_TILE_BYTES >> 4);
+            const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
+            const uint32_t idesc_qk = idesc_qk0 | ((uint32_t)(n16_of(j) * 2) << 17);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tmem + A2_S + t * 128, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
+            tc_commit(&s_full[t]);
+            if (j == n_kv - 1 && t == it.nt - 1) tc_commit(&q_empty[qb]);   // the item's last read of its Q tiles
+          }
+          __syncwarp();
+        }
+        if (j > 0) {
+          const int pstage = (kv_it + j - 1) % A2_KV_STAGES;
+          for (int t = 0; t < it.nt; ++t) issue_pv(t, j - 1, pstage);
+          if (elect_one()) tc_commit(&kv_empty[pstage]);
+          __syncwarp();
+        }
+      }
+      {
+        const int pstage = (kv_it + n_kv - 1) % A2_KV_STAGES;
+        for (int t = 0; t < it.nt; ++t) issue_pv(t, n_kv - 1, pstage);
+        if (elect_one()) tc_commit(&kv_empty[pstage]);
+        __syncwarp();
+      }
+      kv_it += n_kv;
+      ++item_it;
+      for (int t = 0; t < it.nt; ++t) { blk[t] += n_kv; ++items_done[t]; }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: warps 2-5 tile 0, warps 6-9 tile 1 =====================
+    using T = typename TypeOf<DT>::T;
+    const int t = (warp - 2) >> 2;
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may touch
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem + lane_off + A2_S + t * 128, tO = tmem + lane_off + A2_O + t * 64,
+                   tP = tmem + lane_off + A2_P + t * 64;
+    int n = 0;   // blocks this tile has processed so far (all items)
+    for (int item = blockIdx.x; item < total_items; item += G) {
+      const A2Item it = a2_item(p, item, pairs, full, total_items);
+      if (t >= it.nt) continue;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++n) {
+        mbar_wait(&s_full[t], (uint32_t)(n & 1));
+        tc_fence_after();
+        const int kv_left = p.Skv - j * 128;          // valid columns of this block (>= 128: all)
+        const int nch = kv_left >= 128 ? 4 : (((kv_left + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMAs touch
+        uint32_t s[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]));
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);       // S_t may be overwritten by Q K(j+1)^T
+        float mx = -INFINITY;
+        if (kv_left >= 128) {
+#pragma unroll
+          for (int i = 0; i < 128; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
+        }
+        mx *= p.scale_log2;
+        // P_t and O_t may only be touched once PV_t(n - 1) has retired
+        mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
+        tc_fence_after();
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          const bool grow = mx > m_ref + 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {        // this warp's 32 rows only: no agreement with other warps needed
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = exp2f(m_ref - m_new);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+            l *= alpha;
+            m_ref = m_new;
+          }
+        }
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c >= nch) continue;
+          uint32_t pk[16];
+          if (kv_left >= 128) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])), sc2, nm2);
+              float2 e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+              sum2 = __fadd2_rn(sum2, e);
+              pk[i] = pack2<DT>(e.x, e.y);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 32 + 2 * i;
+              if (col < kv_left) {
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sc2, nm2);
+                float2 e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+                if (col + 1 >= kv_left) e.y = 0.f;
+                sum2 = __fadd2_rn(sum2, e);
+                pk[i] = pack2<DT>(e.x, e.y);
+              } else {
+                pk[i] = 0u;
+              }
+            }
+          }
+          tmem_st16(tP + c * 16, pk);
+        }
+        l += sum2.x + sum2.y;
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // epilogue of the item: O / l
+      mbar_wait(&pv_done[t], (uint32_t)((n - 1) & 1));
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const long long qrow = (long long)(it.qt + t) * 128 + row;
+      T* op = reinterpret_cast<T*>(p.out) + ((long long)it.b * p.Sq + qrow) * p.ldo + it.h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tO + c * 16, o);
+        tc_wait_ld();
+        if (qrow < p.Sq) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint4 u;
+            u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+            u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+            u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+            u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c * 16 + i * 8) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);         // the next item's first PV may overwrite O_t
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Short sequences (Sq, Skv <= 32; head_dim 64): the six-token sequence of the stage-1 prior
 // (/root/reference/src/models/stage1_prior_transformer.py:262-285).  A 128-row tcgen05 tile would be > 95 % padding and
 // its set-up (TMEM allocation, tensor maps, barrier ring) is pure latency in a chain of launch-bound kernels, so this is
@@ -441,6 +760,7 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   }
   AttnParams p;
   memset(&p, 0, sizeof(p));
+  const bool v2 = head_dim == 64 && g_tune.att_v2;   // round-2 kernel: persistent CTAs, two q-tiles ping-pong, full-row softmax
   // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and
   // are zero-filled, so short sequences need no special casing (zero K rows are masked, zero V rows add nothing).
   PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128, head_dim), "Q map");
@@ -450,6 +770,19 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+  if (v2) {
+    const long long pair_slots = (long long)B * heads * ((p.q_tiles + 1) / 2);
+    const int grid2 = (int)(pair_slots < num_sms() ? pair_slots : num_sms());
+    if (dtype == DT_F16) {
+      PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_F16>);
+      PCDM_CUDA(launch_kernel(attention2_kernel<DT_F16>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p));
+    } else {
+      PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_BF16>);
+      PCDM_CUDA(launch_kernel(attention2_kernel<DT_BF16>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p));
+    }
+    PCDM_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int grid = B * heads * p.q_tiles;
 #define ATT_LAUNCH(DT_, P_, HD_)                                                                                    \
   do {                                                                                                              \
