@@ -19,6 +19,8 @@
 // Replaces xformers.memory_efficient_attention / F.scaled_dot_product_attention as enabled by the reference at
 // stage2_batchtest_inpaint_model.py:133 and used via diffusers' attention processors (the
 // processor protocol is mirrored at /root/reference/src/pipelines/PCDMs_pipeline.py:78-153).
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -214,36 +216,23 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
       xm[half * 128 + row] = mx;
       pair_barrier(q);
       mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]) * p.scale_log2;
-      // P (and O, if a rescale is needed) may only be touched once PV_{j-1} has retired
-      if (j > 0) {
-        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
+      // Reference maximum: decided now; the rescale of O and the P stores wait for PV_{j-1} AFTER this block's
+      // exponentials (round 2: the exponentials overlap that MMA instead of queueing behind it).  The packed
+      // probabilities overwrite the scores in place, so nothing extra stays live across the wait.
+      float alpha = 1.0f;
+      bool rescale = false;
       if (j == 0) {
         m_ref = mx;
       } else {
         const bool grow = mx > m_ref + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {   // both warps of the pair see the same rows => the same decision
+        rescale = __any_sync(0xffffffffu, grow);   // both warps of the pair see the same rows => the same decision
+        if (rescale) {
           const float m_new = grow ? mx : m_ref;
-          const float alpha = exp2f(m_ref - m_new);
-#pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
-          }
+          alpha = exp2f(m_ref - m_new);
           l *= alpha;
           m_ref = m_new;
         }
       }
-      // p = exp2(s * scale - m_ref), row sum, 16-bit pack into this warp's 32 P columns; packed fp32 (FFMA2) math.
-      // ATT_POLY_OF_4 of every 4 column pairs can take their exp2 on the FMA pipe (exp2_poly2) instead of the SFU — the
-      // FlashAttention-4 remedy for the 16 ex2/clk/SM limit.  Measured here (tools/dev_attn_perf.py, 2048x2048, d=64):
-      // 150 us with 0/4, 156 with 1/4, 182 with 2/4, 208 with 3/4 — these softmax warps are bound by their own
-      // instruction stream (4 warps per scheduler), not by the SFU, so the default is 0.
       float2 sum2 = make_float2(0.f, 0.f);
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
       auto exp_pair = [&](int c, int i) {
@@ -258,34 +247,52 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
         }
         return e;
       };
+      int nst = 2;   // P chunks (16 packed columns each) this warp stores
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
         if (kv_left >= 64) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 e = exp_pair(c, i);
             sum2 = __fadd2_rn(sum2, e);
-            pk[i] = pack2<DT>(e.x, e.y);
+            s[c * 32 + i] = pack2<DT>(e.x, e.y);
           }
         } else {
           // ragged last block: columns past the sequence contribute nothing and cost nothing (warp-uniform skips);
           // the PV MMAs read only the P columns of 16-row groups that exist, so chunks beyond them are not written
-          if (c * 32 >= ((kv_left + 15) & ~15)) continue;
+          if (c * 32 >= ((kv_left + 15) & ~15)) { nst = min(nst, c); continue; }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             if (c * 32 + 2 * i < kv_left) {
               float2 e = exp_pair(c, i);
               if (c * 32 + 2 * i + 1 >= kv_left) e.y = 0.f;
               sum2 = __fadd2_rn(sum2, e);
-              pk[i] = pack2<DT>(e.x, e.y);
+              s[c * 32 + i] = pack2<DT>(e.x, e.y);
             } else {
-              pk[i] = 0u;
+              s[c * 32 + i] = 0u;
             }
           }
         }
-        tmem_st16(tmem + lane_off + ATT_TMEM_P + half * 32 + c * 16, pk);
       }
+      // P (and O, if a rescale is needed) may only be touched once PV_{j-1} has retired
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      if (rescale) {
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t o[16];
+          tmem_ld16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem + lane_off + ATT_TMEM_O + half * (HD / 2) + c * 16, o);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < nst) tmem_st16(tmem + lane_off + ATT_TMEM_P + half * 32 + c * 16, *reinterpret_cast<uint32_t (*)[16]>(&s[c * 32]));
       const float sum = sum2.x + sum2.y;
       l += sum;
       tc_wait_st();
@@ -328,8 +335,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
   }
 }
 
+#ifdef PCDM_EXPERIMENT
 // ---------------------------------------------------------------------------------------------------------------
-// Round 2: head_dim 64 attention restructured (VERDICT r1 "next" item 3).  One PERSISTENT CTA per SM works through
+// Round 2 EXPERIMENT (compiled into the experiment build only; measured 5-15 % SLOWER than the kernel above on every
+// UNet shape, profiles/r2_attention.md): head_dim 64 attention restructured along VERDICT r1 "next" item 3.  One PERSISTENT CTA per SM works through
 // (batch, head, q-tile pair) items; inside an item TWO 128-row query tiles ping-pong through the tensor pipe and share
 // every K/V block that TMA brings in (half the K/V traffic per query row).  320 threads: warp 0 = TMA producer (Q
 // double-buffered across items, 3-deep K/V ring running ahead across item boundaries), warp 1 = tcgen05.mma issuer,
@@ -345,8 +354,12 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
 //   O rescaled), pv_done[t] (MMA->softmax: PV retired, P / O may be touched), o_free[t] (softmax->MMA: O read out).
 // Tail balance: the items of the last partial round are issued as SINGLE tiles (a lone tile gets the SM's whole SFU).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int A2_THREADS = 320;
+constexpr int A2_THREADS = 384;   // warp-group 0: TMA warp, MMA warp, two idle warps (40 registers); warp-groups 1, 2: softmax of tile 0 / 1 (232)
 constexpr int A2_KV_STAGES = 3;
+#ifndef A2_REGS_LO
+#define A2_REGS_LO 0   // setmaxnreg per role: measured worse (ptxas spills the low-budget roles heavily)
+#define A2_REGS_HI 0
+#endif
 constexpr int A2_SMEM = 2 * 2 * ATT_TILE_BYTES + A2_KV_STAGES * 2 * ATT_TILE_BYTES + 1024 + 512;
 constexpr int A2_S = 0, A2_O = 256, A2_P = 384;   // TMEM column bases (tile t: + t * 128 / 64 / 64)
 
@@ -367,7 +380,7 @@ __device__ __forceinline__ A2Item a2_item(const AttnParams& p, int item, int pai
   return it;
 }
 
-template <int DT>
+template <int DT, int PN, int PM>
 __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -412,6 +425,12 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
+
+  // register budget follows the roles (the launch allots 168 per thread to all twelve warps)
+#if A2_REGS_HI > 0
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_LO));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(A2_REGS_HI));
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -509,10 +528,10 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
       ++item_it;
       for (int t = 0; t < it.nt; ++t) { blk[t] += n_kv; ++items_done[t]; }
     }
-  } else {
-    // ===================== softmax / correction / epilogue: warps 2-5 tile 0, warps 6-9 tile 1 =====================
+  } else if (warp >= 4) {
+    // ===================== softmax / correction / epilogue: warps 4-7 tile 0, warps 8-11 tile 1 =====================
     using T = typename TypeOf<DT>::T;
-    const int t = (warp - 2) >> 2;
+    const int t = (warp - 4) >> 2;
     const int q = warp & 3;                       // TMEM lane quadrant this warp may touch
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -536,56 +555,103 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);       // S_t may be overwritten by Q K(j+1)^T
-        float mx = -INFINITY;
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         if (kv_left >= 128) {
+          // ---- full block: SPECULATIVE exponentials.  The probabilities are computed against the reference maximum the
+          // row already has (for the first block: the maximum of its first 32 scores) while the block's true maximum is
+          // tracked on the side (FMNMX3 in the shadow of the MUFUs: no separate row-maximum phase, no dependency of the
+          // first exponential on the last score).  Only if some row's maximum turns out to exceed its reference by more
+          // than 2^8 is the block redone against the new maximum (the scores stay intact in registers; P is streamed to
+          // TMEM 32 columns at a time) and O rescaled.  Same lazy-rescale semantics as before: P <= 2^8.
+          if (j == 0) {
+            float a = -INFINITY, b = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 128; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        } else {
+            for (int i = 0; i < 32; i += 4) {
+              a = fmax3(a, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+              b = fmax3(b, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            }
+            m_ref = fmaxf(a, b) * p.scale_log2;
+          }
+          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          auto pass = [&](const float mref, auto first_tag) -> float {
+            constexpr bool FIRST = decltype(first_tag)::value;
+            const float2 nm2 = make_float2(-mref, -mref);
+            float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
-        }
-        mx *= p.scale_log2;
-        // P_t and O_t may only be touched once PV_t(n - 1) has retired
-        mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
-        tc_fence_after();
-        if (j == 0) {
-          m_ref = mx;
-        } else {
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float s0 = __uint_as_float(s[c * 32 + 2 * i]), s1 = __uint_as_float(s[c * 32 + 2 * i + 1]);
+                const float2 x = __ffma2_rn(make_float2(s0, s1), sc2, nm2);
+                float2 e;
+                if ((i % PM) < PN) {
+                  e = exp2_poly2(x);
+                } else {
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+                }
+                if (FIRST) mxc[c] = fmax3(mxc[c], s0, s1);
+                sum2 = __fadd2_rn(sum2, e);
+                pk[i] = pack2<DT>(e.x, e.y);
+              }
+              if (FIRST && c == 0) {   // P_t (and O_t) may only be touched once PV_t(n - 1) has retired
+                mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
+                tc_fence_after();
+              }
+              tmem_st16(tP + c * 16, pk);
+            }
+            return sum2.x + sum2.y;
+          };
+          float sum = pass(m_ref, std::true_type{});
+          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * p.scale_log2;
           const bool grow = mx > m_ref + 8.0f;
-          if (__any_sync(0xffffffffu, grow)) {        // this warp's 32 rows only: no agreement with other warps needed
+          if (__any_sync(0xffffffffu, grow)) {        // rare; this warp's 32 rows only
             const float m_new = grow ? mx : m_ref;
             const float alpha = exp2f(m_ref - m_new);
+            sum = pass(m_new, std::false_type{});
+            if (j > 0) {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[16];
-              tmem_ld16(tO + c * 16, o);
-              tc_wait_ld();
+              for (int c = 0; c < 4; ++c) {
+                uint32_t o[16];
+                tmem_ld16(tO + c * 16, o);
+                tc_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tO + c * 16, o);
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(tO + c * 16, o);
+              }
             }
             l *= alpha;
             m_ref = m_new;
           }
-        }
-        float2 sum2 = make_float2(0.f, 0.f);
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+          l += sum;
+        } else {
+          // ---- ragged last block: the classic order (true maximum over the valid columns first, exponentials of the
+          // valid columns only, packed in place)
+          float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c >= nch) continue;
-          uint32_t pk[16];
-          if (kv_left >= 128) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])), sc2, nm2);
-              float2 e;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
-              sum2 = __fadd2_rn(sum2, e);
-              pk[i] = pack2<DT>(e.x, e.y);
-            }
+          for (int i = 0; i < 128; ++i)
+            if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
+          mx *= p.scale_log2;
+          float alpha = 1.0f;
+          bool rescale = false;
+          if (j == 0) {
+            m_ref = mx;
           } else {
+            const bool grow = mx > m_ref + 8.0f;
+            rescale = __any_sync(0xffffffffu, grow);
+            if (rescale) {
+              const float m_new = grow ? mx : m_ref;
+              alpha = exp2f(m_ref - m_new);
+              l *= alpha;
+              m_ref = m_new;
+            }
+          }
+          float2 sum2 = make_float2(0.f, 0.f);
+          const float2 nm2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c >= nch) continue;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int col = c * 32 + 2 * i;
@@ -596,15 +662,30 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
                 if (col + 1 >= kv_left) e.y = 0.f;
                 sum2 = __fadd2_rn(sum2, e);
-                pk[i] = pack2<DT>(e.x, e.y);
+                s[c * 32 + i] = pack2<DT>(e.x, e.y);
               } else {
-                pk[i] = 0u;
+                s[c * 32 + i] = 0u;
               }
             }
           }
-          tmem_st16(tP + c * 16, pk);
+          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
+          tc_fence_after();
+          if (rescale) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < nch) tmem_st16(tP + c * 16, *reinterpret_cast<uint32_t (*)[16]>(&s[c * 32]));
+          l += sum2.x + sum2.y;
         }
-        l += sum2.x + sum2.y;
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -646,6 +727,8 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     tmem_dealloc(tmem, 512);
   }
 }
+
+#endif  // PCDM_EXPERIMENT
 
 // ---------------------------------------------------------------------------------------------------------------
 // Short sequences (Sq, Skv <= 32; head_dim 64): the six-token sequence of the stage-1 prior
@@ -760,7 +843,9 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   }
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  const bool v2 = head_dim == 64 && g_tune.att_v2;   // round-2 kernel: persistent CTAs, two q-tiles ping-pong, full-row softmax
+#ifdef PCDM_EXPERIMENT
+  const bool v2 = head_dim == 64 && g_tune.att_v2;   // experiment: persistent CTAs, two q-tiles ping-pong, full-row softmax
+#endif
   // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and
   // are zero-filled, so short sequences need no special casing (zero K rows are masked, zero V rows add nothing).
   PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128, head_dim), "Q map");
@@ -770,19 +855,37 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef PCDM_EXPERIMENT
   if (v2) {
     const long long pair_slots = (long long)B * heads * ((p.q_tiles + 1) / 2);
     const int grid2 = (int)(pair_slots < num_sms() ? pair_slots : num_sms());
+#define A2_LAUNCH(DT_, PN_, PM_)                                                                                      \
+  do {                                                                                                                \
+    PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_, PN_, PM_>);                                                      \
+    PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p)); \
+  } while (0)
+    // g_tune.att_dbg selects the share of exponentials evaluated on the FMA pipe (exp2_poly2): 0 none, 1 = 1 of 4
+    // column pairs, 2 = 1 of 3, 3 = 1 of 2
     if (dtype == DT_F16) {
-      PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_F16>);
-      PCDM_CUDA(launch_kernel(attention2_kernel<DT_F16>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p));
+      switch (g_tune.att_dbg) {
+        case 1: A2_LAUNCH(DT_F16, 1, 4); break;
+        case 2: A2_LAUNCH(DT_F16, 1, 3); break;
+        case 3: A2_LAUNCH(DT_F16, 1, 2); break;
+        default: A2_LAUNCH(DT_F16, 0, 1); break;
+      }
     } else {
-      PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_BF16>);
-      PCDM_CUDA(launch_kernel(attention2_kernel<DT_BF16>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p));
+      switch (g_tune.att_dbg) {
+        case 1: A2_LAUNCH(DT_BF16, 1, 4); break;
+        case 2: A2_LAUNCH(DT_BF16, 1, 3); break;
+        case 3: A2_LAUNCH(DT_BF16, 1, 2); break;
+        default: A2_LAUNCH(DT_BF16, 0, 1); break;
+      }
     }
+#undef A2_LAUNCH
     PCDM_CUDA(cudaGetLastError());
     return 0;
   }
+#endif
   const int grid = B * heads * p.q_tiles;
 #define ATT_LAUNCH(DT_, P_, HD_)                                                                                    \
   do {                                                                                                              \

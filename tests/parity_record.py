@@ -6,6 +6,13 @@ meets it on identical inputs (tests/test_kernels_gpu.py).  For whole-UNet / whol
 elements outside that tolerance is a measured quantity, not an argument: `check()` computes it and appends one JSON
 record per comparison to `gpurun_out/r2_parity.jsonl` (override: $PCDM_PARITY_LOG) so the numbers survive `pytest -q`;
 `tools/collect_parity.py` turns the log into the committed `profiles/r2_parity.json`.
+
+The yardstick for that share: no 16-bit execution of this network meets the tolerance element-wise, the reference's own
+included.  `tests/golden/half_envelope.json` (tools/make_half_envelope.py, CPU) holds the error of the REFERENCE's own
+fp16 / bf16 execution (the oracle classes — bit-equal to the reference's — under `.half()` / `.bfloat16()`, PyTorch
+CPU) against its fp32 path for the same inputs; wherever a comparison's `config` has such an entry, `check()` asserts
+that the CUDA path is AT LEAST AS CLOSE to the fp32 CPU path as the reference's own 16-bit run (mean error, share outside
+the tolerance; max error within 1.25x) and records both sides.
 """
 from __future__ import annotations
 
@@ -18,6 +25,18 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 RTOL, ATOL = 1e-3, 1e-4   # north_star
+
+
+_ENVELOPE = None
+
+
+def reference_half_envelope(config: str, dtype: str):
+    """The reference's own 16-bit error for this comparison (None when the fixture has no such case)."""
+    global _ENVELOPE
+    if _ENVELOPE is None:
+        f = ROOT / "tests" / "golden" / "half_envelope.json"
+        _ENVELOPE = json.loads(f.read_text())["cases"] if f.exists() else {}
+    return _ENVELOPE.get(config, {}).get(dtype)
 
 
 def _log_path() -> Path:
@@ -49,6 +68,13 @@ def check(got, want, max_frac, mean_frac, label, *, config, dtype, against="orac
            "asserted_max_frac": max_frac, "asserted_mean_frac": mean_frac, **m, "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
     if extra:
         rec.update(extra)
+    env = reference_half_envelope(config, rec["dtype"]) if against == "oracle" else None
+    if env:
+        rec["reference_own_16bit_run"] = {k: env[k] for k in ("max_abs_err", "mean_abs_err", "max_err_over_max_ref",
+                                                              "mean_err_over_max_ref", "pct_outside_rtol1e-3_atol1e-4")}
+        rec["closer_to_fp32_than_reference_16bit"] = bool(
+            m["mean_abs_err"] <= env["mean_abs_err"] and m["max_abs_err"] <= 1.25 * env["max_abs_err"] and
+            m["pct_outside_rtol1e-3_atol1e-4"] <= env["pct_outside_rtol1e-3_atol1e-4"])
     try:
         p = _log_path()
         p.parent.mkdir(parents=True, exist_ok=True)
@@ -61,4 +87,8 @@ def check(got, want, max_frac, mean_frac, label, *, config, dtype, against="orac
     assert not m["nan"], label
     assert m["max_abs_err"] <= max_frac * m["max_abs_ref"], (label, m)
     assert m["mean_abs_err"] <= mean_frac * m["max_abs_ref"], (label, m)
+    if env:
+        print(f"[parity] {label}: the reference's own {rec['dtype']} run: max|err| {env['max_abs_err']:.3e}, mean|err| "
+              f"{env['mean_abs_err']:.3e}, outside: {env['pct_outside_rtol1e-3_atol1e-4']:.2f}%")
+        assert rec["closer_to_fp32_than_reference_16bit"], (label, m, env)
     return m
