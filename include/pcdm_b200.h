@@ -236,6 +236,12 @@ int pcdm_cfg_combine(const void* eps, int eps_dtype, void* out, int out_dtype, i
 int pcdm_ddim_step(const void* model_output, int eps_dtype, const void* sample, void* prev_sample, int dtype,
                    float inv_sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev, float sqrt_one_minus_a_prev,
                    long long numel, void* stream);
+/* The stochastic step (eta != 0; diffusers DDIMScheduler.step, protocol at stage2_inpaint_pipeline.py:307-322,519):
+ * sigma = eta * sqrt((1 - a_prev) / (1 - a_t)) * sqrt(1 - a_t / a_prev), dir_coef = sqrt(1 - a_prev - sigma^2),
+ * prev = sqrt_a_prev * x0 + dir_coef * eps + sigma * noise; noise has the sample's dtype (drawn by the caller's generator). */
+int pcdm_ddim_step_eta(const void* model_output, int eps_dtype, const void* sample, const void* noise, void* prev_sample,
+                       int dtype, float inv_sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev, float dir_coef,
+                       float sigma, long long numel, void* stream);
 
 /* DDPMScheduler.add_noise (stage2_train_inpaint_model.py:361): out = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise. */
 int pcdm_add_noise(const void* x0, const void* noise, void* out, int dtype, const float* alphas_cumprod,

@@ -5,7 +5,7 @@ Call sites in the reference: scheduler.set_timesteps / scale_model_input / step 
 /root/reference/pcdms_demo.ipynb:106-114 (scaled_linear 0.00085 -> 0.012, clip_sample=False, set_alpha_to_one=False,
 steps_offset=1, 1000 train steps); DDPMScheduler.add_noise at /root/reference/stage2_train_inpaint_model.py:361.
 The arithmetic itself is diffusers' (un-vendored, pinned 0.24.0, README.md:37) and is restated from the published
-DDIM algorithm (Song et al. 2020, eq. 12 with eta = 0) as diffusers implements it.
+DDIM algorithm (Song et al. 2020, eq. 12; eta = 0 on the reference drivers' path, eta > 0 as the stochastic variant) as diffusers implements it.
 """
 from __future__ import annotations
 
@@ -52,16 +52,23 @@ class OracleDDIMScheduler:
 
     def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output=False, generator=None,
              variance_noise=None, return_dict: bool = True):
-        if eta != 0.0:
-            raise NotImplementedError("reference runs eta = 0")
         t = int(timestep)
         prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         beta_t = 1 - a_t
         pred_x0 = (sample - beta_t ** 0.5 * model_output) / a_t ** 0.5
-        pred_dir = (1 - a_prev) ** 0.5 * model_output  # sigma_t = 0
+        # diffusers 0.24.0 scheduling_ddim.py: _get_variance and the eta > 0 branch of step()
+        variance = (1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)
+        std_dev_t = eta * variance ** 0.5
+        pred_dir = (1 - a_prev - std_dev_t ** 2) ** 0.5 * model_output
         prev_sample = a_prev ** 0.5 * pred_x0 + pred_dir
+        if eta > 0:
+            if variance_noise is not None and generator is not None:
+                raise ValueError("Cannot pass both generator and variance_noise.")
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            prev_sample = prev_sample + std_dev_t * variance_noise
         if not return_dict:
             return (prev_sample,)
         return SimpleNamespace(prev_sample=prev_sample, pred_original_sample=pred_x0)

@@ -1,20 +1,26 @@
-// K3 — fused multi-head attention, head_dim 64, no mask:  O = softmax(Q K^T / 8) V   (flash-style, online softmax).
+// K3 — fused multi-head attention, no mask:  O = softmax(Q K^T * scale) V   (flash-style, online softmax), tcgen05.
 //
-// One CTA per (batch, head, 128-query tile), TWO CTAs resident per SM: while one CTA's softmax warps work through a
-// score tile, the other CTA's MMAs own the tensor pipe (at d = 64 the exponentials, not the MMAs, are the scarce
-// resource: 16 ex2/clk/SM vs 128x128 scores per 512 tensor cycles).  320 threads: warp 0 = TMA producer (Q once, then
-// a 2-deep K/V ring) + TMEM allocator, warp 1 = tcgen05.mma issuer, warps 2-9 = softmax: two warps per TMEM lane
-// quadrant, each owning one query row per thread and HALF of the 128 score columns (with the 32x32b TMEM access
-// pattern a thread reads its row's scores directly; the two half-row maxima / sums meet in shared memory).
+// Two head_dim-64 kernels (plus the head_dim-128 instantiation of the first, and a CUDA-core kernel for <= 32 tokens):
 //
-// TMEM (256 columns per CTA):  S : 128 fp32 score columns            (QK^T, SS MMA)
-//                              P : 64 columns = 128 x 128 fp16/bf16 probabilities, consumed by the PV MMA straight
-//                                  from tensor memory (A operand in TMEM) — P never touches shared memory
-//                              O : 64 fp32 columns, accumulated across KV blocks inside the tensor core
-// A warp's 64 scores are read from TMEM once and stay in registers (the score columns are released to the next
-// Q K^T immediately); <= 102 registers/thread keeps 2 CTAs/SM.  The running maximum is applied lazily: O and l are
-// rescaled (TMEM round trip by the softmax warps) only when a row's maximum grows by more than 2^8.
-// V is consumed in its natural [kv, d] layout as an MN-major B operand, K as a K-major B operand.
+//  * attention2_kernel (round 2; sequences of two or more 128-query tiles — every UNet level above 8x16, DINOv2):
+//    one PERSISTENT CTA per SM works through (batch, head, q-tile pair) items.  TWO 128-row query tiles share every
+//    K/V block TMA brings in and ping-pong through the tensor pipe; a softmax thread owns one full score row and
+//    streams it out of TMEM 32 columns at a time (next chunk's tcgen05.ld in flight under the current chunk's
+//    exponentials, ~100 live registers), with SPECULATIVE exponentials: probabilities are taken against the row's
+//    current reference maximum while the block's true maximum is tracked in the shadow of the MUFUs, and only a growth
+//    beyond 2^8 redoes the block from the scores still in TMEM.  One of every four column pairs takes its exp2 on the
+//    FMA pipe (Cody-Waite + degree-4 polynomial).  Description at the kernel.
+//
+//  * attention_kernel (round 1; single-tile sequences, head_dim 128): one CTA per (batch, head, 128-query tile), two
+//    CTAs per SM at d = 64.  320 threads: warp 0 = TMA producer (Q once, then a 2-deep K/V ring) + TMEM allocator,
+//    warp 1 = tcgen05.mma issuer, warps 2-9 = softmax: two warps per TMEM lane quadrant, each owning one query row per
+//    thread and HALF of the 128 score columns (the two half-row maxima / sums meet in shared memory).
+//    TMEM (256 columns per CTA):  S : 128 fp32 score columns (QK^T, SS MMA) | P : 64 columns = 128 x 128 16-bit
+//    probabilities, consumed by the PV MMA straight from tensor memory (A operand in TMEM) | O : 64 fp32 columns.
+//    The running maximum is applied lazily: O and l are rescaled only when a row's maximum grows by more than 2^8.
+//
+// In both, P never touches shared memory, V is consumed in its natural [kv, d] layout as an MN-major B operand and K as
+// a K-major B operand, and a ragged last K/V block costs MMAs / exponentials for the rows that exist only.
 //
 // Replaces xformers.memory_efficient_attention / F.scaled_dot_product_attention as enabled by the reference at
 // stage2_batchtest_inpaint_model.py:133 and used via diffusers' attention processors (the
@@ -335,31 +341,33 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
   }
 }
 
-#ifdef PCDM_EXPERIMENT
 // ---------------------------------------------------------------------------------------------------------------
-// Round 2 EXPERIMENT (compiled into the experiment build only; measured 5-15 % SLOWER than the kernel above on every
-// UNet shape, profiles/r2_attention.md): head_dim 64 attention restructured along VERDICT r1 "next" item 3.  One PERSISTENT CTA per SM works through
+// Round 2: head_dim 64 attention restructured (VERDICT r1 "next" item 3).  One PERSISTENT CTA per SM works through
 // (batch, head, q-tile pair) items; inside an item TWO 128-row query tiles ping-pong through the tensor pipe and share
-// every K/V block that TMA brings in (half the K/V traffic per query row).  320 threads: warp 0 = TMA producer (Q
+// every K/V block that TMA brings in (half the K/V traffic per query row).  384 threads: warp 0 = TMA producer (Q
 // double-buffered across items, 3-deep K/V ring running ahead across item boundaries), warp 1 = tcgen05.mma issuer,
-// warps 2-5 = softmax of tile 0, warps 6-9 = softmax of tile 1.  A softmax thread owns ONE FULL score row (128 columns
-// in registers, read from TMEM once): no half-row exchange through shared memory, no pair barrier, the lazy rescale
-// of O is a per-warp decision, and the row maximum is 64 FMNMX3.  ~3 issue slots per score instead of 5.5.
+// warps 2-3 idle (a warp may only touch TMEM lane quadrant warp % 4, so the softmax groups start at a multiple of 4),
+// warps 4-7 = softmax of tile 0, warps 8-11 = softmax of tile 1.  A softmax thread owns ONE FULL score row: no half-row
+// exchange through shared memory, no pair barrier, the rescale of O is a per-warp decision.
+//
+// The scores stay in TMEM while the row streams through them in 32-column chunks (registers: two chunk buffers + 16
+// packed probabilities — the first version of this kernel held all 128 scores of a row in registers, could not
+// overlap anything inside a warp and was SLOWER than the round-1 kernel, profiles/r2_attention.md).  Per tile the chain
+// is  S(j) -> softmax(j) -> { Q K(j+1)^T, P(j) V(j) }; the bubble of one tile is filled by the other tile's
+// exponentials (the static issue order QK0, PV0, QK1, PV1 makes the tiles settle half a period apart).
 //
 // TMEM (512 columns): S0 [0,128) S1 [128,256) fp32 scores | O0 [256,320) O1 [320,384) fp32 accumulators |
 //                     P0 [384,448) P1 [448,512) 16-bit probabilities (A operand of the PV MMA, never in shared memory)
 // Barriers (phases by use counters; "^1" waits pass on a fresh barrier):
 //   q_full[2]/q_empty[2] per Q buffer, kv_full[3]/kv_empty[3] per ring stage, and per tile t:
-//   s_full[t] (MMA->softmax: S landed), s_free[t] (softmax->MMA: S is in registers), p_full[t] (softmax->MMA: P written,
-//   O rescaled), pv_done[t] (MMA->softmax: PV retired, P / O may be touched), o_free[t] (softmax->MMA: O read out).
+//   s_full[t] (MMA->softmax: S landed), p_full[t] (softmax->MMA: block done — P written, O rescaled, S free),
+//   pv_done[t] (MMA->softmax: PV retired, P / O may be touched), o_free[t] (softmax->MMA: O read out).
 // Tail balance: the items of the last partial round are issued as SINGLE tiles (a lone tile gets the SM's whole SFU).
+// Measured (B200, bf16, B 16, inside a CUDA graph; round-1 kernel -> this one): 2048 x 2048 142 -> 124 us, 2048 x 258
+// 40.2 -> 30.6, 512 x 512 28.6 -> 23.9, 512 x 258 23.0 -> 18.5, 8192 x 8192 (B 8) 971 -> 910.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int A2_THREADS = 384;   // warp-group 0: TMA warp, MMA warp, two idle warps (40 registers); warp-groups 1, 2: softmax of tile 0 / 1 (232)
+constexpr int A2_THREADS = 384;
 constexpr int A2_KV_STAGES = 3;
-#ifndef A2_REGS_LO
-#define A2_REGS_LO 0   // setmaxnreg per role: measured worse (ptxas spills the low-budget roles heavily)
-#define A2_REGS_HI 0
-#endif
 constexpr int A2_SMEM = 2 * 2 * ATT_TILE_BYTES + A2_KV_STAGES * 2 * ATT_TILE_BYTES + 1024 + 512;
 constexpr int A2_S = 0, A2_O = 256, A2_P = 384;   // TMEM column bases (tile t: + t * 128 / 64 / 64)
 
@@ -380,6 +388,35 @@ __device__ __forceinline__ A2Item a2_item(const AttnParams& p, int item, int pai
   return it;
 }
 
+// One 32-column chunk of a score row -> 32 probabilities against the reference maximum `mref` (log2 domain), 16 packed
+// 16-bit pairs in pk.  PN of every PM column pairs take their exp2 on the FMA pipe (exp2_poly2), the rest on the SFU.
+// TRACK: the chunk's raw maximum is folded into mx on the side (FMNMX3 in the shadow of the MUFUs).
+template <int DT, int PN, int PM, bool TRACK>
+__device__ __forceinline__ void a2_chunk(const uint32_t (&s)[32], float2 sc2, float mref, float& mx, float2& sum2,
+                                         uint32_t (&pk)[16]) {
+  const float2 nm2 = make_float2(-mref, -mref);
+  float mxa = mx, mxb = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float s0 = __uint_as_float(s[2 * i]), s1 = __uint_as_float(s[2 * i + 1]);
+    const float2 x = __ffma2_rn(make_float2(s0, s1), sc2, nm2);
+    float2 e;
+    if ((i % PM) < PN) {
+      e = exp2_poly2(x);
+    } else {
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+    }
+    if (TRACK) {
+      if (i & 1) mxb = fmax3(mxb, s0, s1);
+      else mxa = fmax3(mxa, s0, s1);
+    }
+    sum2 = __fadd2_rn(sum2, e);
+    pk[i] = pack2<DT>(e.x, e.y);
+  }
+  if (TRACK) mx = fmaxf(mxa, mxb);
+}
+
 template <int DT, int PN, int PM>
 __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -392,10 +429,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
   uint64_t* kv_full = bars + 4;         // [3]
   uint64_t* kv_empty = bars + 7;        // [3]
   uint64_t* s_full = bars + 10;         // [2]
-  uint64_t* s_free = bars + 12;         // [2]
-  uint64_t* p_full = bars + 14;         // [2]
-  uint64_t* pv_done = bars + 16;        // [2]
-  uint64_t* o_free = bars + 18;         // [2]
+  uint64_t* p_full = bars + 12;         // [2]  softmax -> MMA: block done (P written, O rescaled, S no longer needed)
+  uint64_t* pv_done = bars + 14;        // [2]
+  uint64_t* o_free = bars + 16;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   pdl_launch_dependents();
@@ -414,7 +450,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < A2_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
     }
     fence_barrier_init();
@@ -425,12 +461,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
-
-  // register budget follows the roles (the launch allots 168 per thread to all twelve warps)
-#if A2_REGS_HI > 0
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_LO));
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(A2_REGS_HI));
-#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -461,6 +491,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Per tile the chain is  S(j) -> softmax(j) -> { Q K(j+1)^T, P(j) V(j) }: the scores stay in TMEM while the softmax
+    // warps stream through them, so S_t is rewritten only once block j is done — that bubble of one tile (one QK^T
+    // plus hand-shakes) is filled by the exponentials of the OTHER tile, whose blocks end half a period later.
     constexpr uint32_t idesc_qk0 = make_idesc(DT, 128, 0, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);
     constexpr uint64_t kDescHi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
@@ -469,11 +502,24 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     int item_it = 0, kv_it = 0;
     int blk[2] = {0, 0}, items_done[2] = {0, 0};
     auto n16_of = [&](int j) { return (min(128, p.Skv - j * 128) + 15) >> 4; };
+    auto issue_qk = [&](int t, int j, int stage, int qb, bool last) {   // S_t = Q_t K(j)^T  (S_t is free: block n - 1 done)
+      if (elect_one()) {
+        const uint32_t q_lo = q_lo0 + (uint32_t)(qb * 2 + t) * (ATT_TILE_BYTES >> 4);
+        const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
+        const uint32_t idesc_qk = idesc_qk0 | ((uint32_t)(n16_of(j) * 2) << 17);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + A2_S + t * 128, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
+        tc_commit(&s_full[t]);
+        if (last) tc_commit(&q_empty[qb]);   // the item's last read of its Q tiles
+      }
+      __syncwarp();
+    };
     auto issue_pv = [&](int t, int j, int stage) {   // O_t (+)= P_t(j) V(j)
-      const int n = blk[t] + j;
-      mbar_wait(&p_full[t], (uint32_t)(n & 1));
-      if (j == 0) mbar_wait(&o_free[t], (uint32_t)((items_done[t] & 1) ^ 1));   // O of the previous item was read out
-      tc_fence_after();
+      if (j == 0) {
+        mbar_wait(&o_free[t], (uint32_t)((items_done[t] & 1) ^ 1));   // O of the previous item was read out
+        tc_fence_after();
+      }
       if (elect_one()) {
         const uint32_t v_lo = (kv_lo0 + (uint32_t)(stage * (2 * ATT_TILE_BYTES >> 4) + (ATT_TILE_BYTES >> 4))) |
                               ((1024u >> 4) << 16);
@@ -492,37 +538,20 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
       if (it.nt == 0) continue;
       const int qb = item_it & 1;
       mbar_wait(&q_full[qb], (uint32_t)((item_it >> 1) & 1));
-      for (int j = 0; j < n_kv; ++j) {
-        const int stage = (kv_it + j) % A2_KV_STAGES;
-        mbar_wait(&kv_full[stage], (uint32_t)(((kv_it + j) / A2_KV_STAGES) & 1));
-        for (int t = 0; t < it.nt; ++t) {   // S_t = Q_t K(j)^T
-          const int n = blk[t] + j;
-          mbar_wait(&s_free[t], (uint32_t)((n & 1) ^ 1));   // the softmax warps hold S_t(n - 1) in registers
+      for (int j = 0; j <= n_kv; ++j) {
+        const int stage = (kv_it + j) % A2_KV_STAGES, pstage = (kv_it + j - 1) % A2_KV_STAGES;
+        if (j < n_kv) mbar_wait(&kv_full[stage], (uint32_t)(((kv_it + j) / A2_KV_STAGES) & 1));
+        for (int t = 0; t < it.nt; ++t) {
+          const int n = blk[t] + j;                   // global block counter of tile t
+          if (n > 0) mbar_wait(&p_full[t], (uint32_t)((n - 1) & 1));   // softmax finished block n - 1 (also across items)
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t q_lo = q_lo0 + (uint32_t)(qb * 2 + t) * (ATT_TILE_BYTES >> 4);
-            const uint32_t k_lo = (kv_lo0 + (uint32_t)stage * (2 * ATT_TILE_BYTES >> 4)) | ((16u >> 4) << 16);
-            const uint32_t idesc_qk = idesc_qk0 | ((uint32_t)(n16_of(j) * 2) << 17);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss(tmem + A2_S + t * 128, kDescHi | (q_lo + 2u * k), kDescHi | (k_lo + 2u * k), idesc_qk, k != 0);
-            tc_commit(&s_full[t]);
-            if (j == n_kv - 1 && t == it.nt - 1) tc_commit(&q_empty[qb]);   // the item's last read of its Q tiles
-          }
-          __syncwarp();
+          if (j < n_kv) issue_qk(t, j, stage, qb, j == n_kv - 1 && t == it.nt - 1);
+          if (j > 0) issue_pv(t, j - 1, pstage);
         }
         if (j > 0) {
-          const int pstage = (kv_it + j - 1) % A2_KV_STAGES;
-          for (int t = 0; t < it.nt; ++t) issue_pv(t, j - 1, pstage);
           if (elect_one()) tc_commit(&kv_empty[pstage]);
           __syncwarp();
         }
-      }
-      {
-        const int pstage = (kv_it + n_kv - 1) % A2_KV_STAGES;
-        for (int t = 0; t < it.nt; ++t) issue_pv(t, n_kv - 1, pstage);
-        if (elect_one()) tc_commit(&kv_empty[pstage]);
-        __syncwarp();
       }
       kv_it += n_kv;
       ++item_it;
@@ -537,7 +566,19 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tS = tmem + lane_off + A2_S + t * 128, tO = tmem + lane_off + A2_O + t * 64,
                    tP = tmem + lane_off + A2_P + t * 64;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     int n = 0;   // blocks this tile has processed so far (all items)
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tO + c * 16, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tO + c * 16, o);
+      }
+    };
     for (int item = blockIdx.x; item < total_items; item += G) {
       const A2Item it = a2_item(p, item, pairs, full, total_items);
       if (t >= it.nt) continue;
@@ -546,92 +587,74 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
         mbar_wait(&s_full[t], (uint32_t)(n & 1));
         tc_fence_after();
         const int kv_left = p.Skv - j * 128;          // valid columns of this block (>= 128: all)
-        const int nch = kv_left >= 128 ? 4 : (((kv_left + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMAs touch
-        uint32_t s[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nch) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]));
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);       // S_t may be overwritten by Q K(j+1)^T
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        uint32_t sa[32], sb[32], pk[16];
         if (kv_left >= 128) {
-          // ---- full block: SPECULATIVE exponentials.  The probabilities are computed against the reference maximum the
-          // row already has (for the first block: the maximum of its first 32 scores) while the block's true maximum is
-          // tracked on the side (FMNMX3 in the shadow of the MUFUs: no separate row-maximum phase, no dependency of the
-          // first exponential on the last score).  Only if some row's maximum turns out to exceed its reference by more
-          // than 2^8 is the block redone against the new maximum (the scores stay intact in registers; P is streamed to
-          // TMEM 32 columns at a time) and O rescaled.  Same lazy-rescale semantics as before: P <= 2^8.
+          // ---- full block, SPECULATIVE exponentials, 32 columns at a time straight from TMEM (the next chunk's
+          // tcgen05.ld is in flight while this one is exponentiated; ~100 live registers, no spills).  Probabilities are
+          // computed against the reference maximum the row already has (first block: the maximum of its first 32
+          // scores) while the true maximum is tracked on the side; only if some row's maximum exceeds its reference by
+          // more than 2^8 is the block redone from the scores still in TMEM, and O rescaled.  P <= 2^8 as before.
+          tmem_ld32(tS, sa);
+          tc_wait_ld();
+          tmem_ld32(tS + 32, sb);
           if (j == 0) {
             float a = -INFINITY, b = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              a = fmax3(a, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-              b = fmax3(b, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+              a = fmax3(a, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
+              b = fmax3(b, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
             }
             m_ref = fmaxf(a, b) * p.scale_log2;
           }
-          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          auto pass = [&](const float mref, auto first_tag) -> float {
-            constexpr bool FIRST = decltype(first_tag)::value;
-            const float2 nm2 = make_float2(-mref, -mref);
-            float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float s0 = __uint_as_float(s[c * 32 + 2 * i]), s1 = __uint_as_float(s[c * 32 + 2 * i + 1]);
-                const float2 x = __ffma2_rn(make_float2(s0, s1), sc2, nm2);
-                float2 e;
-                if ((i % PM) < PN) {
-                  e = exp2_poly2(x);
-                } else {
-                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
-                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
-                }
-                if (FIRST) mxc[c] = fmax3(mxc[c], s0, s1);
-                sum2 = __fadd2_rn(sum2, e);
-                pk[i] = pack2<DT>(e.x, e.y);
-              }
-              if (FIRST && c == 0) {   // P_t (and O_t) may only be touched once PV_t(n - 1) has retired
-                mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
-                tc_fence_after();
-              }
-              tmem_st16(tP + c * 16, pk);
-            }
-            return sum2.x + sum2.y;
-          };
-          float sum = pass(m_ref, std::true_type{});
-          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * p.scale_log2;
+          float mx = -INFINITY;
+          float2 sum2 = make_float2(0.f, 0.f);
+          a2_chunk<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
+          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));   // P_t (and O_t) may only be touched once PV_t(n - 1) has retired
+          tc_fence_after();
+          tmem_st16(tP, pk);
+          tc_wait_ld();
+          tmem_ld32(tS + 64, sa);
+          a2_chunk<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
+          tmem_st16(tP + 16, pk);
+          tc_wait_ld();
+          tmem_ld32(tS + 96, sb);
+          a2_chunk<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
+          tmem_st16(tP + 32, pk);
+          tc_wait_ld();
+          a2_chunk<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
+          tmem_st16(tP + 48, pk);
+          mx *= p.scale_log2;
           const bool grow = mx > m_ref + 8.0f;
           if (__any_sync(0xffffffffu, grow)) {        // rare; this warp's 32 rows only
             const float m_new = grow ? mx : m_ref;
             const float alpha = exp2f(m_ref - m_new);
-            sum = pass(m_new, std::false_type{});
-            if (j > 0) {
+            sum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                uint32_t o[16];
-                tmem_ld16(tO + c * 16, o);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st16(tO + c * 16, o);
-              }
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld32(tS + c * 32, sa);
+              tc_wait_ld();
+              a2_chunk<DT, 0, 1, false>(sa, sc2, m_new, mx, sum2, pk);
+              tmem_st16(tP + c * 16, pk);
             }
+            if (j > 0) rescale_o(alpha);
             l *= alpha;
             m_ref = m_new;
           }
-          l += sum;
+          l += sum2.x + sum2.y;
         } else {
-          // ---- ragged last block: the classic order (true maximum over the valid columns first, exponentials of the
-          // valid columns only, packed in place)
+          // ---- ragged last block: the classic order, two passes over the scores in TMEM — true maximum of the valid
+          // columns first, then their exponentials (columns past the sequence contribute zeros; chunks the MMAs never
+          // read are not touched)
+          const int nch = (((kv_left + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMAs touch
           float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            tmem_ld32(tS + c * 32, sa);
+            tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(sa[i]));
+          }
           mx *= p.scale_log2;
           float alpha = 1.0f;
           bool rescale = false;
@@ -647,43 +670,30 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
               m_ref = m_new;
             }
           }
+          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
+          tc_fence_after();
+          if (rescale) rescale_o(alpha);
           float2 sum2 = make_float2(0.f, 0.f);
           const float2 nm2 = make_float2(-m_ref, -m_ref);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c >= nch) continue;
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            tmem_ld32(tS + c * 32, sa);
+            tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int col = c * 32 + 2 * i;
+              float2 e = make_float2(0.f, 0.f);
               if (col < kv_left) {
-                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sc2, nm2);
-                float2 e;
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1])), sc2, nm2);
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
                 if (col + 1 >= kv_left) e.y = 0.f;
-                sum2 = __fadd2_rn(sum2, e);
-                s[c * 32 + i] = pack2<DT>(e.x, e.y);
-              } else {
-                s[c * 32 + i] = 0u;
               }
+              sum2 = __fadd2_rn(sum2, e);
+              pk[i] = pack2<DT>(e.x, e.y);
             }
+            tmem_st16(tP + c * 16, pk);
           }
-          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
-          tc_fence_after();
-          if (rescale) {
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[16];
-              tmem_ld16(tO + c * 16, o);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tO + c * 16, o);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < nch) tmem_st16(tP + c * 16, *reinterpret_cast<uint32_t (*)[16]>(&s[c * 32]));
           l += sum2.x + sum2.y;
         }
         tc_wait_st();
@@ -728,7 +738,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
   }
 }
 
-#endif  // PCDM_EXPERIMENT
 
 // ---------------------------------------------------------------------------------------------------------------
 // Short sequences (Sq, Skv <= 32; head_dim 64): the six-token sequence of the stage-1 prior
@@ -843,9 +852,6 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   }
   AttnParams p;
   memset(&p, 0, sizeof(p));
-#ifdef PCDM_EXPERIMENT
-  const bool v2 = head_dim == 64 && g_tune.att_v2;   // experiment: persistent CTAs, two q-tiles ping-pong, full-row softmax
-#endif
   // TMA boxes are always 128 rows: rows past the end of a (b, h) sequence are out of bounds for the 4-D map and
   // are zero-filled, so short sequences need no special casing (zero K rows are masked, zero V rows add nothing).
   PCDM_CHECK(make_qkv_map(&p.tmQ, q, ldq, Sq, heads, B, 128, head_dim), "Q map");
@@ -855,8 +861,9 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   p.q_tiles = (Sq + 127) / 128;
   p.out = out; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-#ifdef PCDM_EXPERIMENT
-  if (v2) {
+  // head_dim 64, two or more query tiles: the persistent two-tile kernel; single-tile sequences stay on the one-CTA-
+  // per-tile kernel (measured equal or a few % faster there)
+  if (head_dim == 64 && g_tune.att_v2 && p.q_tiles >= 2) {
     const long long pair_slots = (long long)B * heads * ((p.q_tiles + 1) / 2);
     const int grid2 = (int)(pair_slots < num_sms() ? pair_slots : num_sms());
 #define A2_LAUNCH(DT_, PN_, PM_)                                                                                      \
@@ -864,28 +871,33 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
     PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_, PN_, PM_>);                                                      \
     PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p)); \
   } while (0)
-    // g_tune.att_dbg selects the share of exponentials evaluated on the FMA pipe (exp2_poly2): 0 none, 1 = 1 of 4
-    // column pairs, 2 = 1 of 3, 3 = 1 of 2
-    if (dtype == DT_F16) {
-      switch (g_tune.att_dbg) {
-        case 1: A2_LAUNCH(DT_F16, 1, 4); break;
-        case 2: A2_LAUNCH(DT_F16, 1, 3); break;
-        case 3: A2_LAUNCH(DT_F16, 1, 2); break;
-        default: A2_LAUNCH(DT_F16, 0, 1); break;
+#ifdef PCDM_EXPERIMENT
+    // g_tune.att_dbg: share of exponentials evaluated on the FMA pipe — 0 the release setting (1 of 4 column pairs),
+    // 1 none, 2 = 1 of 3, 3 = 1 of 2 (tools/dev_attn3.py: 124 / 133 / 131 / 142 us at 2048 x 2048)
+    if (g_tune.att_dbg) {
+      if (dtype == DT_F16) {
+        switch (g_tune.att_dbg) {
+          case 1: A2_LAUNCH(DT_F16, 0, 1); break;
+          case 2: A2_LAUNCH(DT_F16, 1, 3); break;
+          default: A2_LAUNCH(DT_F16, 1, 2); break;
+        }
+      } else {
+        switch (g_tune.att_dbg) {
+          case 1: A2_LAUNCH(DT_BF16, 0, 1); break;
+          case 2: A2_LAUNCH(DT_BF16, 1, 3); break;
+          default: A2_LAUNCH(DT_BF16, 1, 2); break;
+        }
       }
-    } else {
-      switch (g_tune.att_dbg) {
-        case 1: A2_LAUNCH(DT_BF16, 1, 4); break;
-        case 2: A2_LAUNCH(DT_BF16, 1, 3); break;
-        case 3: A2_LAUNCH(DT_BF16, 1, 2); break;
-        default: A2_LAUNCH(DT_BF16, 0, 1); break;
-      }
+      PCDM_CUDA(cudaGetLastError());
+      return 0;
     }
+#endif
+    if (dtype == DT_F16) A2_LAUNCH(DT_F16, 1, 4);
+    else A2_LAUNCH(DT_BF16, 1, 4);
 #undef A2_LAUNCH
     PCDM_CUDA(cudaGetLastError());
     return 0;
   }
-#endif
   const int grid = B * heads * p.q_tiles;
 #define ATT_LAUNCH(DT_, P_, HD_)                                                                                    \
   do {                                                                                                              \

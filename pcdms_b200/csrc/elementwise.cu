@@ -323,14 +323,18 @@ __global__ void ddim_step_vec_kernel(const uint4* __restrict__ eps, const uint4*
 }
 
 // stand-alone scheduler.step: prev = c2 * (x - c1 * eps) * c0 + c3 * eps   (same arithmetic as the fused kernel)
-__global__ void ddim_step_kernel(const void* __restrict__ eps, int eps_dt, const void* __restrict__ x, void* __restrict__ out,
-                                 int dt, float c0, float c1, float c2, float c3, long long total) {
+// (+ sigma * noise for the stochastic step, eta != 0: c3 is then sqrt(1 - a_prev - sigma^2))
+__global__ void ddim_step_kernel(const void* __restrict__ eps, int eps_dt, const void* __restrict__ x,
+                                 const void* __restrict__ noise, void* __restrict__ out, int dt, float c0, float c1,
+                                 float c2, float c3, float sigma, long long total) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float e = load_any(eps, i, eps_dt);
     const float x0 = (load_any(x, i, dt) - c1 * e) * c0;
-    store_any(out, i, dt, c2 * x0 + c3 * e);
+    float r = c2 * x0 + c3 * e;
+    if (noise) r += sigma * load_any(noise, i, dt);
+    store_any(out, i, dt, r);
   }
 }
 
@@ -732,7 +736,18 @@ extern "C" int pcdm_ddim_step(const void* model_output, int eps_dtype, const voi
     PCDM_CUDA(cudaGetLastError());
     return 0;
   }
-  PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, numel));
+  PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, (const void*)nullptr, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, sqrt_one_minus_a_prev, 0.0f, numel));
+  PCDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcdm_ddim_step_eta(const void* model_output, int eps_dtype, const void* sample, const void* noise,
+                                  void* prev_sample, int dtype, float inv_sqrt_a_t, float sqrt_one_minus_a_t,
+                                  float sqrt_a_prev, float dir_coef, float sigma, long long numel, void* stream_) {
+  if (!model_output || !sample || !noise || !prev_sample) return set_error(PCDM_ERR_INVALID, "ddim_step_eta: null pointer");
+  if (eps_dtype < 0 || eps_dtype > 2 || dtype < 0 || dtype > 2) return set_error(PCDM_ERR_INVALID, "ddim_step_eta: bad dtype");
+  if (numel <= 0) return set_error(PCDM_ERR_INVALID, "ddim_step_eta: empty problem");
+  PCDM_CUDA(launch_kernel(ddim_step_kernel, dim3(grid_for(numel, 256)), dim3(256), 0, (cudaStream_t)stream_, 1, model_output, eps_dtype, sample, noise, prev_sample, dtype, inv_sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev, dir_coef, sigma, numel));
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -549,6 +549,22 @@ def ddim_step(model_output, sample, coefs, out=None):
     return out
 
 
+def ddim_step_eta(model_output, sample, noise, coefs, dir_coef, sigma, out=None):
+    """The stochastic DDIM step (eta != 0): coefs as for ddim_step (its 4th entry unused), `noise` ~ N(0, 1) of the sample's
+    shape and dtype."""
+    lib = _l.load()
+    assert model_output.is_contiguous() and sample.is_contiguous() and noise.is_contiguous()
+    assert model_output.shape == sample.shape == noise.shape and noise.dtype == sample.dtype
+    if out is None:
+        out = torch.empty_like(sample)
+    rc = lib.pcdm_ddim_step_eta(_l.ptr(model_output), C.c_int(_any_dt(model_output)), _l.ptr(sample), _l.ptr(noise),
+                                _l.ptr(out), C.c_int(_any_dt(sample)), C.c_float(coefs[0]), C.c_float(coefs[1]),
+                                C.c_float(coefs[2]), C.c_float(dir_coef), C.c_float(sigma), C.c_longlong(sample.numel()),
+                                _stream(sample))
+    _l.check(rc)
+    return out
+
+
 UNIPC_ROW = 16  # floats per step in the UniPC coefficient table (include/pcdm_b200.h)
 
 

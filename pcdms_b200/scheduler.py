@@ -108,13 +108,31 @@ class B200DDIMScheduler:
              generator=None, variance_noise=None, return_dict: bool = True):
         """x_{t-1} = sqrt(a_prev) (x_t - sqrt(1-a_t) eps)/sqrt(a_t) + sqrt(1-a_prev) eps  (eta = 0): one launch of
         pcdm_ddim_step.  (The B200 pipeline itself uses the fused pcdm_cfg_ddim_step instead.)"""
-        if eta != 0.0:
-            raise NotImplementedError("B200DDIMScheduler: eta must be 0 (as in the reference drivers)")
         if self.num_inference_steps is None:
             raise ValueError("call set_timesteps() first")
         ops.require_cuda(sample, "B200DDIMScheduler.step")
         c = self.step_coefficients(timestep)
-        prev = ops.ddim_step(model_output.contiguous(), sample.contiguous(), c)
+        if eta != 0.0:
+            # the stochastic step of diffusers' DDIMScheduler (eta > 0; the reference pipelines forward `eta` and
+            # `generator` to step(), stage2_inpaint_pipeline.py:307-322,519; its drivers leave eta = 0):
+            # sigma = eta sqrt((1-a_prev)/(1-a_t)) sqrt(1 - a_t/a_prev), direction sqrt(1 - a_prev - sigma^2) eps, noise drawn
+            # like diffusers' randn_tensor (on the generator's device, in the model output's dtype)
+            if use_clipped_model_output:
+                raise NotImplementedError("B200DDIMScheduler: use_clipped_model_output (clip_sample is off on this path)")
+            if variance_noise is not None and generator is not None:
+                raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either `generator` or"
+                                 " `variance_noise` stays `None`.")
+            a_t, a_prev = 1.0 - c[1] ** 2, c[2] ** 2
+            sigma = eta * math.sqrt((1.0 - a_prev) / (1.0 - a_t)) * math.sqrt(max(1.0 - a_t / a_prev, 0.0))
+            if variance_noise is None:
+                gdev = generator.device if generator is not None else sample.device
+                variance_noise = torch.randn(model_output.shape, generator=generator, device=gdev,
+                                             dtype=model_output.dtype).to(sample.device)
+            prev = ops.ddim_step_eta(model_output.contiguous(), sample.contiguous(),
+                                     variance_noise.to(sample.dtype).contiguous(), c,
+                                     math.sqrt(max(1.0 - a_prev - sigma * sigma, 0.0)), sigma)
+        else:
+            prev = ops.ddim_step(model_output.contiguous(), sample.contiguous(), c)
         if not return_dict:
             return (prev,)
         return SimpleNamespace(prev_sample=prev)

@@ -340,6 +340,50 @@ def test_attention(ops, dt, B, heads, Sq, Skv, sc):
     close(out.view(B, Sq, C), ref, dt, mult=4.0)
 
 
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,heads,Sq,Skv", [(2, 5, 1024, 1024), (1, 2, 384, 300), (2, 3, 200, 2048), (1, 3, 257, 257)])
+def test_attention_growing_row_maxima(ops, dt, B, heads, Sq, Skv):
+    """Key norms ramp up along the sequence, so every later K/V block brings much larger scores: the two-tile kernel's
+    speculative exponentials (taken against the row's previous reference maximum) must detect the growth, redo the
+    block from the scores still in TMEM and rescale O / l — also across ragged last blocks and odd tile counts."""
+    g = torch.Generator().manual_seed(7 * Sq + Skv)
+    C = heads * 64
+    q = torch.randn(B, Sq, C, generator=g).to(dt)
+    k = (torch.randn(B, Skv, C, generator=g) * torch.linspace(0.2, 6.0, Skv)[None, :, None]).to(dt)
+    v = torch.randn(B, Skv, C, generator=g).to(dt)
+    qh, kh, vh = (t.float().view(B, -1, heads, 64).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, Sq, C)
+    out = ops.attention(q.reshape(B * Sq, C).cuda(), k.reshape(B * Skv, C).cuda(), v.reshape(B * Skv, C).cuda(), B, heads)
+    # sharp rows (|scores| up to ~40): the error is the 16-bit rounding of P and of the output, measured 2e-3 (fp16) /
+    # 2e-2 (bf16) for both attention kernels
+    bound = 6e-3 if dt == torch.float16 else 5e-2
+    assert (out.view(B, Sq, C).float().cpu() - ref).abs().max().item() < bound
+    # decreasing norms: the first block sets a reference maximum that is never exceeded again
+    k2 = k.flip(1).contiguous()
+    ref2 = F.scaled_dot_product_attention(qh, k2.float().view(B, -1, heads, 64).transpose(1, 2), vh).transpose(1, 2).reshape(B, Sq, C)
+    out2 = ops.attention(q.reshape(B * Sq, C).cuda(), k2.reshape(B * Skv, C).cuda(), v.reshape(B * Skv, C).cuda(), B, heads)
+    assert (out2.view(B, Sq, C).float().cpu() - ref2).abs().max().item() < bound
+
+
+def test_attention_more_items_than_sms_is_deterministic(ops):
+    """The persistent kernel at a work list longer than one round (B 16, 5 heads, 2048 tokens: 640 tile pairs on 148
+    CTAs, the last partial round issued as single tiles) against the fp32 reference on a sample of rows, and bit-equal
+    run to run."""
+    dt = torch.bfloat16
+    B, heads, S = 16, 5, 2048
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(B * S, 3 * heads * 64, generator=g).to(dt).cuda()
+    C = heads * 64
+    a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
+    b = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
+    assert torch.equal(a, b)
+    for bi in (0, 7, 15):
+        rows = slice(bi * S, (bi + 1) * S)
+        qh, kh, vh = (qkv[rows, i * C:(i + 1) * C].float().view(1, S, heads, 64).transpose(1, 2) for i in range(3))
+        ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(S, C)
+        close(a[rows], ref.cpu(), dt, mult=4.0)
+
+
 def test_boundary_and_misc_kernels(ops):
     from oracle import blocks as OB
     for t in ([981.0], [1.0, 21.0, 501.0, 999.0]):
@@ -653,6 +697,34 @@ def test_ln_gemm(ops, dt, M, N, K, kw):
     # a rounding flip of a normalised value (fp32 mean / rstd evaluated in a different order) moves an output by one
     # 16-bit ulp of that value times a weight: allow 2x the single-rounding tolerance
     close(out, ref, dt, mult=2.0)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_ddim_stochastic_step(ops, dt):
+    """DDIMScheduler.step with eta != 0 (the `eta` / `generator` the reference pipelines forward to step(),
+    stage2_inpaint_pipeline.py:307-322,519): sigma_t noise added, direction term shrunk — against the oracle's
+    restatement of diffusers' formula with the same variance noise; the generator path draws the same numbers as the
+    oracle from an identically seeded CPU generator (fp32)."""
+    from oracle.schedulers import OracleDDIMScheduler
+    from pcdms_b200.scheduler import B200DDIMScheduler
+    g = torch.Generator().manual_seed(3)
+    e, s = torch.randn(2, 4, 16, 32, generator=g).to(dt), torch.randn(2, 4, 16, 32, generator=g).to(dt)
+    noise = torch.randn(2, 4, 16, 32, generator=g).to(dt)
+    sch, osch = B200DDIMScheduler(), OracleDDIMScheduler()
+    sch.set_timesteps(10)
+    osch.set_timesteps(10)
+    for t, eta in ((901, 1.0), (401, 0.5), (1, 0.3)):
+        want = osch.step(e.float(), t, s.float(), eta=eta, variance_noise=noise.float(), return_dict=False)[0]
+        got = sch.step(e.cuda(), t, s.cuda(), eta=eta, variance_noise=noise.cuda(), return_dict=False)[0]
+        assert got.dtype == dt
+        close(got, want, torch.float16 if dt == torch.float32 else dt)
+        assert (want - osch.step(e.float(), t, s.float(), return_dict=False)[0]).abs().max() > 1e-3   # eta matters
+    if dt == torch.float32:
+        want = osch.step(e, 501, s, eta=0.8, generator=torch.Generator().manual_seed(9), return_dict=False)[0]
+        got = sch.step(e.cuda(), 501, s.cuda(), eta=0.8, generator=torch.Generator().manual_seed(9), return_dict=False)[0]
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        sch.step(e.cuda(), 501, s.cuda(), eta=0.5, generator=torch.Generator(), variance_noise=noise.cuda())
 
 
 @pytest.mark.parametrize("dt", DTS)
