@@ -367,8 +367,9 @@ __global__ void __launch_bounds__(ATT_THREADS, HD == 64 ? 2 : 1) attention_kerne
 // 40.2 -> 30.6, 512 x 512 28.6 -> 23.9, 512 x 258 23.0 -> 18.5, 8192 x 8192 (B 8) 971 -> 910.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int A2_THREADS = 384;
+constexpr int A2_THREADS_HALF = 576;   // half-row variant: warps 2-17 = softmax, two warps per (tile, TMEM lane quadrant)
 constexpr int A2_KV_STAGES = 3;
-constexpr int A2_SMEM = 2 * 2 * ATT_TILE_BYTES + A2_KV_STAGES * 2 * ATT_TILE_BYTES + 1024 + 512;
+constexpr int A2_SMEM = 2 * 2 * ATT_TILE_BYTES + A2_KV_STAGES * 2 * ATT_TILE_BYTES + 1024 + 512 + 2048;   // + half-row exchange [tile][half][128]
 constexpr int A2_S = 0, A2_O = 256, A2_P = 384;   // TMEM column bases (tile t: + t * 128 / 64 / 64)
 
 struct A2Item { int b, h, qt, nt; };   // nt = 1 or 2 query tiles (qt, qt + 1) of head (b, h); nt = 0: nothing
@@ -417,8 +418,49 @@ __device__ __forceinline__ void a2_chunk(const uint32_t (&s)[32], float2 sc2, fl
   if (TRACK) mx = fmaxf(mxa, mxb);
 }
 
-template <int DT, int PN, int PM>
-__global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
+// Half-row variant: one 16-column piece of a score row -> 16 probabilities (8 packed pairs); PN of every PM pairs on the
+// FMA pipe.  TRACK: the piece's raw maximum is folded into mx on the side.
+template <int DT, int PN, int PM, bool TRACK>
+__device__ __forceinline__ void a2_piece(const uint32_t (&s)[16], float2 sc2, float mref, float& mx, float2& sum2,
+                                         uint32_t (&pk)[8]) {
+  const float2 nm2 = make_float2(-mref, -mref);
+  float mxa = mx, mxb = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float s0 = __uint_as_float(s[2 * i]), s1 = __uint_as_float(s[2 * i + 1]);
+    const float2 x = __ffma2_rn(make_float2(s0, s1), sc2, nm2);
+    float2 e;
+    if ((i % PM) < PN) {
+      e = exp2_poly2(x);
+    } else {
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+    }
+    if (TRACK) {
+      if (i & 1) mxb = fmax3(mxb, s0, s1);
+      else mxa = fmax3(mxa, s0, s1);
+    }
+    sum2 = __fadd2_rn(sum2, e);
+    pk[i] = pack2<DT>(e.x, e.y);
+  }
+  if (TRACK) mx = fmaxf(mxa, mxb);
+}
+
+// barrier over the 64 threads of a half-row warp pair that also ORs a predicate across them
+__device__ __forceinline__ bool pair_barrier_or(int id, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "barrier.red.or.pred q, %1, 64, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(r) : "r"(id), "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
+__device__ __forceinline__ void pair_barrier_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int DT, int PN, int PM, bool EARLY, bool HALF>
+__global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [buf][tile][16 KB]
@@ -432,7 +474,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
   uint64_t* p_full = bars + 12;         // [2]  softmax -> MMA: block done (P written, O rescaled, S no longer needed)
   uint64_t* pv_done = bars + 14;        // [2]
   uint64_t* o_free = bars + 16;         // [2]
+  uint64_t* s_free = bars + 18;         // [2]  EARLY: softmax -> MMA: the block's scores are in registers / checked
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 24);   // HALF: [tile][half][128 rows] maxima / sums exchanged by a warp pair
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -450,8 +494,8 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < A2_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], HALF ? 8 : 4); mbar_init(&s_free[i], 4);
+      mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], HALF ? 8 : 4);
     }
     fence_barrier_init();
   }
@@ -543,10 +587,23 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
         if (j < n_kv) mbar_wait(&kv_full[stage], (uint32_t)(((kv_it + j) / A2_KV_STAGES) & 1));
         for (int t = 0; t < it.nt; ++t) {
           const int n = blk[t] + j;                   // global block counter of tile t
-          if (n > 0) mbar_wait(&p_full[t], (uint32_t)((n - 1) & 1));   // softmax finished block n - 1 (also across items)
-          tc_fence_after();
-          if (j < n_kv) issue_qk(t, j, stage, qb, j == n_kv - 1 && t == it.nt - 1);
-          if (j > 0) issue_pv(t, j - 1, pstage);
+          if (EARLY) {
+            if (j < n_kv) {
+              if (n > 0) mbar_wait(&s_free[t], (uint32_t)((n - 1) & 1));   // block n - 1's scores are out of TMEM (also across items)
+              tc_fence_after();
+              issue_qk(t, j, stage, qb, j == n_kv - 1 && t == it.nt - 1);
+            }
+            if (j > 0) {
+              mbar_wait(&p_full[t], (uint32_t)((n - 1) & 1));            // softmax finished block n - 1
+              tc_fence_after();
+              issue_pv(t, j - 1, pstage);
+            }
+          } else {
+            if (n > 0) mbar_wait(&p_full[t], (uint32_t)((n - 1) & 1));   // softmax finished block n - 1 (also across items)
+            tc_fence_after();
+            if (j < n_kv) issue_qk(t, j, stage, qb, j == n_kv - 1 && t == it.nt - 1);
+            if (j > 0) issue_pv(t, j - 1, pstage);
+          }
         }
         if (j > 0) {
           if (elect_one()) tc_commit(&kv_empty[pstage]);
@@ -557,7 +614,195 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
       ++item_it;
       for (int t = 0; t < it.nt; ++t) { blk[t] += n_kv; ++items_done[t]; }
     }
-  } else if (warp >= 4) {
+  } else if (HALF) {
+    // ===================== HALF-ROW softmax: warps 2-17; (tile, column half, TMEM quadrant) = (idx >> 3, (idx >> 2) & 1,
+    // warp & 3) with idx = warp - 2.  Four softmax warps per scheduler instead of two: the full-row variant leaves the
+    // issue slots half empty (each warp stalls on its own MUFU / TMEM latencies and there is only one other warp to
+    // switch to).  A thread owns 64 columns of a row, streamed in 16-column pieces; the two halves of a row agree on
+    // the reference maximum through shared memory — at the first block of an item, and when one of them sees its
+    // maximum grow past 2^8 (a barrier.red.or per block tells both).
+    using T = typename TypeOf<DT>::T;
+    const int idx = warp - 2;
+    const int t = idx >> 3, half = (idx >> 2) & 1, q = warp & 3;
+    const int row = q * 32 + lane;
+    const int bar_id = 1 + t * 4 + q;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem + lane_off + A2_S + t * 128 + half * 64, tO = tmem + lane_off + A2_O + t * 64 + half * 32,
+                   tP = tmem + lane_off + A2_P + t * 64 + half * 32;
+    float* xm = xch + (t * 2 + half) * 128, *xo = xch + (t * 2 + (half ^ 1)) * 128;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    int n = 0;
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tO + c * 16, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tO + c * 16, o);
+      }
+    };
+    for (int item = blockIdx.x; item < total_items; item += G) {
+      const A2Item it = a2_item(p, item, pairs, full, total_items);
+      if (t >= it.nt) continue;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++n) {
+        mbar_wait(&s_full[t], (uint32_t)(n & 1));
+        tc_fence_after();
+        const int kv_left = p.Skv - j * 128 - half * 64;   // valid columns among this thread's 64 (may be <= 0)
+        uint32_t sa[16], sb[16], pk[8];
+        if (p.Skv - j * 128 >= 128) {
+          tmem_ld16(tS, sa);
+          tc_wait_ld();
+          tmem_ld16(tS + 16, sb);
+          if (j == 0) {   // first block of the item: reference maximum = max over both halves' first 16 scores
+            float a = -INFINITY, b = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              a = fmax3(a, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
+              b = fmax3(b, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
+            }
+            const float mine = fmaxf(a, b);
+            xm[row] = mine;
+            pair_barrier_id(bar_id);
+            m_ref = fmaxf(mine, xo[row]) * p.scale_log2;
+            pair_barrier_id(bar_id);   // the slot is reused by the growth exchange below
+          }
+          float mx = -INFINITY;
+          float2 sum2 = make_float2(0.f, 0.f);
+          a2_piece<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
+          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));   // P_t (and O_t) may only be touched once PV_t(n - 1) has retired
+          tc_fence_after();
+          tmem_st8(tP, pk);
+          tc_wait_ld();
+          tmem_ld16(tS + 32, sa);
+          a2_piece<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
+          tmem_st8(tP + 8, pk);
+          tc_wait_ld();
+          tmem_ld16(tS + 48, sb);
+          a2_piece<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
+          tmem_st8(tP + 16, pk);
+          tc_wait_ld();
+          a2_piece<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
+          tmem_st8(tP + 24, pk);
+          mx *= p.scale_log2;
+          if (pair_barrier_or(bar_id, mx > m_ref + 8.0f)) {   // rare: some row of this quadrant grew (either half)
+            xm[row] = mx;
+            pair_barrier_id(bar_id);
+            const float mrow = fmaxf(mx, xo[row]);
+            pair_barrier_id(bar_id);
+            const float m_new = mrow > m_ref + 8.0f ? mrow : m_ref;
+            const float alpha = exp2f(m_ref - m_new);
+            sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld16(tS + c * 16, sa);
+              tc_wait_ld();
+              a2_piece<DT, 0, 1, false>(sa, sc2, m_new, mx, sum2, pk);
+              tmem_st8(tP + c * 8, pk);
+            }
+            if (j > 0) rescale_o(alpha);
+            l *= alpha;
+            m_ref = m_new;
+          }
+          l += sum2.x + sum2.y;
+        } else {
+          // ---- ragged last block: classic order; this half may own no valid column at all
+          const int nv = kv_left < 0 ? 0 : (kv_left > 64 ? 64 : kv_left);
+          const int ncols = ((p.Skv - j * 128 + 15) & ~15) - half * 64;          // P columns the PV MMAs read, of this half
+          const int npc = ncols <= 0 ? 0 : (ncols > 64 ? 4 : (ncols + 15) >> 4);  // 16-column pieces to write
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c * 16 < nv; ++c) {
+            tmem_ld16(tS + c * 16, sa);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < nv) mx = fmaxf(mx, __uint_as_float(sa[i]));
+          }
+          xm[row] = mx;
+          pair_barrier_id(bar_id);
+          mx = fmaxf(mx, xo[row]) * p.scale_log2;
+          pair_barrier_id(bar_id);
+          float alpha = 1.0f;
+          bool rescale = false;
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            const bool grow = mx > m_ref + 8.0f;          // identical in both halves (same mx, same m_ref)
+            rescale = __any_sync(0xffffffffu, grow);
+            if (rescale) {
+              const float m_new = grow ? mx : m_ref;
+              alpha = exp2f(m_ref - m_new);
+              l *= alpha;
+              m_ref = m_new;
+            }
+          }
+          mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));
+          tc_fence_after();
+          if (rescale) rescale_o(alpha);
+          float2 sum2 = make_float2(0.f, 0.f);
+          const float2 nm2 = make_float2(-m_ref, -m_ref);
+#pragma unroll 1
+          for (int c = 0; c < npc; ++c) {
+            if (c * 16 < nv) {
+              tmem_ld16(tS + c * 16, sa);
+              tc_wait_ld();
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int col = c * 16 + 2 * i;
+              float2 e = make_float2(0.f, 0.f);
+              if (col < nv) {
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1])), sc2, nm2);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+                if (col + 1 >= nv) e.y = 0.f;
+              }
+              sum2 = __fadd2_rn(sum2, e);
+              pk[i] = pack2<DT>(e.x, e.y);
+            }
+            tmem_st8(tP + c * 8, pk);
+          }
+          l += sum2.x + sum2.y;
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // epilogue of the item: O / l, this half's 32 output columns; the row sum is the two halves'
+      xm[row] = l;
+      pair_barrier_id(bar_id);
+      const float inv_l = 1.0f / (l + xo[row]);
+      mbar_wait(&pv_done[t], (uint32_t)((n - 1) & 1));
+      tc_fence_after();
+      const long long qrow = (long long)(it.qt + t) * 128 + row;
+      T* op = reinterpret_cast<T*>(p.out) + ((long long)it.b * p.Sq + qrow) * p.ldo + it.h * 64 + half * 32;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tO + c * 16, o);
+        tc_wait_ld();
+        if (qrow < p.Sq) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint4 u;
+            u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+            u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+            u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+            u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c * 16 + i * 8) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);         // the next item's first PV may overwrite O_t
+      pair_barrier_id(bar_id);                         // the exchange slot is rewritten by the next item's first block
+    }
+  } else if (warp >= 4 && warp < 12) {
     // ===================== softmax / correction / epilogue: warps 4-7 tile 0, warps 8-11 tile 1 =====================
     using T = typename TypeOf<DT>::T;
     const int t = (warp - 4) >> 2;
@@ -621,24 +866,57 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
           a2_chunk<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
           tmem_st16(tP + 32, pk);
           tc_wait_ld();
-          a2_chunk<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
-          tmem_st16(tP + 48, pk);
-          mx *= p.scale_log2;
-          const bool grow = mx > m_ref + 8.0f;
-          if (__any_sync(0xffffffffu, grow)) {        // rare; this warp's 32 rows only
-            const float m_new = grow ? mx : m_ref;
-            const float alpha = exp2f(m_ref - m_new);
-            sum2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld32(tS + c * 32, sa);
-              tc_wait_ld();
-              a2_chunk<DT, 0, 1, false>(sa, sc2, m_new, mx, sum2, pk);
-              tmem_st16(tP + c * 16, pk);
+          if (EARLY) {
+            // the last chunk's maximum directly, and the block's growth check BEFORE the score columns are handed back
+            // to the MMA warp (a redo re-reads them): Q K(j+1)^T then runs under this block's last 32 exponentials
+            float a = -INFINITY, b = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              a = fmax3(a, __uint_as_float(sb[i]), __uint_as_float(sb[i + 1]));
+              b = fmax3(b, __uint_as_float(sb[i + 2]), __uint_as_float(sb[i + 3]));
             }
-            if (j > 0) rescale_o(alpha);
-            l *= alpha;
-            m_ref = m_new;
+            mx = fmaxf(mx, fmaxf(a, b)) * p.scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            if (__any_sync(0xffffffffu, grow)) {        // rare; this warp's 32 rows only
+              const float m_new = grow ? mx : m_ref;
+              const float alpha = exp2f(m_ref - m_new);
+              sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+              for (int c = 0; c < 3; ++c) {
+                tmem_ld32(tS + c * 32, sa);
+                tc_wait_ld();
+                a2_chunk<DT, 0, 1, false>(sa, sc2, m_new, mx, sum2, pk);
+                tmem_st16(tP + c * 16, pk);
+              }
+              if (j > 0) rescale_o(alpha);
+              l *= alpha;
+              m_ref = m_new;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);
+            a2_chunk<DT, PN, PM, false>(sb, sc2, m_ref, mx, sum2, pk);
+            tmem_st16(tP + 48, pk);
+          } else {
+            a2_chunk<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
+            tmem_st16(tP + 48, pk);
+            mx *= p.scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            if (__any_sync(0xffffffffu, grow)) {        // rare; this warp's 32 rows only
+              const float m_new = grow ? mx : m_ref;
+              const float alpha = exp2f(m_ref - m_new);
+              sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                tmem_ld32(tS + c * 32, sa);
+                tc_wait_ld();
+                a2_chunk<DT, 0, 1, false>(sa, sc2, m_new, mx, sum2, pk);
+                tmem_st16(tP + c * 16, pk);
+              }
+              if (j > 0) rescale_o(alpha);
+              l *= alpha;
+              m_ref = m_new;
+            }
           }
           l += sum2.x + sum2.y;
         } else {
@@ -695,6 +973,11 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention2_kernel(const __grid_
             tmem_st16(tP + c * 16, pk);
           }
           l += sum2.x + sum2.y;
+          if (EARLY) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);
+          }
         }
         tc_wait_st();
         tc_fence_before();
@@ -866,34 +1149,43 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   if (head_dim == 64 && g_tune.att_v2 && p.q_tiles >= 2) {
     const long long pair_slots = (long long)B * heads * ((p.q_tiles + 1) / 2);
     const int grid2 = (int)(pair_slots < num_sms() ? pair_slots : num_sms());
-#define A2_LAUNCH(DT_, PN_, PM_)                                                                                      \
+#define A2_LAUNCH(DT_, PN_, PM_, EARLY_, HALF_)                                                                                    \
   do {                                                                                                                \
-    PCDM_ENSURE_SMEM(A2_SMEM, attention2_kernel<DT_, PN_, PM_>);                                                      \
-    PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_>, dim3(grid2), dim3(A2_THREADS), A2_SMEM, stream, 1, p)); \
+    PCDM_ENSURE_SMEM(A2_SMEM, (attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_>));                                     \
+    PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_>, dim3(grid2),                             \
+                            dim3(HALF_ ? A2_THREADS_HALF : A2_THREADS), A2_SMEM, stream, 1, p));                      \
   } while (0)
 #ifdef PCDM_EXPERIMENT
-    // g_tune.att_dbg: share of exponentials evaluated on the FMA pipe — 0 the release setting (1 of 4 column pairs),
-    // 1 none, 2 = 1 of 3, 3 = 1 of 2 (tools/dev_attn3.py: 124 / 133 / 131 / 142 us at 2048 x 2048)
+    // g_tune.att_dbg: 0 the release setting (1 of 4 column pairs' exp2 on the FMA pipe), 1 none, 2 = 1 of 3 (tools/
+    // dev_attn3.py: 124 / 133 / 131 us at 2048 x 2048; 1 of 2: 142), 3 = release setting + early hand-back of the score
+    // columns, 4 = no FMA-pipe exp2 + early hand-back, 5 = half-row threads (16 softmax warps) with the release exp2 share,
+    // 6 = half-row threads without FMA-pipe exp2
     if (g_tune.att_dbg) {
       if (dtype == DT_F16) {
         switch (g_tune.att_dbg) {
-          case 1: A2_LAUNCH(DT_F16, 0, 1); break;
-          case 2: A2_LAUNCH(DT_F16, 1, 3); break;
-          default: A2_LAUNCH(DT_F16, 1, 2); break;
+          case 1: A2_LAUNCH(DT_F16, 0, 1, false, false); break;
+          case 2: A2_LAUNCH(DT_F16, 1, 3, false, false); break;
+          case 3: A2_LAUNCH(DT_F16, 1, 4, true, false); break;
+          case 5: A2_LAUNCH(DT_F16, 1, 4, false, true); break;
+          case 6: A2_LAUNCH(DT_F16, 0, 1, false, true); break;
+          default: A2_LAUNCH(DT_F16, 0, 1, true, false); break;
         }
       } else {
         switch (g_tune.att_dbg) {
-          case 1: A2_LAUNCH(DT_BF16, 0, 1); break;
-          case 2: A2_LAUNCH(DT_BF16, 1, 3); break;
-          default: A2_LAUNCH(DT_BF16, 1, 2); break;
+          case 1: A2_LAUNCH(DT_BF16, 0, 1, false, false); break;
+          case 2: A2_LAUNCH(DT_BF16, 1, 3, false, false); break;
+          case 3: A2_LAUNCH(DT_BF16, 1, 4, true, false); break;
+          case 5: A2_LAUNCH(DT_BF16, 1, 4, false, true); break;
+          case 6: A2_LAUNCH(DT_BF16, 0, 1, false, true); break;
+          default: A2_LAUNCH(DT_BF16, 0, 1, true, false); break;
         }
       }
       PCDM_CUDA(cudaGetLastError());
       return 0;
     }
 #endif
-    if (dtype == DT_F16) A2_LAUNCH(DT_F16, 1, 4);
-    else A2_LAUNCH(DT_BF16, 1, 4);
+    if (dtype == DT_F16) A2_LAUNCH(DT_F16, 1, 4, false, false);
+    else A2_LAUNCH(DT_BF16, 1, 4, false, false);
 #undef A2_LAUNCH
     PCDM_CUDA(cudaGetLastError());
     return 0;

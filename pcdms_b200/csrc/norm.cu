@@ -148,21 +148,47 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
   const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
   const int c0 = cv * 8;
   const int cpg = C / groups;
-  // gamma / beta are parameters: fetched before the wait on the statistics kernel
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  // Per-channel scale / shift ONCE PER CTA, through shared memory (round 2: every thread used to derive its eight pairs
+  // itself — eight integer divisions and sixteen dependent global loads in front of a loop of only ~10 pixels per
+  // thread).  gamma / beta are parameters: fetched before the wait on the statistics kernel.
+  extern __shared__ __align__(16) float gn_apply_smem[];   // [C] scale | [C] shift
+  float* s_sc = gn_apply_smem;
+  float* s_sh = gn_apply_smem + C;
+  const int tid = py * blockDim.x + cv, nthr = blockDim.x * PY;
+  float gm_r[2], bt_r[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * nthr;
+    gm_r[i] = c < C ? __ldg(gamma + c) : 0.f;
+    bt_r[i] = c < C ? __ldg(beta + c) : 0.f;
+  }
   pdl_wait();
   const float2* stats_b = final_stats + (size_t)b * groups;
-  float2 sc2[4], sh2[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + 2 * k;
-    const float2 sa = stats_b[c / cpg];
-    const float2 sb = stats_b[(c + 1) / cpg];
-    sc2[k] = make_float2(sa.y * gm[2 * k], sb.y * gm[2 * k + 1]);
-    sh2[k] = make_float2(bt[2 * k] - sa.x * sc2[k].x, bt[2 * k + 1] - sb.x * sc2[k].y);
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * nthr;
+    if (c < C) {
+      const float2 st = stats_b[c / cpg];
+      const float sc = st.y * gm_r[i];
+      s_sc[c] = sc;
+      s_sh[c] = bt_r[i] - st.x * sc;
+    }
+  }
+  for (int c = tid + 2 * nthr; c < C; c += nthr) {   // C > 2 x threads: not a shape of this network
+    const float2 st = stats_b[c / cpg];
+    const float sc = st.y * __ldg(gamma + c);
+    s_sc[c] = sc;
+    s_sh[c] = __ldg(beta + c) - st.x * sc;
+  }
+  __syncthreads();
+  float2 sc2[4], sh2[4];
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(s_sc + c0), a1 = *reinterpret_cast<const float4*>(s_sc + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(s_sh + c0), h1 = *reinterpret_cast<const float4*>(s_sh + c0 + 4);
+    sc2[0] = make_float2(a0.x, a0.y); sc2[1] = make_float2(a0.z, a0.w);
+    sc2[2] = make_float2(a1.x, a1.y); sc2[3] = make_float2(a1.z, a1.w);
+    sh2[0] = make_float2(h0.x, h0.y); sh2[1] = make_float2(h0.z, h0.w);
+    sh2[2] = make_float2(h1.x, h1.y); sh2[3] = make_float2(h1.z, h1.w);
   }
   const T* src;
   int cs, coff;
@@ -670,12 +696,12 @@ extern "C" int pcdm_groupnorm(const void* x1, const void* x2, int C1, void* y, c
   if (dtype == DT_F16) {
     PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_F16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
                             pix_per_cta, eps, ws));
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, (size_t)2 * C * sizeof(float), stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
                             (const float2*)ws.final_stats, gamma, beta, silu, y));
   } else {
     PCDM_CUDA(launch_kernel(gn_stats_kernel<DT_BF16>, grid, block, smem, stream, 1, x1, x2, C1, C, HW, groups,
                             pix_per_cta, eps, ws));
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, (size_t)2 * C * sizeof(float), stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
                             (const float2*)ws.final_stats, gamma, beta, silu, y));
   }
   PCDM_CUDA(cudaGetLastError());
@@ -704,10 +730,10 @@ extern "C" int pcdm_groupnorm_apply(const void* x1, const float* stats1, const v
   const dim3 grid(chunks, B), block(C / 8, PY);
   const int silu = (flags & PCDM_FLAG_SILU) ? 1 : 0;
   if (dtype == DT_F16)
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_F16>, grid, block, (size_t)2 * C * sizeof(float), stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
                             (const float2*)final_stats, gamma, beta, silu, y));
   else
-    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, 0, stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
+    PCDM_CUDA(launch_kernel(gn_apply_kernel<DT_BF16>, grid, block, (size_t)2 * C * sizeof(float), stream, 1, x1, x2, C1, C, HW, groups, pix_per_cta,
                             (const float2*)final_stats, gamma, beta, silu, y));
   PCDM_CUDA(cudaGetLastError());
   return 0;

@@ -28,7 +28,13 @@ records = []          # (key, flops, bytes, ev0, ev1)
 
 
 def _nb(*ts):
-    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+    n = 0
+    for t in ts:
+        if isinstance(t, (tuple, list)):      # (tensor, statistics) results of the round-2 fused epilogues
+            n += _nb(*t)
+        elif isinstance(t, torch.Tensor):
+            n += t.numel() * t.element_size()
+    return n
 
 
 def describe(name, args, kw, result):
@@ -49,6 +55,13 @@ def describe(name, args, kw, result):
         tag = "r" if kw.get("residual") is not None else ""
         return (f"conv {H}x{W} {Cin}->{Cout} s{s} {tag}", 2.0 * B * (H // s) * (W // s) * Cout * 9 * Cin,
                 _nb(x, w, result, kw.get("residual")))
+    if name == "conv3x3_up2x":
+        x, w = args[0], args[1]
+        B, H, W, Cin = x.shape
+        Cout = w.shape[1] if w.dim() == 3 else w.shape[0] // 4 if w.dim() == 2 and w.shape[0] % 4 == 0 else w.shape[0]
+        r0 = result[0] if isinstance(result, (tuple, list)) else result
+        Cout = r0.shape[-1]
+        return f"up2x+conv {H}x{W}->{2 * H}x{2 * W} {Cin}->{Cout}", 2.0 * B * 4 * H * W * Cout * 9 * Cin, _nb(x, w, result)
     if name == "groupnorm":
         x1, x2 = args[0], kw.get("x2")
         C_ = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
@@ -92,7 +105,8 @@ for _ in range(2):
     m.forward_nhwc(x9, t, kv, cls, pose)
 torch.cuda.synchronize()
 
-for n in ["gemm", "conv3x3", "groupnorm", "layernorm", "attention", "timestep_embedding", "upsample_nearest2x"]:
+for n in ["gemm", "conv3x3", "conv3x3_up2x", "groupnorm", "layernorm", "attention", "timestep_embedding",
+          "upsample_nearest2x"]:
     setattr(ops, n, wrap(n))
 
 table = OrderedDict()
