@@ -20,6 +20,7 @@ int pcdm_set_attention_small(int on);   /* 0: Sq, Skv <= 32 attention stays on t
 int pcdm_set_attention_poly(int on);    /* 1: half of the softmax exp2 on the FMA pipe (measured slower) */
 int pcdm_set_attention_debug(int code); /* FMA-pipe exp2 share of the two-tile attention kernel: 0 release setting (1 of 4
                                          * column pairs), 1 none, 2 = 1 of 3, 3 = 1 of 2 */
+int pcdm_set_attention_trace(void* device_buffer); /* 2 x 96 x 16 u64: cycle stamps of CTA 0 of the two-tile attention kernel (NULL: off) */
 int pcdm_set_attention_v2(int on);      /* 0: head_dim 64 back on the round-1 kernel (one q-tile per CTA, two CTAs per SM) */
 int pcdm_set_groupnorm_two_pass(int mode); /* 0 automatic, 1 two kernels, 2 single pass, 2 + T single pass with T threads */
 #ifdef __cplusplus

@@ -39,6 +39,7 @@ struct AttnParams {
   void* out;
   long long ldo;       // row stride of O in elements
   float scale_log2;    // softmax scale * log2(e)
+  unsigned long long* trace;   // experiment build: per-block cycle stamps of CTA 0 (tools/dev_attn_trace.py), else NULL
 };
 
 constexpr int ATT_THREADS = 320;   // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax (2 per TMEM quadrant)
@@ -459,7 +460,18 @@ __device__ __forceinline__ bool pair_barrier_or(int id, bool pred) {
 }
 __device__ __forceinline__ void pair_barrier_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-template <int DT, int PN, int PM, bool EARLY, bool HALF>
+// TRACE (experiment build): CTA 0 stamps clock64() at the hand-shakes of its first A2_TRACE_N blocks per tile —
+//   softmax warp of quadrant 0: [0] S landed, [1] chunk 0 in registers, [2] chunk 0 exponentiated, [3] PV(n - 1) seen
+//   retired, [4] / [5] / [6] chunks 1 / 2 / 3 done, [7] P stores complete, p_full arrive;
+//   MMA warp: [8] about to wait for block n - 1, [9] wait passed, [10] QK(n) issued, [11] PV(n - 1) issued.
+constexpr int A2_TRACE_N = 96;
+#define A2_STAMP(t_, n_, k_)                                                                                   \
+  do {                                                                                                         \
+    if (TRACE && p.trace && blockIdx.x == 0 && (n_) < A2_TRACE_N && lane == 0)                                 \
+      p.trace[((t_) * A2_TRACE_N + (n_)) * 16 + (k_)] = (unsigned long long)clock64();                          \
+  } while (0)
+
+template <int DT, int PN, int PM, bool EARLY, bool HALF, bool TRACE = false>
 __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -599,10 +611,14 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
               issue_pv(t, j - 1, pstage);
             }
           } else {
+            A2_STAMP(t, n, 8);
             if (n > 0) mbar_wait(&p_full[t], (uint32_t)((n - 1) & 1));   // softmax finished block n - 1 (also across items)
             tc_fence_after();
+            A2_STAMP(t, n, 9);
             if (j < n_kv) issue_qk(t, j, stage, qb, j == n_kv - 1 && t == it.nt - 1);
+            A2_STAMP(t, n, 10);
             if (j > 0) issue_pv(t, j - 1, pstage);
+            A2_STAMP(t, n, 11);
           }
         }
         if (j > 0) {
@@ -831,6 +847,7 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
       for (int j = 0; j < n_kv; ++j, ++n) {
         mbar_wait(&s_full[t], (uint32_t)(n & 1));
         tc_fence_after();
+        if (q == 0) A2_STAMP(t, n, 0);
         const int kv_left = p.Skv - j * 128;          // valid columns of this block (>= 128: all)
         uint32_t sa[32], sb[32], pk[16];
         if (kv_left >= 128) {
@@ -841,6 +858,7 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
           // more than 2^8 is the block redone from the scores still in TMEM, and O rescaled.  P <= 2^8 as before.
           tmem_ld32(tS, sa);
           tc_wait_ld();
+          if (q == 0) A2_STAMP(t, n, 1);
           tmem_ld32(tS + 32, sb);
           if (j == 0) {
             float a = -INFINITY, b = -INFINITY;
@@ -854,17 +872,21 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
           float mx = -INFINITY;
           float2 sum2 = make_float2(0.f, 0.f);
           a2_chunk<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
+          if (q == 0) A2_STAMP(t, n, 2);
           mbar_wait(&pv_done[t], (uint32_t)((n & 1) ^ 1));   // P_t (and O_t) may only be touched once PV_t(n - 1) has retired
           tc_fence_after();
+          if (q == 0) A2_STAMP(t, n, 3);
           tmem_st16(tP, pk);
           tc_wait_ld();
           tmem_ld32(tS + 64, sa);
           a2_chunk<DT, PN, PM, true>(sb, sc2, m_ref, mx, sum2, pk);
           tmem_st16(tP + 16, pk);
+          if (q == 0) A2_STAMP(t, n, 4);
           tc_wait_ld();
           tmem_ld32(tS + 96, sb);
           a2_chunk<DT, PN, PM, true>(sa, sc2, m_ref, mx, sum2, pk);
           tmem_st16(tP + 32, pk);
+          if (q == 0) A2_STAMP(t, n, 5);
           tc_wait_ld();
           if (EARLY) {
             // the last chunk's maximum directly, and the block's growth check BEFORE the score columns are handed back
@@ -919,6 +941,7 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
             }
           }
           l += sum2.x + sum2.y;
+          if (q == 0) A2_STAMP(t, n, 6);
         } else {
           // ---- ragged last block: the classic order, two passes over the scores in TMEM — true maximum of the valid
           // columns first, then their exponentials (columns past the sequence contribute zeros; chunks the MMAs never
@@ -983,6 +1006,7 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (q == 0) A2_STAMP(t, n, 7);
       }
       // epilogue of the item: O / l
       mbar_wait(&pv_done[t], (uint32_t)((n - 1) & 1));
@@ -1149,10 +1173,11 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
   if (head_dim == 64 && g_tune.att_v2 && p.q_tiles >= 2) {
     const long long pair_slots = (long long)B * heads * ((p.q_tiles + 1) / 2);
     const int grid2 = (int)(pair_slots < num_sms() ? pair_slots : num_sms());
-#define A2_LAUNCH(DT_, PN_, PM_, EARLY_, HALF_)                                                                                    \
+#define A2_LAUNCH(DT_, PN_, PM_, EARLY_, HALF_) A2_LAUNCH_T(DT_, PN_, PM_, EARLY_, HALF_, false)
+#define A2_LAUNCH_T(DT_, PN_, PM_, EARLY_, HALF_, TRACE_)                                                                                    \
   do {                                                                                                                \
-    PCDM_ENSURE_SMEM(A2_SMEM, (attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_>));                                     \
-    PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_>, dim3(grid2),                             \
+    PCDM_ENSURE_SMEM(A2_SMEM, (attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_, TRACE_>));                             \
+    PCDM_CUDA(launch_kernel(attention2_kernel<DT_, PN_, PM_, EARLY_, HALF_, TRACE_>, dim3(grid2),                     \
                             dim3(HALF_ ? A2_THREADS_HALF : A2_THREADS), A2_SMEM, stream, 1, p));                      \
   } while (0)
 #ifdef PCDM_EXPERIMENT
@@ -1160,6 +1185,12 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
     // dev_attn3.py: 124 / 133 / 131 us at 2048 x 2048; 1 of 2: 142), 3 = release setting + early hand-back of the score
     // columns, 4 = no FMA-pipe exp2 + early hand-back, 5 = half-row threads (16 softmax warps) with the release exp2 share,
     // 6 = half-row threads without FMA-pipe exp2
+    if (g_tune.att_trace && dtype == DT_BF16) {   // cycle stamps of CTA 0 (release configuration of the kernel)
+      p.trace = reinterpret_cast<unsigned long long*>(g_tune.att_trace);
+      A2_LAUNCH_T(DT_BF16, 1, 4, false, false, true);
+      PCDM_CUDA(cudaGetLastError());
+      return 0;
+    }
     if (g_tune.att_dbg) {
       if (dtype == DT_F16) {
         switch (g_tune.att_dbg) {
@@ -1187,6 +1218,7 @@ extern "C" int pcdm_attention_hd(const void* q, long long ldq, const void* k, lo
     if (dtype == DT_F16) A2_LAUNCH(DT_F16, 1, 4, false, false);
     else A2_LAUNCH(DT_BF16, 1, 4, false, false);
 #undef A2_LAUNCH
+#undef A2_LAUNCH_T
     PCDM_CUDA(cudaGetLastError());
     return 0;
   }

@@ -101,5 +101,6 @@ extern "C" int pcdm_set_attention_small(int on) { pcdm::g_tune.att_small = on ? 
 extern "C" int pcdm_set_attention_poly(int on) { pcdm::g_tune.att_poly = on ? 1 : 0; return 0; }
 extern "C" int pcdm_set_attention_v2(int on) { pcdm::g_tune.att_v2 = on ? 1 : 0; return 0; }
 extern "C" int pcdm_set_attention_debug(int mask) { pcdm::g_tune.att_dbg = mask; return 0; }
+extern "C" int pcdm_set_attention_trace(void* buf) { pcdm::g_tune.att_trace = buf; return 0; }
 extern "C" int pcdm_set_groupnorm_two_pass(int mode) { pcdm::g_tune.gn_mode = mode; return 0; }
 #endif

@@ -30,6 +30,7 @@ struct Tuning {
   int att_small = 1;       // Sq, Skv <= 32 attention on the one-warp-per-head kernel
   int att_poly = 0;        // half of the softmax exp2 on the FMA pipe
   int att_v2 = 1;          // head_dim 64, >= 2 query tiles: the persistent two-tile kernel (0: the round-1 kernel, for A/B)
+  void* att_trace = nullptr;   // experiment build: device buffer for the two-tile attention kernel's cycle stamps
   int att_dbg = 0;         // experiment build: FMA-pipe exp2 share of that kernel (0 release setting 1/4, 1 none, 2 = 1/3, 3 = 1/2)
   int gn_mode = 0;         // 0 auto, 1 two kernels, 2 single pass, 2 + T single pass with T threads per CTA
 };

@@ -258,16 +258,58 @@ def ln_gemm(x, gamma, beta, eps, w, out=None, *, bias=None, rowvec=None, rows_pe
     return out
 
 
+def conv_tile_geometry(H, W):
+    """The output sizes the implicit-GEMM tile map covers directly (an M-tile is 128 consecutive NHWC pixels = whole rows
+    of a width that divides 128, or a 128-pixel segment of a row whose width is a multiple of 128), and the smallest
+    such (Hp, Wp) >= (H, W) for everything else.  -> (ok, Hp, Wp)"""
+    if W > 128:
+        Wp = (W + 127) // 128 * 128
+        return Wp == W, H, Wp
+    Wp = 1 << max(W - 1, 0).bit_length()            # next power of two
+    rows = 128 // Wp                                 # rows per tile
+    if H * Wp >= 128 or H > rows:
+        Hp = (H + rows - 1) // rows * rows
+    else:
+        Hp = 1 << max(H - 1, 0).bit_length()        # H * W < 128: the image must divide a tile
+    return (Wp == W and Hp == H), Hp, Wp
+
+
+def _pad_hw(t, Hp, Wp):
+    """Zero-pad an NHWC tensor at the bottom / right (layout plumbing for the odd-canvas fallback below)."""
+    B, H, W, C_ = t.shape
+    o = torch.zeros((B, Hp, Wp, C_), device=t.device, dtype=t.dtype)
+    o[:, :H, :W] = t
+    return o
+
+
 def conv3x3(x, w_packed, out=None, *, bias=None, rowvec=None, residual=None, stride=1, out_f32=False, silu=False,
             pad_br=False, bn=0, cta_group=0, chan_stats=False):
     """x: [B, Hin, Win, Cin] NHWC; w_packed: [Cout, 9*Cin]; returns [B, Hin/stride, Win/stride, Cout].
     pad_br (stride 2 only): zero padding on the bottom/right instead of all round (the VAE encoder's downsampler).
-    chan_stats=True: -> `(out, ChanStats | None)`, the GroupNorm statistics of the output from the epilogue."""
+    chan_stats=True: -> `(out, ChanStats | None)`, the GroupNorm statistics of the output from the epilogue.
+
+    Output sizes outside the tile map (a latent width that neither divides 128 nor is a multiple of it — no BASELINE
+    configuration, but the reference accepts any canvas divisible by 8, stage2_batchtest_inpaint_model.py:258-260) run
+    on the next covered size: zeros appended at the bottom / right of the input are exactly the convolution's own zero
+    padding, so the outputs inside the real image are unchanged and the rest is cut off again.  Exact; costs the
+    padded work plus two copies; no epilogue statistics (the consumer GroupNorm then takes its own)."""
     lib = _l.load()
     B, Hin, Win, Cin = x.shape
     Cout = w_packed.shape[0]
     assert w_packed.shape[1] == 9 * Cin and x.is_contiguous() and w_packed.is_contiguous()
     H, W = Hin // stride, Win // stride
+    ok, Hp, Wp = conv_tile_geometry(H, W)
+    if not ok:
+        assert Hin == H * stride and Win == W * stride
+        res_p = _pad_hw(residual, Hp, Wp) if residual is not None else None
+        full = conv3x3(_pad_hw(x, Hp * stride, Wp * stride), w_packed, bias=bias, rowvec=rowvec, residual=res_p,
+                       stride=stride, out_f32=out_f32, silu=silu, pad_br=pad_br, bn=bn, cta_group=cta_group)
+        cut = full[:, :H, :W]
+        if out is None:
+            out = cut.contiguous()
+        else:
+            out.copy_(cut)
+        return (out, None) if chan_stats else out
     if out is None:
         out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
     assert out.is_contiguous() and tuple(out.shape) == (B, H, W, Cout)
@@ -294,6 +336,18 @@ def conv3x3_up2x(x, w_up, out=None, *, bias=None, silu=False, bn=0, cta_group=0,
     B, H, W, Cin = x.shape
     Cout = w_up.shape[1]
     assert w_up.shape == (4, Cout, 4 * Cin) and x.is_contiguous() and w_up.is_contiguous()
+    ok, Hp, Wp = conv_tile_geometry(H, W)
+    if not ok or W > 128 or (W < 32 and (32 % W or (H * W) % 32) and H * W >= 32):   # odd canvases: see conv3x3
+        if W > 128:
+            raise NotImplementedError("conv3x3_up2x: input rows wider than 128 pixels (no caller has them)")
+        if ok:                                       # tile map fine, the 32-pixel store boxes are not: pad to 32 | H*W
+            Hp, Wp = (H + (32 // W) - 1) // (32 // W) * (32 // W), W
+        cut = conv3x3_up2x(_pad_hw(x, Hp, Wp), w_up, bias=bias, silu=silu, bn=bn, cta_group=cta_group)[:, :2 * H, :2 * W]
+        if out is None:
+            out = cut.contiguous()
+        else:
+            out.copy_(cut)
+        return (out, None) if chan_stats else out
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=x.dtype)
     assert out.is_contiguous() and tuple(out.shape) == (B, 2 * H, 2 * W, Cout)

@@ -266,13 +266,52 @@ def test_two_devices_from_one_process(ops):
 
 
 def test_conv3x3_rejects_unsupported_shapes(ops):
-    from pcdms_b200.lib import PcdmError
+    """The C entry point itself still refuses output sizes its tile map does not cover (the host wrapper pads them)."""
+    import ctypes as C
+    from pcdms_b200 import lib as _l
+    L = _l.load()
     x = torch.zeros(1, 8, 24, 64, device="cuda", dtype=torch.float16)  # W = 24 does not divide 128
-    with pytest.raises(PcdmError):
-        ops.conv3x3(x, torch.zeros(64, 9 * 64, device="cuda", dtype=torch.float16))
-    with pytest.raises(PcdmError):  # Cin not a multiple of 64
-        ops.conv3x3(torch.zeros(1, 8, 16, 48, device="cuda", dtype=torch.float16),
-                    torch.zeros(64, 9 * 48, device="cuda", dtype=torch.float16))
+    w = torch.zeros(64, 9 * 64, device="cuda", dtype=torch.float16)
+    out = torch.empty(1, 8, 24, 64, device="cuda", dtype=torch.float16)
+    rc = L.pcdm_conv3x3(_l.ptr(x), _l.ptr(w), _l.ptr(out), None, None, C.c_longlong(0), None, C.c_int(1), C.c_int(8),
+                        C.c_int(24), C.c_int(64), C.c_int(64), C.c_int(1), C.c_int(0), C.c_int(0), C.c_int(0), None, None)
+    assert rc == _l.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 12, 24, 64, 64, 1), (2, 6, 12, 128, 64, 1), (1, 3, 6, 64, 128, 1),
+                                                   (2, 48, 96, 64, 32, 1), (2, 12, 24, 64, 64, 2), (1, 5, 3, 64, 64, 1),
+                                                   (1, 11, 22, 64, 64, 2), (1, 40, 200, 64, 32, 1)])
+def test_conv3x3_any_canvas(ops, dt, B, H, W, Cin, Cout, stride):
+    """Latent sizes outside the tile map (widths that neither divide 128 nor are multiples of it, row counts that do not
+    fill whole tiles) — the reference accepts any canvas divisible by 8 (stage2_batchtest_inpaint_model.py:258-260).
+    The wrapper runs them on the next covered size: appended zeros ARE the convolution's zero padding."""
+    g = torch.Generator().manual_seed(H * W + Cin)
+    x = torch.randn(B, Cin, H * stride, W * stride, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dt)
+    b = torch.randn(Cout, generator=g)
+    t = torch.randn(B, Cout, generator=g)
+    r = torch.randn(B, Cout, H, W, generator=g).to(dt)
+    ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1) + t[:, :, None, None] + r.float()
+    out, st = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_conv3x3_weight(w, dt).cuda(), bias=b.cuda(),
+                          rowvec=t.cuda(), residual=r.permute(0, 2, 3, 1).contiguous().cuda(), stride=stride,
+                          chan_stats=True)
+    assert st is None and out.shape == (B, H, W, Cout)
+    close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 6, 12, 64, 64), (1, 12, 24, 128, 64), (1, 3, 6, 64, 64)])
+def test_conv3x3_up2x_any_canvas(ops, B, H, W, Cin, Cout):
+    dt = torch.float16
+    g = torch.Generator().manual_seed(H * W + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dt)
+    w32 = torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = ops.conv3x3_up2x(xd, ops.pack_upsample_conv_weight(w32, dt).cuda(), bias=b.cuda())
+    assert out.shape == (B, 2 * H, 2 * W, Cout)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2, mode="nearest"), w32, b, padding=1)
+    torch.testing.assert_close(out.permute(0, 3, 1, 2).float().cpu(), ref, rtol=4e-3, atol=4e-3)   # taps pre-summed in 16 bits
 
 
 @pytest.mark.parametrize("dt", DTS)

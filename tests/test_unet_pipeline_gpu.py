@@ -91,6 +91,23 @@ def test_unet_tiny_with_producer_groupnorm_statistics_everywhere():
            config="tiny UNet B2 16x32 s_kv9", dtype=torch.float16)
 
 
+@pytest.mark.parametrize("h,w", [(24, 48), (8, 24)])
+def test_unet_tiny_on_a_canvas_outside_the_tile_map(h, w):
+    """A latent size no BASELINE configuration has (the reference takes any canvas divisible by 8,
+    stage2_batchtest_inpaint_model.py:258-260): widths 48 / 24 / 12 / 6 neither divide 128 nor are multiples of it, so
+    every conv of the net takes the padded route; GroupNorm, attention (1152 / 288 / 72 / 18 tokens) and the GEMMs run
+    on the real sizes."""
+    from oracle.factory import make_unet_inputs
+    from oracle.unet import UNetConfig
+    cfg = UNetConfig.tiny()
+    o, m = _models(cfg, torch.float16)
+    i = make_unet_inputs(cfg, batch=2, h=h, w=w, s_kv=9)
+    out, ref = _run_unet(o, m, i, 501)
+    assert out.shape == ref.shape
+    _check(out, ref, 3e-3, 5e-4, f"tiny stage-2 UNet fp16 on a {h}x{w} latent canvas",
+           config=f"tiny UNet B2 {h}x{w} (outside the conv tile map)", dtype=torch.float16)
+
+
 def test_unet_tiny_stage3_topology():
     from oracle.factory import make_unet_inputs
     from oracle.unet import UNetConfig
