@@ -377,6 +377,16 @@ struct A2Item { int b, h, qt, nt; };   // nt = 1 or 2 query tiles (qt, qt + 1) o
 
 // item k of this CTA -> its tiles.  `pairs` = ceil(q_tiles / 2) pair slots per (b, h); items [0, full) are pairs, the
 // remaining pair slots are issued as two single-tile items each.
+// (item boundaries are on every role's critical path: the two divisions go through the float reciprocal + one exact
+// correction step instead of the ~40-instruction integer division sequence)
+__device__ __forceinline__ int a2_div(int x, int d, int* rem) {
+  int qv = __float2int_rz(__fdividef((float)x + 0.5f, (float)d));
+  int r = x - qv * d;
+  if (r < 0) { --qv; r += d; }
+  else if (r >= d) { ++qv; r -= d; }
+  *rem = r;
+  return qv;
+}
 __device__ __forceinline__ A2Item a2_item(const AttnParams& p, int item, int pairs, int full, int total_items) {
   A2Item it;
   it.nt = 0; it.b = it.h = it.qt = 0;
@@ -384,8 +394,10 @@ __device__ __forceinline__ A2Item a2_item(const AttnParams& p, int item, int pai
   int slot, want;   // slot = tile slot index (2 per pair)
   if (item < full) { slot = 2 * item; want = 2; }
   else { slot = 2 * full + (item - full); want = 1; }
-  const int bh = slot / (2 * pairs), qt = slot - bh * 2 * pairs;
-  it.h = bh % p.heads; it.b = bh / p.heads; it.qt = qt;
+  int qt, h;
+  const int bh = a2_div(slot, 2 * pairs, &qt);
+  it.b = a2_div(bh, p.heads, &h);
+  it.h = h; it.qt = qt;
   it.nt = qt >= p.q_tiles ? 0 : ((want == 2 && qt + 1 < p.q_tiles) ? 2 : 1);
   return it;
 }
@@ -1014,20 +1026,31 @@ __global__ void __launch_bounds__(HALF ? A2_THREADS_HALF : A2_THREADS, 1) attent
       const float inv_l = 1.0f / l;
       const long long qrow = (long long)(it.qt + t) * 128 + row;
       T* op = reinterpret_cast<T*>(p.out) + ((long long)it.b * p.Sq + qrow) * p.ldo + it.h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[16];
-        tmem_ld16(tO + c * 16, o);
+      {
+        // all 64 accumulator columns in one TMEM round trip (four dependent load -> wait -> store rounds cost an item
+        // ~2800 cycles here, r2_attn_trace_258_items.log), then eight 16-byte stores per row
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tO, o0);
+        tmem_ld32(tO + 32, o1);
         tc_wait_ld();
         if (qrow < p.Sq) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = pack2<DT>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-            u.y = pack2<DT>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-            u.z = pack2<DT>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-            u.w = pack2<DT>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(op + c * 16 + i * 8) = u;
+            u.x = pack2<DT>(__uint_as_float(o0[i * 8 + 0]) * inv_l, __uint_as_float(o0[i * 8 + 1]) * inv_l);
+            u.y = pack2<DT>(__uint_as_float(o0[i * 8 + 2]) * inv_l, __uint_as_float(o0[i * 8 + 3]) * inv_l);
+            u.z = pack2<DT>(__uint_as_float(o0[i * 8 + 4]) * inv_l, __uint_as_float(o0[i * 8 + 5]) * inv_l);
+            u.w = pack2<DT>(__uint_as_float(o0[i * 8 + 6]) * inv_l, __uint_as_float(o0[i * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + i * 8) = u;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack2<DT>(__uint_as_float(o1[i * 8 + 0]) * inv_l, __uint_as_float(o1[i * 8 + 1]) * inv_l);
+            u.y = pack2<DT>(__uint_as_float(o1[i * 8 + 2]) * inv_l, __uint_as_float(o1[i * 8 + 3]) * inv_l);
+            u.z = pack2<DT>(__uint_as_float(o1[i * 8 + 4]) * inv_l, __uint_as_float(o1[i * 8 + 5]) * inv_l);
+            u.w = pack2<DT>(__uint_as_float(o1[i * 8 + 6]) * inv_l, __uint_as_float(o1[i * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + 32 + i * 8) = u;
           }
         }
       }

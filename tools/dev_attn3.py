@@ -24,7 +24,7 @@ def ref(q, k, v, B, heads):
 
 
 torch.manual_seed(0)
-VARIANTS = [(0, 0), (1, 0), (1, 3), (1, 4), (1, 5), (1, 6)]   # (two-tile kernel on, pcdm_set_attention_debug code: 0 release = 1/4 of the exp2 on the FMA pipe, 1 none, 2 = 1/3, 3 = release + early score hand-back, 4 = none + early hand-back, 5 = half-row threads + release share, 6 = half-row threads, no FMA-pipe exp2)
+VARIANTS = [(0, 0), (1, 0), (1, 3)]   # (two-tile kernel on, pcdm_set_attention_debug code: 0 release = 1/4 of the exp2 on the FMA pipe, 1 none, 2 = 1/3, 3 = release + early score hand-back, 4 = none + early hand-back, 5 = half-row threads + release share, 6 = half-row threads, no FMA-pipe exp2)
 for dt in (torch.float16, torch.bfloat16):
     for (B, heads, Sq, Skv, grow) in [(2, 5, 2048, 2048, 0), (2, 5, 1024, 1024, 1), (2, 10, 512, 512, 0), (2, 5, 2048, 258, 0),
                                       (1, 2, 384, 300, 1), (1, 5, 256, 95, 0), (3, 20, 128, 128, 0), (2, 3, 200, 2048, 1)]:

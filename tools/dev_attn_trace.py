@@ -24,13 +24,14 @@ out = torch.empty_like(q)
 for _ in range(3):
     ops.attention(q, k, v, B, heads, out=out)
 torch.cuda.synchronize()
-trace = torch.zeros(2 * N * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * N * 16 + 32 * 8, dtype=torch.int64, device=dev)
 L.pcdm_set_attention_trace.argtypes = [C.c_void_p]
 L.pcdm_set_attention_trace(C.c_void_p(trace.data_ptr()))
 ops.attention(q, k, v, B, heads, out=out)
 torch.cuda.synchronize()
 L.pcdm_set_attention_trace(C.c_void_p(0))
-tr = trace.cpu().view(2, N, 16)
+items = trace.cpu()[2 * N * 16:].view(32, 8)
+tr = trace.cpu()[:2 * N * 16].view(2, N, 16)
 n_kv = (Skv + 127) // 128
 t0 = int(tr[tr > 0].min())
 names = ["S landed", "chunk0 in regs", "chunk0 exp done", "PV(n-1) retired seen", "chunk1 done", "chunk2 done", "chunk3 done",
@@ -61,3 +62,10 @@ for t in range(2):
           f"wait passed -> QK issued {(nxt[:, 10] - nxt[:, 9]).mean().item():6.0f}, QK issued -> S landed "
           f"{(nxt[:, 0] - nxt[:, 10]).mean().item():6.0f}, QK issued -> PV issued {(nxt[:, 11] - nxt[:, 10]).mean().item():6.0f}, "
           f"MMA idle before the wait {(nxt[:, 9] - nxt[:, 8]).mean().item():6.0f}")
+
+print("--- per item (cycles since the CTA's first stamp): MMA [0] item start [1] Q landed [2] first K/V landed | TMA [3] Q buffer free "
+      "[4] first K/V slot free | softmax tile 0 [5] last PV retired [6] O written [7] first S landed")
+for i in range(32):
+    if int(items[i].max()) == 0:
+        break
+    print(f"item {i:2d}: " + " ".join(f"{(int(x) - t0) if int(x) else -1:8d}" for x in items[i]))
