@@ -394,9 +394,46 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
                      __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
 }
 
-// Two GELUs at once: the same A&S 7.1.26 form with the fp32 arithmetic on the packed FFMA2 path (the GEGLU epilogue
-// is issue-bound: ~10 issue slots + 2 SFU ops per element instead of ~22 + 2).
-__device__ __forceinline__ float2 gelu_erf2_f(float2 x) {
+// Two GELUs at once with ONE SFU op per element (round 2; the GEGLU epilogue evaluates this 42 M times per UNet step and
+// its three per-tile costs — SFU ops, TMEM reads, issue slots — add up instead of overlapping).  With t = |x|:
+//   gelu(x) = x Phi(x) = max(x, 0) - t Phi(-t),   Phi(-t) = 2^P(t),   P = polynomial fit of log2 Phi(-t)
+// (no reciprocal, no cancellation in the negative tail: the small quantity is produced directly by the ex2).  The fit is
+// weighted by t Phi(-t), i.e. minimises the absolute error of the result: DEG 8 -> 2.5e-7 (the A&S 7.1.26 form it
+// replaces: 1.5e-7 |x| / 2), DEG 5 -> 6.4e-7 — both at the level of one fp32 rounding of the result and 2-3 orders of
+// magnitude below the 16-bit output rounding (tools/fit_gelu.py regenerates and checks the coefficients).  The leading
+// coefficients are negative, so P -> -inf and the correction term vanishes for |x| beyond the fitted range.
+// ~10 (DEG 5) / ~13 (DEG 8) issue slots + 2 SFU ops per pair, against ~19 + 4 for the form below.
+template <int DEG>
+__device__ __forceinline__ float2 gelu2_phi(float2 x) {
+  static_assert(DEG == 5 || DEG == 8, "fitted degrees");
+  const float2 t = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 p;
+#define PCDM_C2(v) make_float2(v, v)
+  if (DEG == 5) {
+    p = __ffma2_rn(PCDM_C2(-4.732939706e-04f), t, PCDM_C2(7.084460929e-03f));
+    p = __ffma2_rn(p, t, PCDM_C2(-5.182716995e-02f));
+    p = __ffma2_rn(p, t, PCDM_C2(-4.599926472e-01f));
+    p = __ffma2_rn(p, t, PCDM_C2(-1.150787711e+00f));
+    p = __ffma2_rn(p, t, PCDM_C2(-1.000037670e+00f));
+  } else {
+    p = __ffma2_rn(PCDM_C2(-1.690381168e-06f), t, PCDM_C2(2.508305806e-05f));
+    p = __ffma2_rn(p, t, PCDM_C2(-1.144614507e-04f));
+    p = __ffma2_rn(p, t, PCDM_C2(-3.233452735e-04f));
+    p = __ffma2_rn(p, t, PCDM_C2(7.333388552e-03f));
+    p = __ffma2_rn(p, t, PCDM_C2(-5.271420255e-02f));
+    p = __ffma2_rn(p, t, PCDM_C2(-4.591154456e-01f));
+    p = __ffma2_rn(p, t, PCDM_C2(-1.151123285e+00f));
+    p = __ffma2_rn(p, t, PCDM_C2(-9.999988675e-01f));
+  }
+#undef PCDM_C2
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p.y));
+  return __ffma2_rn(make_float2(-t.x, -t.y), make_float2(e0, e1), make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+
+// The former two-SFU-op form (A&S 7.1.26: rcp + 5-term Horner + ex2), kept for the A/B build (-DPCDM_GELU_AS).
+__device__ __forceinline__ float2 gelu_erf2_as(float2 x) {
   const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
   const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
   float t0, t1, e0, e1;
@@ -415,6 +452,15 @@ __device__ __forceinline__ float2 gelu_erf2_f(float2 x) {
   const float2 erf = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
   const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(h, erf, h);
+}
+
+// exact-form GELU for a 16-bit output of type DT: bf16 takes the degree-5 fit, fp16 the degree-8 one
+template <int DT> __device__ __forceinline__ float2 gelu_erf2_f(float2 x) {
+#ifdef PCDM_GELU_AS
+  return gelu_erf2_as(x);
+#else
+  return gelu2_phi<DT == DT_BF16 ? 5 : 8>(x);
+#endif
 }
 
 // max of three in ONE instruction (FMNMX3, sm_100): halves the row-maximum pass of the attention softmax

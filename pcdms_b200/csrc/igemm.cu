@@ -134,13 +134,14 @@ __device__ __forceinline__ void ln_prefetch(const IGemmParams& p, long long m) {
 // One GEGLU chunk of a row: 32 value + 32 gate accumulators -> 32 outputs  value * act(gate)  (+ bias, + folded LayerNorm:
 // rstd * acc + bias', rstd == 1 otherwise).  ACT: 1 = SiLU (SwiGLU, DINOv2's FFN), 2 = GELU erf (GEGLU, diffusers).
 // Straight-line code: the eight iterations are independent and the compiler interleaves their MUFU / FFMA2 chains.
-template <int DT, int ACT>
-__device__ __forceinline__ void geglu_math(const uint32_t (&rh)[32], const uint32_t (&rg)[32], const float* __restrict__ bias,
-                                           int n0, float2 rstd2, uint32_t (&o)[16]) {
+template <int DT, int ACT, int NC>
+__device__ __forceinline__ void geglu_math(const uint32_t (&rh)[NC], const uint32_t (&rg)[NC], const float* __restrict__ bias,
+                                           int n0, int off, float2 rstd2, uint32_t (&o)[NC / 2]) {
+  // rh / rg: NC value / gate accumulators of chunk columns [off, off + NC); bias = [32 value | 32 gate] per chunk
   const bool has_bias = bias != nullptr;
-  const float* bp = has_bias ? bias + n0 : nullptr;
+  const float* bp = has_bias ? bias + n0 + off : nullptr;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < NC; j += 4) {
     float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
     if (has_bias) {
       bh = __ldg(reinterpret_cast<const float4*>(bp + j));
@@ -150,8 +151,8 @@ __device__ __forceinline__ void geglu_math(const uint32_t (&rh)[32], const uint3
     const float2 h1 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rh[j + 2]), __uint_as_float(rh[j + 3])), make_float2(bh.z, bh.w));
     const float2 g0 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), make_float2(bg.x, bg.y));
     const float2 g1 = __ffma2_rn(rstd2, make_float2(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), make_float2(bg.z, bg.w));
-    const float2 v0 = __fmul2_rn(h0, ACT == 1 ? silu2_exact(g0) : gelu_erf2_f(g0));
-    const float2 v1 = __fmul2_rn(h1, ACT == 1 ? silu2_exact(g1) : gelu_erf2_f(g1));
+    const float2 v0 = __fmul2_rn(h0, ACT == 1 ? silu2_exact(g0) : gelu_erf2_f<DT>(g0));
+    const float2 v1 = __fmul2_rn(h1, ACT == 1 ? silu2_exact(g1) : gelu_erf2_f<DT>(g1));
     o[j / 2] = pack2<DT>(v0.x, v0.y);
     o[j / 2 + 1] = pack2<DT>(v1.x, v1.y);
   }
@@ -484,6 +485,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             if (lane == 0) bulk_wait_read<1>();   // every store but the most recent has finished reading its slot
             __syncwarp();
           }
+          // (requesting chunk c + 2 here, under the arithmetic of chunk c, was measured 10-15 % SLOWER on the short-K GEMMs:
+          //  profiles/r2_s3_epilogue.md)
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tc_wait_ld();
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             for (int j = 0; j < 16; ++j) v[j] = silu2_exact(v[j]);
           } else if (p.silu == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_erf2_f(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf2_f<DT>(v[j]);
           }
           if (p.stats_out) {
 #pragma unroll
@@ -620,9 +623,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           // packed fp32 (FFMA2) arithmetic.  The gate activation is chosen OUTSIDE the unrolled loop: a warp-uniform
           // `silu ? a : b` inside it compiled to a branch per element pair, which fenced the eight independent GELU
           // chains off from each other (no instruction-level parallelism: the K = 320 GEGLU GEMM ran at 0.4 of its bound).
+          // (Streaming the chunk in two 16 + 16 column halves with the TMEM reads one half ahead of the GELUs was
+          //  measured 8 % SLOWER: profiles/r2_s3_epilogue.md.)
           uint32_t o[16];
-          if (p.silu == 1) geglu_math<DT, 1>(rh, rg, p.bias, n0, ln_rstd2, o);
-          else geglu_math<DT, 2>(rh, rg, p.bias, n0, ln_rstd2, o);
+          if (p.silu == 1) geglu_math<DT, 1, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
+          else geglu_math<DT, 2, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
