@@ -27,7 +27,7 @@ namespace pcdm {
 #endif
 
 constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
-constexpr int IG_EPI_WARPS = 8;
+constexpr int IG_EPI_WARPS = 8;        // EW of the kernel template: 8, or 16 for the GEGLU-only instances (640 threads)
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
 constexpr int IG_RES_SLOTS = 5;        // residual slots per epilogue warp: the chunks one warp owns in a <= 320-wide tile
 constexpr int IG_MAX_STAGES = 8;
@@ -161,18 +161,23 @@ __device__ __forceinline__ void geglu_math(const uint32_t (&rh)[NC], const uint3
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA loads its own 128 activation rows and HALF of the weight tile, the leader CTA issues the M = 256 MMAs, each
 // CTA's TMEM receives (and each CTA's epilogue stores) its own 128 rows.
-template <int BN, int DT, int CG>
-__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IGemmParams p) {
+// EW = epilogue warps.  8 everywhere except the GEGLU GEMMs with a short K, whose epilogue (two TMEM reads, a GELU and a
+// product per output) out-lasts the tile's MMAs 2.4 : 1 with two warps per scheduler issuing on 17 % of their cycles
+// (profiles/r2_s3_epilogue.md): EW = 16 puts four warps on every scheduler, one 64-column chunk of the tile each.
+// An EW = 16 instance compiles the GEGLU epilogue only.
+template <int BN, int DT, int CG, int EW = IG_EPI_WARPS>
+__global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_constant__ IGemmParams p) {
+  static_assert(EW == 8 || EW == 16, "epilogue warps");
   using Cfg = IGemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + p.stages * Cfg::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + EW * p.nbuf * IG_SLOT_BYTES);
   uint64_t* empty = full + IG_MAX_STAGES;
   uint64_t* tfull = empty + IG_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* res_bar = tempty + 2;                 // [IG_EPI_WARPS][IG_RES_SLOTS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + IG_EPI_WARPS * IG_RES_SLOTS);
+  uint64_t* res_bar = tempty + 2;                 // [EW][IG_RES_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EW * IG_RES_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -194,9 +199,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], IG_EPI_WARPS * CG);
+      mbar_init(&tempty[i], EW * CG);
     }
-    for (int i = 0; i < IG_EPI_WARPS * IG_RES_SLOTS; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < EW * IG_RES_SLOTS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -378,11 +383,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps: TMEM quadrant q, column-chunk parity `half`) =====================
+    // ===================== epilogue (EW warps: TMEM quadrant q, column-chunk phase `half` of CSTEP) ==============
     using T = typename TypeOf<DT>::T;
     const int e = warp - 4;
     const int q = e & 3;      // == warp % 4: the TMEM lane quadrant this warp may touch
     const int half = e >> 2;
+    constexpr int CSTEP = EW / 4;   // warps per TMEM quadrant: each takes every CSTEP-th column chunk of the tile
     const int row = q * 32 + lane;
     uint8_t* slots = epi_smem + e * p.nbuf * IG_SLOT_BYTES;
     const uint32_t slots_s = smem_u32(slots);
@@ -409,12 +415,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       const int cols_here = min(BN, p.N - n_tile0);
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const float* rv = (p.rowvec && valid) ? p.rowvec + (long long)(m / p.hw) * p.ld_rowvec : nullptr;
-      if (p.out_f32) {
+      if (EW == 8 && p.out_f32) {
         // ---- fp32 output (conv_out, stacked time-embedding projection): direct per-row stores ----
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = half; c * 32 < cols_here; c += 2) {
+        for (int c = half; c * 32 < cols_here; c += CSTEP) {
           const int n0 = n_tile0 + c * 32;
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
           }
         }
-      } else if (!p.geglu) {
+      } else if (EW == 8 && !p.geglu) {
         // ---- 16-bit output: TMEM -> registers -> (+bias, +rowvec, +residual, act) -> swizzled smem slot -> TMA store.
         //      ALL residual chunks this warp owns in the tile are TMA-prefetched (one slot each) before the wait for the
         //      tile's MMAs: their HBM latency overlaps the mainloop instead of being paid chunk by chunk (a short-K
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           if (lane == 0) {
             bulk_wait_read<0>();   // this warp's earlier stores have finished reading their slots
             int i = 0;
-            for (int c = half; c * 32 < cols_here; c += 2, ++i) {
+            for (int c = half; c * 32 < cols_here; c += CSTEP, ++i) {
               mbar_expect_tx(&rbar[i], IG_SLOT_BYTES);
               tma_load_2d(slots + i * IG_SLOT_BYTES, &p.tmRes, &rbar[i], n_tile0 + c * 32, m_warp0);
             }
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         tc_fence_after();
         int ci = 0;
 #pragma unroll 1
-        for (int c = half; c * 32 < cols_here && !IG_DBG(p, 8); c += 2, ++ci) {
+        for (int c = half; c * 32 < cols_here && !IG_DBG(p, 8); c += CSTEP, ++ci) {
           const int n0 = n_tile0 + c * 32;
           const uint32_t slot = use_res ? (uint32_t)ci : (cnt & (uint32_t)(nbuf - 1));   // nbuf is 2 or 4
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = half; c * 64 < cols_here; c += 2) {
+        for (int c = half; c * 64 < cols_here; c += CSTEP) {
           const int n0 = n_tile0 + c * 64;
           const uint32_t slot = cnt & (uint32_t)(nbuf - 1);
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
@@ -719,13 +725,13 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits,
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_SMEM_LIMIT = 227 * 1024;
 
-template <int BN, int DT, int CG>
+template <int BN, int DT, int CG, int EW = IG_EPI_WARPS>
 static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, CG>;
-  PCDM_ENSURE_SMEM(IG_SMEM_LIMIT, igemm_kernel<BN, DT, CG>);
+  PCDM_ENSURE_SMEM(IG_SMEM_LIMIT, igemm_kernel<BN, DT, CG, EW>);
   p.nbuf = p.has_res ? (BN > 256 ? 5 : 4) : 2;   // residual: one slot per 32-column chunk a warp owns in the tile
   p.dbg = g_tune.gemm_dbg;
-  const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + IG_EPI_WARPS * p.nbuf * IG_SLOT_BYTES;
+  const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + EW * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
   if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
   if (stages > g_tune.max_stages) stages = g_tune.max_stages;
@@ -733,17 +739,25 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   p.stages = stages;
   const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
   const int total = p.m_tiles * p.n_tiles * p.splits;
+  constexpr int threads = (4 + EW) * 32;
   if (CG == 1) {
     const int grid = total < num_sms() ? total : num_sms();
-    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG>, dim3(grid), dim3(IG_THREADS), smem_bytes, stream, 1, p));
+    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG, EW>, dim3(grid), dim3(threads), smem_bytes, stream, 1, p));
   } else {
     const int pairs = num_sms() / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
-    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG>, dim3(grid), dim3(IG_THREADS), smem_bytes, stream, 2, p));
+    PCDM_CUDA(launch_kernel(igemm_kernel<BN, DT, CG, EW>, dim3(grid), dim3(threads), smem_bytes, stream, 2, p));
   }
   PCDM_CUDA(cudaGetLastError());
   return 0;
 }
+
+// GEGLU GEMMs on 256-wide CTA-pair tiles run the 16-epilogue-warp instance up to this many 64-deep k-blocks per tile
+// (measured, profiles/r2_s3_epilogue.md: K = 320 54.9 -> 51.6 us; K = 640 38.5 -> 38.9, K = 1280 unchanged — there the
+// tile's MMAs out-last the epilogue anyway and the 32 KB of extra staging slots cost a pipeline stage)
+#ifndef PCDM_GEGLU_EW16_MAX_KB
+#define PCDM_GEGLU_EW16_MAX_KB 5
+#endif
 
 // Tile-shape selection from a cost model fitted to B200 measurements (tools/autotune.py, profiles/r1_autotune2.json):
 // cycles per 64-deep k-block of one CTA in steady state.  Once the issue chains were shortened the loop is bound by
@@ -943,7 +957,12 @@ static int dispatch_igemm(IGemmParams& p, int dt, int bn, const void* w, int K, 
     case 64: rc = PCDM_LAUNCH(64, 1); break;
     case 128: rc = cg == 2 ? PCDM_LAUNCH(128, 2) : PCDM_LAUNCH(128, 1); break;
     case 160: rc = cg == 2 ? PCDM_LAUNCH(160, 2) : PCDM_LAUNCH(160, 1); break;
-    case 256: rc = cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1); break;
+    case 256:
+      if (cg == 2 && p.geglu && p.kb_per_split <= PCDM_GEGLU_EW16_MAX_KB)
+        rc = dt == DT_F16 ? launch_igemm<256, DT_F16, 2, 16>(p, stream) : launch_igemm<256, DT_BF16, 2, 16>(p, stream);
+      else
+        rc = cg == 2 ? PCDM_LAUNCH(256, 2) : PCDM_LAUNCH(256, 1);
+      break;
     case 320:
       if (cg != 2 || (p.N % 320)) return set_error(PCDM_ERR_UNSUPPORTED, "igemm: the 320-wide tile needs a CTA pair (M > 128) and N % 320 == 0");
       rc = PCDM_LAUNCH(320, 2);
