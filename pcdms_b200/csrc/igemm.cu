@@ -28,6 +28,7 @@ namespace pcdm {
 
 constexpr int IG_THREADS = 384;        // warps 0-3: TMA(A) / MMA / TMEM-alloc / TMA(B); warps 4-11: epilogue
 constexpr int IG_EPI_WARPS = 8;        // EW of the kernel template: 8, or 16 for the GEGLU-only instances (640 threads)
+static_assert(IG_THREADS == (4 + IG_EPI_WARPS) * 32, "default instance: 4 role warps + 8 epilogue warps");
 constexpr int IG_SLOT_BYTES = 32 * 64; // one epilogue staging slot: 32 rows x 32 columns x 16 bit (64-byte swizzle)
 constexpr int IG_RES_SLOTS = 5;        // residual slots per epilogue warp: the chunks one warp owns in a <= 320-wide tile
 constexpr int IG_MAX_STAGES = 8;
@@ -61,7 +62,7 @@ struct IGemmParams {
   int hw;          // rows per image for rowvec indexing
   int has_res;
   int dbg;         // experiment mask (pcdm_set_gemm_debug; results are WRONG when non-zero): 1 no TMA stores, 2 no
-                   // residual, 4 no bias / rowvec, 8 epilogue body skipped, 16 no MMAs
+                   // residual, 4 no bias / rowvec, 8 epilogue body skipped, 16 no MMAs, 32 GEGLU without its arithmetic
   void* out;       // only dereferenced for fp32 output
   long long ldo;
   int geglu;
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = half; c * 64 < cols_here; c += CSTEP) {
+        for (int c = half; c * 64 < cols_here && !IG_DBG(p, 8); c += CSTEP) {
           const int n0 = n_tile0 + c * 64;
           const uint32_t slot = cnt & (uint32_t)(nbuf - 1);
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
@@ -632,14 +633,17 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
           // (Streaming the chunk in two 16 + 16 column halves with the TMEM reads one half ahead of the GELUs was
           //  measured 8 % SLOWER: profiles/r2_s3_epilogue.md.)
           uint32_t o[16];
-          if (p.silu == 1) geglu_math<DT, 1, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
+          if (IG_DBG(p, 32)) {   // experiment build: no arithmetic, the accumulators go out as they are
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = pack2<DT>(__uint_as_float(rh[2 * j]), __uint_as_float(rg[2 * j + 1]));
+          } else if (p.silu == 1) geglu_math<DT, 1, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
           else geglu_math<DT, 2, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !IG_DBG(p, 1)) {
             tma_store_2d(&p.tmOut, sl, n0 >> 1, m_warp0);
             bulk_commit();
           }

@@ -34,6 +34,10 @@ def ops():
     (256, 256, 128, 128, {}), (1000, 320, 320, 0, {"resid": True}), (4096, 1280, 1024, 256, {}),
     (516, 640, 1024, 64, {"bias": False}), (300, 2560, 320, 0, {"geglu": True}), (512, 320, 960, 160, {"split": 640}),
     (2, 1280, 320, 0, {"silu": True}), (4128, 640, 1024, 0, {"bias": False}),
+    # K <= 320 with >= 2 tiles per CTA pair: the activation-stationary instances (contiguous tile runs, resident A slab,
+    # ragged last m-tile; GEGLU additionally on the 16-epilogue-warp instance)
+    (20000, 640, 320, 0, {"resid": True}), (33000, 2560, 320, 0, {"geglu": True}), (16448, 960, 256, 0, {}),
+    (40000, 320, 64, 0, {"bias": False}), (32768, 320, 320, 0, {"resid": True, "silu": True}),
 ])
 def test_gemm(ops, dt, M, N, K, bn, kw):
     g = torch.Generator().manual_seed(M + N + K)
