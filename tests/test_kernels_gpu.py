@@ -91,6 +91,35 @@ def test_conv3x3(ops, dt, B, H, W, Cin, Cout, stride, extra):
     close(out.permute(0, 3, 1, 2), ref, dt)
 
 
+@pytest.mark.parametrize("dt", DTS)
+def test_pair_tiles_match_single_cta_tiles_bit_for_bit(ops, dt):
+    """The N = 320 convs / GEMMs of the 32x64 level at batch 16: 256 CTA-pair tiles of 256 x 160 on 74 pairs (the automatic
+    choice) against 512 single-CTA tiles of 128 x 160 (forced).  Same arithmetic per output element, so outputs AND the
+    GroupNorm statistics of the epilogue must agree bit for bit, and with the oracle.  (Written for the remainder-split
+    instance of round 2 — the last, partly filled wave's tiles cut into 96 + 64 columns — which passed it and was
+    measured not faster: profiles/r2_s3_epilogue.md.)"""
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Cin, Cout = 16, 32, 64, 64, 320
+    x = torch.randn(B, H, W, Cin, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dt)
+    b, t = torch.randn(Cout, generator=g), torch.randn(B, Cout, generator=g)
+    r = torch.randn(B, H, W, Cout, generator=g).to(dt)
+    wp = ops.pack_conv3x3_weight(w, dt).cuda()
+    args = dict(bias=b.cuda(), rowvec=t.cuda(), residual=r.cuda())
+    y, st = ops.conv3x3(x.cuda(), wp, chan_stats=True, **args)                 # automatic: pair tiles
+    y1, st1 = ops.conv3x3(x.cuda(), wp, chan_stats=True, bn=160, cta_group=1, **args)   # 512 single-CTA tiles
+    assert torch.equal(y, y1) and torch.equal(st.buf, st1.buf)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1) + t[:, :, None, None] + r.float().permute(0, 3, 1, 2)
+    close(y.permute(0, 3, 1, 2), ref, dt)
+    torch.testing.assert_close(st.buf.double().cpu(), _slab_sums(y.view(-1, Cout)), rtol=2e-5, atol=2e-4)
+    # plain GEMM with residual (ff.net.2 of the 32x64 transformer blocks: M 32768, N 320, K 1280), ragged M
+    M, N, K = 32768 - 96, 320, 256
+    a, wg, rg = torch.randn(M, K, generator=g).to(dt), (torch.randn(N, K, generator=g) / K ** 0.5).to(dt), torch.randn(M, N, generator=g).to(dt)
+    o = ops.gemm(a.cuda(), wg.cuda(), bias=b.cuda(), residual=rg.cuda())
+    assert torch.equal(o, ops.gemm(a.cuda(), wg.cuda(), bias=b.cuda(), residual=rg.cuda(), bn=160, cta_group=1))
+    close(o, a.float() @ wg.float().t() + b + rg.float(), dt)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(16, 4, 8, 1280, 1280), (2, 8, 16, 2560, 1280), (2, 4, 8, 1920, 640)])
 def test_conv3x3_split_k_matches_single_pass(ops, B, H, W, Cin, Cout):
     """Tile-starved shapes take the split-K route (fp32 partials + finishing kernel); forcing bn disables it.  Both
