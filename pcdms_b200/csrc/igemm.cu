@@ -102,6 +102,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
   return u;
 }
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
+  return f;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 u) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
@@ -137,14 +142,18 @@ __device__ __forceinline__ void ln_prefetch(const IGemmParams& p, long long m) {
 // Straight-line code: the eight iterations are independent and the compiler interleaves their MUFU / FFMA2 chains.
 template <int DT, int ACT, int NC>
 __device__ __forceinline__ void geglu_math(const uint32_t (&rh)[NC], const uint32_t (&rg)[NC], const float* __restrict__ bias,
-                                           int n0, int off, float2 rstd2, uint32_t (&o)[NC / 2]) {
-  // rh / rg: NC value / gate accumulators of chunk columns [off, off + NC); bias = [32 value | 32 gate] per chunk
+                                           int n0, int off, float2 rstd2, uint32_t (&o)[NC / 2], uint32_t bias_s = 0) {
+  // rh / rg: NC value / gate accumulators of chunk columns [off, off + NC); bias = [32 value | 32 gate] per chunk,
+  // read from the warp's staged copy in shared memory (bias_s: its 256 bytes for this chunk) when there is one
   const bool has_bias = bias != nullptr;
   const float* bp = has_bias ? bias + n0 + off : nullptr;
 #pragma unroll
   for (int j = 0; j < NC; j += 4) {
     float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
-    if (has_bias) {
+    if (has_bias && bias_s) {
+      bh = lds128f(bias_s + (uint32_t)(off + j) * 4u);
+      bg = lds128f(bias_s + (uint32_t)(32 + off + j) * 4u);
+    } else if (has_bias) {
       bh = __ldg(reinterpret_cast<const float4*>(bp + j));
       bg = __ldg(reinterpret_cast<const float4*>(bp + 32 + j));
     }
@@ -179,6 +188,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
   uint64_t* tempty = tfull + 2;
   uint64_t* res_bar = tempty + 2;                 // [EW][IG_RES_SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EW * IG_RES_SLOTS);
+  // per-warp copy of the bias values of the chunks the warp owns in the current tile (see the epilogue): [EW][512 B]
+  uint8_t* bias_smem = epi_smem + EW * p.nbuf * IG_SLOT_BYTES + 1024;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -479,6 +490,24 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
             }
           }
         }
+#ifndef PCDM_NO_BIAS_SMEM
+        // The bias values of this warp's (up to four) chunks go through a warp-private 512 B of shared memory: one
+        // coalesced 16-byte load per lane, issued BEFORE the wait for the tile's MMAs, instead of eight dependent
+        // broadcast loads per chunk between the TMEM read-out and the arithmetic.
+        const uint32_t bias_s = smem_u32(bias_smem) + (uint32_t)e * 512u;
+        const bool bias_staged = p.bias != nullptr;
+        if (bias_staged) {
+          const int c = half + (lane >> 3) * CSTEP;
+          if (c * 32 < cols_here)
+            sts128(bias_s + (uint32_t)lane * 16u,
+                   __ldg(reinterpret_cast<const uint4*>(p.bias + n_tile0 + c * 32 + (lane & 7) * 4)));
+          __syncwarp();
+        }
+#define IG_BIAS4(ci_, n0_, j_) ((bias_staged && (ci_) < 4) ? lds128f(bias_s + (uint32_t)(ci_) * 128u + (uint32_t)(j_) * 4u) \
+                                                        : __ldg(reinterpret_cast<const float4*>(p.bias + (n0_) + (j_))))
+#else
+#define IG_BIAS4(ci_, n0_, j_) __ldg(reinterpret_cast<const float4*>(p.bias + (n0_) + (j_)))
+#endif
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         int ci = 0;
@@ -503,14 +532,14 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
           if (p.ln_stats) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {   // rstd * acc + bias'[n]: the same issue slots as a plain bias add
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 b = IG_BIAS4(ci, n0, j);
               v[j / 2] = __ffma2_rn(ln_rstd2, v[j / 2], make_float2(b.x, b.y));
               v[j / 2 + 1] = __ffma2_rn(ln_rstd2, v[j / 2 + 1], make_float2(b.z, b.w));
             }
           } else if (p.bias && !IG_DBG(p, 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 b = IG_BIAS4(ci, n0, j);
               v[j / 2] = __fadd2_rn(v[j / 2], make_float2(b.x, b.y));
               v[j / 2 + 1] = __fadd2_rn(v[j / 2 + 1], make_float2(b.z, b.w));
             }
@@ -613,10 +642,22 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
           ln_rstd2 = ln_row_rstd(p, m, valid);
           ln_prefetch(p, next_tile_row(tile + tile_step));
         }
+        uint32_t gb_s = 0;   // this warp's staged bias (two 256-byte chunks at EW = 8, one at EW = 16)
+#ifndef PCDM_NO_BIAS_SMEM
+        if (p.bias) {
+          gb_s = smem_u32(bias_smem) + (uint32_t)e * 512u;
+          const int c = half + (lane >> 4) * CSTEP;
+          if (c * 64 < cols_here && (EW == 8 || lane < 16))
+            sts128(gb_s + (uint32_t)lane * 16u,
+                   __ldg(reinterpret_cast<const uint4*>(p.bias + n_tile0 + c * 64 + (lane & 15) * 4)));
+          __syncwarp();
+        }
+#endif
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        int gci = 0;
 #pragma unroll 1
-        for (int c = half; c * 64 < cols_here && !IG_DBG(p, 8); c += CSTEP) {
+        for (int c = half; c * 64 < cols_here && !IG_DBG(p, 8); c += CSTEP, ++gci) {
           const int n0 = n_tile0 + c * 64;
           const uint32_t slot = cnt & (uint32_t)(nbuf - 1);
           uint8_t* sl = slots + slot * IG_SLOT_BYTES;
@@ -636,8 +677,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) igemm_kernel(const __grid_co
           if (IG_DBG(p, 32)) {   // experiment build: no arithmetic, the accumulators go out as they are
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = pack2<DT>(__uint_as_float(rh[2 * j]), __uint_as_float(rg[2 * j + 1]));
-          } else if (p.silu == 1) geglu_math<DT, 1, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
-          else geglu_math<DT, 2, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o);
+          } else if (p.silu == 1) geglu_math<DT, 1, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o, (gb_s && gci < 2) ? gb_s + gci * 256u : 0u);
+          else geglu_math<DT, 2, 32>(rh, rg, p.bias, n0, 0, ln_rstd2, o, (gb_s && gci < 2) ? gb_s + gci * 256u : 0u);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(sl_s + sw64(lane, j), make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]));
@@ -735,7 +776,7 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
   PCDM_ENSURE_SMEM(IG_SMEM_LIMIT, igemm_kernel<BN, DT, CG, EW>);
   p.nbuf = p.has_res ? (BN > 256 ? 5 : 4) : 2;   // residual: one slot per 32-column chunk a warp owns in the tile
   p.dbg = g_tune.gemm_dbg;
-  const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + EW * p.nbuf * IG_SLOT_BYTES;
+  const int fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + EW * 512 /*bias staging*/ + EW * p.nbuf * IG_SLOT_BYTES;
   int stages = (IG_SMEM_LIMIT - fixed) / Cfg::STAGE_BYTES;
   if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
   if (stages > g_tune.max_stages) stages = g_tune.max_stages;
