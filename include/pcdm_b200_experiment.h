@@ -14,7 +14,7 @@ int pcdm_set_gemm_cta_group(int mode);  /* 0 automatic, 1 single-CTA tiles, 2 CT
 int pcdm_set_gemm_max_stages(int n);    /* cap the GEMM/conv shared-memory ring depth (2..8) */
 int pcdm_set_gemm_debug(int mask);      /* switch parts of the GEMM/conv kernel off for timing — results are WRONG while
                                          * non-zero: 1 no TMA stores, 2 no residual, 4 no bias/rowvec, 8 no epilogue body,
-                                         * 16 no MMAs */
+                                         * 16 no MMAs, 32 GEGLU epilogue without its arithmetic (1 and 8 also act on the GEGLU path) */
 int pcdm_set_skinny_gemm(int enabled);  /* 0: M <= 32 GEMMs stay on the tcgen05 tiles */
 int pcdm_set_attention_small(int on);   /* 0: Sq, Skv <= 32 attention stays on the tcgen05 kernel */
 int pcdm_set_attention_poly(int on);    /* 1: half of the softmax exp2 on the FMA pipe (measured slower) */
