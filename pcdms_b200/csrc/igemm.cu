@@ -808,7 +808,16 @@ static int launch_igemm(IGemmParams& p, cudaStream_t stream) {
 // cycles per 64-deep k-block of one CTA in steady state.  Once the issue chains were shortened the loop is bound by
 // L2 -> shared-memory delivery (~70 B/clk/SM: (128 + BN / cta_group) x 128 B per k-block) or by the MMAs (2 BN
 // cycles), which makes 160-wide tiles on CTA pairs the best shape for this UNet (every N is a multiple of 160).
-static bool g_tune_bn320() { return false; }   // measured (tools/dev_bn320.py): never faster than 160 / 256; kept for explicit bn = 320
+// The 320-wide pair tile is chosen automatically only where it was measured faster (tools/dev_bn320.py,
+// profiles/r2_bn320.md): N = 320 with K >= 5760 (the 640 -> 320 and 960 -> 320 convs of the 32x64 level: the k-loop of a
+// 160-wide tile is paced by the activation fill, 26 KB per 320 MMA cycles; the 320-wide one stages 36 KB per 640 and
+// its unhidden epilogue is amortised over >= 90 k-blocks).  Extending it to N = 640 at the 16x32 level was mixed
+// (640 -> 640 47.1 vs 50.6 us, 1280 -> 640 93.4 vs 85.4): not taken.  Everywhere else 160 / 256 win; explicit bn = 320 stays.
+#ifdef PCDM_NO_AUTO_BN320
+static bool g_tune_bn320(int, int, int) { return false; }
+#else
+static bool g_tune_bn320(int N, int num_kb, int geglu) { return N == 320 && num_kb >= 90 && !geglu; }
+#endif
 
 static int kb_cycles(int bn, int cg) {
   if (cg == 2) return bn == 128 ? 361 : (bn == 160 ? 398 : (bn == 320 ? 680 : 629));
@@ -827,7 +836,7 @@ static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int forc
       const int bn = cand[i];
       if (geglu && (bn % 64)) continue;
       if (bn == 160 && (N % 160)) continue;
-      if (bn == 320 && (cg != 2 || (N % 320) || !g_tune_bn320())) continue;
+      if (bn == 320 && (cg != 2 || (N % 320) || !g_tune_bn320(N, num_kb, geglu))) continue;
       if (cg == 2 && bn < 128) continue;
       if (planes > 1 && (N % bn)) continue;   // stacked per-plane weights: an N tile must not straddle two planes
       const long long tiles = (long long)((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn) * planes;
@@ -837,7 +846,8 @@ static void pick_tile(int M, int N, int num_kb, int geglu, int has_res, int forc
       // (the 320-wide tile's accumulator is single-buffered: its epilogue is not hidden behind the next tile's MMAs)
       const long long tile_cycles = (long long)num_kb * kb_cycles(bn, cg) + 1500 + (geglu ? 1500 : 0) + (has_res ? 300 : 0) +
                                     (cg == 2 ? 400 : 0) + (bn == 320 ? 2500 : 0);
-      const long long cost = waves * tile_cycles;
+      long long cost = waves * tile_cycles;
+      if (bn == 320) cost += cost / 12;   // ties go to the double-buffered tiles (32x64 640 -> 640: measured 162 vs 193 us)
       if (cost < best) { best = cost; *bn_out = bn; *cg_out = cg; }
     }
   }

@@ -112,6 +112,12 @@ def test_pair_tiles_match_single_cta_tiles_bit_for_bit(ops, dt):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1) + t[:, :, None, None] + r.float().permute(0, 3, 1, 2)
     close(y.permute(0, 3, 1, 2), ref, dt)
     torch.testing.assert_close(st.buf.double().cpu(), _slab_sums(y.view(-1, Cout)), rtol=2e-5, atol=2e-4)
+    # K = 5760 at N = 320 (conv1 of the 32x64 up-block resnets: 640 -> 320): the automatic choice is the 320-wide pair tile
+    x6 = torch.randn(B, H, W, 640, generator=g).to(dt).cuda()
+    w6 = (torch.randn(Cout, 9 * 640, generator=g) / (9 * 640) ** 0.5).to(dt).cuda()
+    y6, st6 = ops.conv3x3(x6, w6, bias=b.cuda(), rowvec=t.cuda(), chan_stats=True)
+    y7, st7 = ops.conv3x3(x6, w6, bias=b.cuda(), rowvec=t.cuda(), chan_stats=True, bn=160, cta_group=1)
+    assert torch.equal(y6, y7) and torch.equal(st6.buf, st7.buf)
     # plain GEMM with residual (ff.net.2 of the 32x64 transformer blocks: M 32768, N 320, K 1280), ragged M
     M, N, K = 32768 - 96, 320, 256
     a, wg, rg = torch.randn(M, K, generator=g).to(dt), (torch.randn(N, K, generator=g) / K ** 0.5).to(dt), torch.randn(M, N, generator=g).to(dt)

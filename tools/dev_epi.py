@@ -18,8 +18,9 @@ for (M, N, K, kw) in [(32768, 2560, 320, dict(geglu=True)), (8192, 5120, 640, di
     out = torch.empty(M, N // 2 if kw.get("geglu") else N, device=dev, dtype=dt)
     t = graph_us(lambda: ops.gemm(a, w, bias=b, residual=r, geglu=bool(kw.get("geglu")), out=out))
     rows.append((f"gemm M{M} N{N} K{K} {'+'.join(kw) or '-'}", t))
-for (B, H, W, Ci, Co, res) in [(16, 32, 64, 320, 320, True), (16, 16, 32, 640, 640, True), (16, 8, 16, 1280, 1280, True),
-                               (16, 4, 8, 1280, 1280, True)]:
+for (B, H, W, Ci, Co, res) in [(16, 32, 64, 320, 320, True), (16, 32, 64, 640, 320, False), (16, 32, 64, 960, 320, False),
+                               (16, 32, 64, 640, 640, False), (16, 16, 32, 640, 640, True), (16, 16, 32, 1280, 640, False), (16, 16, 32, 1920, 640, False),
+                               (16, 8, 16, 1280, 1280, True), (16, 8, 16, 2560, 1280, False), (16, 4, 8, 1280, 1280, True)]:
     x = rnd(B, H, W, Ci)
     wp = ops.pack_conv3x3_weight(torch.randn(Co, Ci, 3, 3, device=dev) * (9 * Ci) ** -0.5, dt)
     b = torch.randn(Co, device=dev)
